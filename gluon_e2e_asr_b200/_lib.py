@@ -1,0 +1,101 @@
+"""ctypes binding of libctcb.so (include/ctcb.h, include/ctcb_dlpack.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``build_ext.py``; importing the
+compute API without it fails loudly -- there is no Python or CPU fallback for the path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libctcb.so")
+
+CTCB_OK, CTCB_INVALID_VALUE, CTCB_WORKSPACE_TOO_SMALL, CTCB_EXECUTION_FAILED, CTCB_MEMOPS_FAILED, CTCB_UNSUPPORTED = range(6)
+DT_I32, DT_I64, DT_F32, DT_F64 = range(4)
+UTT_INFEASIBLE, UTT_BAD_LABEL, UTT_LEN_CLAMPED = 1, 2, 4
+LAYOUT_NTC, LABEL_TN, KEEP_FOR_BACKWARD = 1, 2, 4
+PHASE_FUSED, PHASE_FORWARD, PHASE_BACKWARD = 0 << 8, 1 << 8, 2 << 8
+
+EXPORTS = (
+    "ctcb_version", "ctcb_last_error", "ctcb_workspace_bytes", "ctcb_loss_grad", "ctcb_forward",
+    "ctcb_backward", "ctcb_loss_grad_host", "ctcb_greedy_decode", "ctcb_loss_sum_allreduce",
+    "ctcb_last_launch_count", "ctcb_last_walk_config", "ctcb_loss_grad_dlpack",
+)
+
+
+class CtcbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libctcb error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Problem(ctypes.Structure):
+    """ctcb_problem_t (include/ctcb.h)."""
+    _fields_ = [
+        ("T", ctypes.c_int32), ("B", ctypes.c_int32), ("V", ctypes.c_int32), ("Lmax", ctypes.c_int32),
+        ("blank", ctypes.c_int32), ("label_pad", ctypes.c_int32),
+        ("logits", ctypes.c_void_p), ("logits_stride_t", ctypes.c_int64), ("logits_stride_b", ctypes.c_int64),
+        ("grad", ctypes.c_void_p), ("grad_stride_t", ctypes.c_int64), ("grad_stride_b", ctypes.c_int64),
+        ("labels", ctypes.c_void_p), ("label_dtype", ctypes.c_int32),
+        ("label_stride_b", ctypes.c_int64), ("label_stride_l", ctypes.c_int64),
+        ("data_lengths", ctypes.c_void_p), ("data_lengths_dtype", ctypes.c_int32),
+        ("label_lengths", ctypes.c_void_p), ("label_lengths_dtype", ctypes.c_int32),
+        ("head_grad", ctypes.c_void_p), ("loss", ctypes.c_void_p), ("loss_sum", ctypes.c_void_p),
+        ("status", ctypes.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def load():
+    """Returns the loaded library; raises if the CUDA extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "gluon_e2e_asr_b200: %s is missing -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  There is no CPU fallback for the CTC path." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t
+    PP = ctypes.POINTER(Problem)
+    lib.ctcb_version.restype = ctypes.c_int
+    lib.ctcb_last_error.restype = ctypes.c_char_p
+    lib.ctcb_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, ctypes.POINTER(sz)]
+    lib.ctcb_loss_grad.argtypes = [PP, vp, sz, vp]
+    lib.ctcb_forward.argtypes = [PP, i32, vp, sz, vp]
+    lib.ctcb_backward.argtypes = [PP, vp, sz, vp]
+    lib.ctcb_loss_grad_host.argtypes = [PP, ctypes.c_int]
+    lib.ctcb_greedy_decode.argtypes = [vp, i64, i64, vp, i32, i32, i32, i32, i32, vp, vp, vp]
+    lib.ctcb_loss_sum_allreduce.argtypes = [vp, vp, i32, vp]
+    lib.ctcb_last_walk_config.argtypes = [ctypes.POINTER(i32), ctypes.POINTER(i32)]
+    lib.ctcb_loss_grad_dlpack.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, sz, vp]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if name != "ctcb_last_error":
+            fn.restype = ctypes.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != CTCB_OK:
+        raise CtcbError(rc, load().ctcb_last_error().decode("utf-8", "replace"))
+
+
+def workspace_bytes(T, B, V, Lmax, need_grad=True):
+    out = ctypes.c_size_t(0)
+    check(load().ctcb_workspace_bytes(T, B, V, Lmax, 1 if need_grad else 0, ctypes.byref(out)))
+    return out.value
+
+
+def last_launch_count():
+    return int(load().ctcb_last_launch_count())
+
+
+def last_walk_config():
+    p, nw = ctypes.c_int32(0), ctypes.c_int32(0)
+    load().ctcb_last_walk_config(ctypes.byref(p), ctypes.byref(nw))
+    return p.value, nw.value

@@ -1,0 +1,496 @@
+// ctcb.cu -- host side of libctcb.so: the C ABI declared in include/ctcb.h and
+// include/ctcb_dlpack.h.  Validates the problem, carves the caller's workspace, picks the
+// walker configuration and enqueues the kernels of ctcb_kernels.cuh on the caller's stream.
+// No host synchronisation, no allocation and no CPU arithmetic on the device path.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
+#include "ctcb.h"
+#include "ctcb_dlpack.h"
+#include "ctcb_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local int g_launches = 0;
+thread_local int g_walk_p = 0, g_walk_nw = 0;
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                   \
+    do {                                                                                 \
+        cudaError_t e_ = (expr);                                                         \
+        if (e_ != cudaSuccess)                                                           \
+            return fail(CTCB_EXECUTION_FAILED, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Layout {
+    size_t off_Tb, off_Lb, off_flags, off_lab, off_nxt, off_first, off_fr, off_E, off_hA, off_hB, total;
+    int Lp, W, HP;
+};
+
+Layout make_layout(int T, int B, int /*V*/, int Lmax, int need_grad) {
+    Layout l{};
+    l.Lp = (int)align_up((size_t)(Lmax > 0 ? Lmax : 1), 4);
+    l.W = (int)align_up((size_t)Lmax + 1, 4);
+    l.HP = Lmax + 1;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+    l.off_Tb = take(sizeof(int) * B);
+    l.off_Lb = take(sizeof(int) * B);
+    l.off_flags = take(sizeof(int) * B);
+    l.off_lab = take(sizeof(int) * (size_t)B * l.Lp);
+    l.off_nxt = take(sizeof(int) * (size_t)B * l.Lp);
+    l.off_first = take(sizeof(int) * (size_t)B * l.Lp);
+    l.off_fr = take(sizeof(float2) * (size_t)B * T);
+    l.off_E = take(sizeof(float) * (size_t)B * T * l.W);
+    if (need_grad) {
+        l.off_hA = take(sizeof(int4) * (size_t)B * T * l.HP);
+        l.off_hB = take(sizeof(int4) * (size_t)B * T * l.HP);
+    }
+    l.total = o;
+    return l;
+}
+
+ctcb::Workspace carve(const Layout& l, void* ws) {
+    char* base = static_cast<char*>(ws);
+    ctcb::Workspace w{};
+    w.Tb = reinterpret_cast<int*>(base + l.off_Tb);
+    w.Lb = reinterpret_cast<int*>(base + l.off_Lb);
+    w.flags = reinterpret_cast<int*>(base + l.off_flags);
+    w.lab = reinterpret_cast<int*>(base + l.off_lab);
+    w.nxt = reinterpret_cast<int*>(base + l.off_nxt);
+    w.first = reinterpret_cast<int*>(base + l.off_first);
+    w.fr = reinterpret_cast<float2*>(base + l.off_fr);
+    w.E = reinterpret_cast<float*>(base + l.off_E);
+    w.hA = reinterpret_cast<int4*>(base + l.off_hA);
+    w.hB = reinterpret_cast<int4*>(base + l.off_hB);
+    w.Lp = l.Lp; w.W = l.W; w.HP = l.HP;
+    return w;
+}
+
+// ---- walker configuration -------------------------------------------------------------
+struct WalkCfg { int P, NW; };
+
+using WalkFn = void (*)(ctcb::WalkArgs);
+struct WalkEntry { int P, NW; WalkFn fn; };
+#define WALK(P_, NW_) {P_, NW_, ctcb::k_walk<P_, NW_>}
+const WalkEntry kWalkTable[] = {
+    WALK(1, 1),  WALK(2, 1),  WALK(1, 2),  WALK(1, 4),  WALK(2, 2),  WALK(4, 1),
+    WALK(1, 8),  WALK(2, 4),  WALK(4, 2),  WALK(1, 16), WALK(2, 8),  WALK(4, 4),
+    WALK(1, 32), WALK(2, 16), WALK(4, 8),  WALK(2, 32), WALK(4, 16), WALK(4, 32),
+    WALK(8, 16), WALK(8, 32), WALK(16, 32),
+};
+#undef WALK
+
+const WalkEntry* find_walk(int P, int NW) {
+    for (const auto& e : kWalkTable) if (e.P == P && e.NW == NW) return &e;
+    return nullptr;
+}
+
+// default choice per capacity (pairs = Lmax+1); tuned on B200, see DESIGN.md section 6
+const WalkEntry* choose_walk(int pairs) {
+    const char* ep = getenv("CTCB_WALK_P");
+    const char* en = getenv("CTCB_WALK_NW");
+    if (ep && en) {
+        const WalkEntry* e = find_walk(atoi(ep), atoi(en));
+        if (e && e->P * e->NW * 32 >= pairs) return e;
+    }
+    static const WalkCfg pref[] = {{1, 1}, {1, 2}, {1, 4}, {2, 4}, {2, 8}, {4, 8}, {4, 16}, {4, 32}, {8, 32}, {16, 32}};
+    for (const auto& c : pref)
+        if (c.P * c.NW * 32 >= pairs) return find_walk(c.P, c.NW);
+    return nullptr;
+}
+
+int pick_kb(int W) {
+    if (W <= 256) return 16;
+    if (W <= 512) return 8;
+    if (W <= 1024) return 4;
+    if (W <= 2048) return 2;
+    return 1;
+}
+
+size_t walk_smem(int KB, int W, int NW) {
+    return (size_t)ctcb::kStages * KB * W * sizeof(float) + ctcb::kStages * sizeof(uint64_t) + 2 * (size_t)NW * sizeof(int2);
+}
+
+int pick_vec(const void* base, long long st_t, long long st_b, int V) {
+    auto ok = [&](int v) {
+        return V % v == 0 && st_t % v == 0 && st_b % v == 0 && (reinterpret_cast<uintptr_t>(base) % (v * sizeof(float))) == 0;
+    };
+    if (ok(4)) return 4;
+    if (ok(2)) return 2;
+    return 1;
+}
+
+int validate(const ctcb_problem_t* p) {
+    if (!p) return fail(CTCB_INVALID_VALUE, "problem is NULL");
+    if (p->T <= 0 || p->B <= 0 || p->V <= 1 || p->Lmax < 0)
+        return fail(CTCB_INVALID_VALUE, "bad shape T=%d B=%d V=%d Lmax=%d", p->T, p->B, p->V, p->Lmax);
+    if (p->blank < 0 || p->blank >= p->V) return fail(CTCB_INVALID_VALUE, "blank %d outside [0,%d)", p->blank, p->V);
+    if (!p->logits || !p->loss) return fail(CTCB_INVALID_VALUE, "logits and loss must not be NULL");
+    if (p->Lmax > 0 && !p->labels) return fail(CTCB_INVALID_VALUE, "labels is NULL");
+    auto dt_ok = [](int d) { return d >= CTCB_I32 && d <= CTCB_F64; };
+    if (!dt_ok(p->label_dtype) || (p->data_lengths && !dt_ok(p->data_lengths_dtype)) ||
+        (p->label_lengths && !dt_ok(p->label_lengths_dtype)))
+        return fail(CTCB_INVALID_VALUE, "unsupported label/length dtype");
+    if (p->Lmax + 1 > 16 * 32 * 32)
+        return fail(CTCB_UNSUPPORTED, "Lmax=%d exceeds the largest walker (16383 labels)", p->Lmax);
+    if ((long long)p->B > 65535) return fail(CTCB_UNSUPPORTED, "B=%d exceeds 65535 utterances per call", p->B);
+    return CTCB_OK;
+}
+
+ctcb::Problem to_device_problem(const ctcb_problem_t* p) {
+    ctcb::Problem d{};
+    d.T = p->T; d.B = p->B; d.V = p->V; d.Lmax = p->Lmax; d.blank = p->blank; d.label_pad = p->label_pad;
+    d.logits = p->logits; d.st_t = p->logits_stride_t; d.st_b = p->logits_stride_b;
+    d.grad = p->grad; d.gst_t = p->grad_stride_t; d.gst_b = p->grad_stride_b;
+    d.labels = p->labels; d.label_dtype = p->label_dtype; d.lst_b = p->label_stride_b; d.lst_l = p->label_stride_l;
+    d.data_len = p->data_lengths; d.data_len_dtype = p->data_lengths_dtype;
+    d.label_len = p->label_lengths; d.label_len_dtype = p->label_lengths_dtype;
+    d.head = p->head_grad; d.loss = p->loss; d.loss_sum = p->loss_sum; d.status = p->status;
+    return d;
+}
+
+bool is_device_ptr(const void* ptr) {
+    if (!ptr) return true;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ctcb_version(void) { return CTCB_VERSION; }
+const char* ctcb_last_error(void) { return g_err; }
+int ctcb_last_launch_count(void) { return g_launches; }
+int ctcb_last_walk_config(int32_t* p, int32_t* nw) {
+    if (p) *p = g_walk_p;
+    if (nw) *nw = g_walk_nw;
+    return CTCB_OK;
+}
+
+int ctcb_workspace_bytes(int32_t T, int32_t B, int32_t V, int32_t Lmax, int32_t need_grad, size_t* out) {
+    if (!out) return fail(CTCB_INVALID_VALUE, "out_bytes is NULL");
+    if (T <= 0 || B <= 0 || V <= 1 || Lmax < 0) return fail(CTCB_INVALID_VALUE, "bad shape T=%d B=%d V=%d Lmax=%d", T, B, V, Lmax);
+    *out = make_layout(T, B, V, Lmax, need_grad).total;
+    return CTCB_OK;
+}
+
+namespace {
+
+// phase bits
+enum { PH_FORWARD = 1, PH_BACKWARD = 2 };
+
+int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, void* stream_, int phases, bool keep_hist) {
+    if (int rc = validate(p)) return rc;
+    const bool need_grad = keep_hist || (phases & PH_BACKWARD);
+    if ((phases & PH_BACKWARD) && !p->grad) return fail(CTCB_INVALID_VALUE, "grad is NULL");
+    const Layout lay = make_layout(p->T, p->B, p->V, p->Lmax, need_grad);
+    if (!workspace) return fail(CTCB_INVALID_VALUE, "workspace is NULL");
+    if (workspace_bytes < lay.total)
+        return fail(CTCB_WORKSPACE_TOO_SMALL, "workspace %zu < required %zu bytes", workspace_bytes, lay.total);
+    if (reinterpret_cast<uintptr_t>(workspace) % 256) return fail(CTCB_INVALID_VALUE, "workspace must be 256-byte aligned");
+    if (!is_device_ptr(p->logits) || !is_device_ptr(p->loss) || !is_device_ptr(workspace) || !is_device_ptr(p->grad) ||
+        !is_device_ptr(p->labels))
+        return fail(CTCB_INVALID_VALUE, "logits/labels/loss/grad/workspace must be CUDA device memory (there is no CPU path)");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const ctcb::Problem dp = to_device_problem(p);
+    const ctcb::Workspace w = carve(lay, workspace);
+    static std::mutex mu;
+    const dim3 fgrid((p->T + ctcb::kFramesPerCta - 1) / ctcb::kFramesPerCta, p->B);
+
+    if (phases & PH_FORWARD) {
+        const WalkEntry* we = choose_walk(p->Lmax + 1);
+        if (!we) return fail(CTCB_UNSUPPORTED, "no walker configuration for Lmax=%d", p->Lmax);
+        g_walk_p = we->P; g_walk_nw = we->NW;
+        const int KB = pick_kb(lay.W);
+        const size_t smem = walk_smem(KB, lay.W, we->NW);
+        if (smem > 227 * 1024) return fail(CTCB_UNSUPPORTED, "emission ring needs %zu bytes of shared memory", smem);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(we->fn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        ctcb::k_prepare<<<p->B, 128, 0, stream>>>(dp, w);
+        ++g_launches;
+        switch (pick_vec(p->logits, p->logits_stride_t, p->logits_stride_b, p->V)) {
+            case 4: ctcb::k_logsoftmax_gather<4><<<fgrid, 128, 0, stream>>>(dp, w); break;
+            case 2: ctcb::k_logsoftmax_gather<2><<<fgrid, 128, 0, stream>>>(dp, w); break;
+            default: ctcb::k_logsoftmax_gather<1><<<fgrid, 128, 0, stream>>>(dp, w); break;
+        }
+        ++g_launches;
+        ctcb::WalkArgs wa{w, p->T, KB, p->loss, p->loss_sum, need_grad ? 1 : 0};
+        we->fn<<<dim3(p->B, need_grad ? 2 : 1), we->NW * 32, smem, stream>>>(wa);
+        ++g_launches;
+    }
+    if (phases & PH_BACKWARD) {
+        ctcb::GradArgs ga{dp, w};
+        const size_t gsm = 4 * (size_t)lay.Lp * sizeof(float);
+        int vec = pick_vec(p->logits, p->logits_stride_t, p->logits_stride_b, p->V);
+        const int gvec = pick_vec(p->grad, p->grad_stride_t, p->grad_stride_b, p->V);
+        if (gvec < vec) vec = gvec;
+        if (gsm > 200 * 1024) return fail(CTCB_UNSUPPORTED, "Lmax=%d too long for the gradient kernel", p->Lmax);
+        if (gsm > 48 * 1024) {
+            std::lock_guard<std::mutex> lk(mu);
+            CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(ctcb::k_grad<1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
+            CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(ctcb::k_grad<2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
+            CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(ctcb::k_grad<4>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
+        }
+        switch (vec) {
+            case 4: ctcb::k_grad<4><<<fgrid, 128, gsm, stream>>>(ga); break;
+            case 2: ctcb::k_grad<2><<<fgrid, 128, gsm, stream>>>(ga); break;
+            default: ctcb::k_grad<1><<<fgrid, 128, gsm, stream>>>(ga); break;
+        }
+        ++g_launches;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return CTCB_OK;
+}
+
+}  // namespace
+
+int ctcb_loss_grad(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, void* stream) {
+    g_launches = 0;
+    const bool need_grad = p && p->grad != nullptr;
+    return enqueue(p, workspace, workspace_bytes, stream, need_grad ? (PH_FORWARD | PH_BACKWARD) : PH_FORWARD, need_grad);
+}
+
+int ctcb_forward(const ctcb_problem_t* p, int32_t keep_for_backward, void* workspace, size_t workspace_bytes, void* stream) {
+    g_launches = 0;
+    return enqueue(p, workspace, workspace_bytes, stream, PH_FORWARD, keep_for_backward != 0);
+}
+
+int ctcb_backward(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, void* stream) {
+    g_launches = 0;
+    return enqueue(p, workspace, workspace_bytes, stream, PH_BACKWARD, true);
+}
+
+// ---- host-buffer entry ------------------------------------------------------------------
+namespace {
+struct HostScratch { void* ptr = nullptr; size_t bytes = 0; cudaStream_t stream = nullptr; };
+std::mutex g_hs_mu;
+HostScratch g_hs[64];
+size_t dt_size(int d) { return (d == CTCB_I32 || d == CTCB_F32) ? 4 : 8; }
+}  // namespace
+
+int ctcb_loss_grad_host(const ctcb_problem_t* hp, int device) {
+    if (int rc = validate(hp)) return rc;
+    if (device < 0 || device >= 64) return fail(CTCB_INVALID_VALUE, "device %d out of range", device);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev)
+        return fail(CTCB_UNSUPPORTED, "CUDA device %d not available (there is no CPU path)", device);
+    CUDA_TRY(cudaSetDevice(device));
+    const int T = hp->T, B = hp->B, V = hp->V, Lmax = hp->Lmax;
+    const bool need_grad = hp->grad != nullptr;
+    // the host entry takes compact buffers only: strides must describe TNC or NTC exactly
+    const bool tnc = hp->logits_stride_t == (long long)B * V && hp->logits_stride_b == V;
+    const bool ntc = hp->logits_stride_t == V && hp->logits_stride_b == (long long)T * V;
+    if (!tnc && !ntc) return fail(CTCB_INVALID_VALUE, "host entry needs compact TNC or NTC logits");
+    if (need_grad && (hp->grad_stride_t != hp->logits_stride_t || hp->grad_stride_b != hp->logits_stride_b))
+        return fail(CTCB_INVALID_VALUE, "host entry needs grad in the logits' layout");
+    if (Lmax > 0 && !((hp->label_stride_b == Lmax && hp->label_stride_l == 1) || (hp->label_stride_b == 1 && hp->label_stride_l == B)))
+        return fail(CTCB_INVALID_VALUE, "host entry needs compact NT or TN labels");
+
+    size_t ws_bytes = 0;
+    ctcb_workspace_bytes(T, B, V, Lmax, need_grad, &ws_bytes);
+    const size_t n_log = sizeof(float) * (size_t)T * B * V;
+    const size_t n_lab = dt_size(hp->label_dtype) * (size_t)B * (Lmax > 0 ? Lmax : 1);
+    const size_t n_dl = hp->data_lengths ? dt_size(hp->data_lengths_dtype) * (size_t)B : 0;
+    const size_t n_ll = hp->label_lengths ? dt_size(hp->label_lengths_dtype) * (size_t)B : 0;
+    const size_t n_head = hp->head_grad ? sizeof(float) * (size_t)B : 0;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+    const size_t o_ws = take(ws_bytes), o_log = take(n_log), o_grad = take(need_grad ? n_log : 0), o_lab = take(n_lab),
+                 o_dl = take(n_dl), o_ll = take(n_ll), o_head = take(n_head), o_loss = take(sizeof(float) * B),
+                 o_sum = take(sizeof(double)), o_stat = take(sizeof(int) * B);
+    std::lock_guard<std::mutex> lk(g_hs_mu);
+    HostScratch& hs = g_hs[device];
+    if (!hs.stream && cudaStreamCreateWithFlags(&hs.stream, cudaStreamNonBlocking) != cudaSuccess)
+        return fail(CTCB_MEMOPS_FAILED, "cudaStreamCreate failed");
+    if (hs.bytes < o) {
+        if (hs.ptr) cudaFree(hs.ptr);
+        hs.ptr = nullptr; hs.bytes = 0;
+        if (cudaMalloc(&hs.ptr, o) != cudaSuccess) { cudaGetLastError(); return fail(CTCB_MEMOPS_FAILED, "cudaMalloc(%zu) failed", o); }
+        hs.bytes = o;
+    }
+    char* base = static_cast<char*>(hs.ptr);
+    cudaStream_t s = hs.stream;
+    ctcb_problem_t d = *hp;
+    d.logits = reinterpret_cast<float*>(base + o_log);
+    d.grad = need_grad ? reinterpret_cast<float*>(base + o_grad) : nullptr;
+    d.labels = base + o_lab;
+    d.data_lengths = hp->data_lengths ? base + o_dl : nullptr;
+    d.label_lengths = hp->label_lengths ? base + o_ll : nullptr;
+    d.head_grad = hp->head_grad ? reinterpret_cast<float*>(base + o_head) : nullptr;
+    d.loss = reinterpret_cast<float*>(base + o_loss);
+    d.loss_sum = hp->loss_sum ? reinterpret_cast<double*>(base + o_sum) : nullptr;
+    d.status = hp->status ? reinterpret_cast<int32_t*>(base + o_stat) : nullptr;
+#define COPY_TRY(expr) do { if ((expr) != cudaSuccess) return fail(CTCB_MEMOPS_FAILED, "%s: %s", #expr, cudaGetErrorString(cudaGetLastError())); } while (0)
+    COPY_TRY(cudaMemcpyAsync(base + o_log, hp->logits, n_log, cudaMemcpyHostToDevice, s));
+    if (Lmax > 0) COPY_TRY(cudaMemcpyAsync(base + o_lab, hp->labels, n_lab, cudaMemcpyHostToDevice, s));
+    if (n_dl) COPY_TRY(cudaMemcpyAsync(base + o_dl, hp->data_lengths, n_dl, cudaMemcpyHostToDevice, s));
+    if (n_ll) COPY_TRY(cudaMemcpyAsync(base + o_ll, hp->label_lengths, n_ll, cudaMemcpyHostToDevice, s));
+    if (n_head) COPY_TRY(cudaMemcpyAsync(base + o_head, hp->head_grad, n_head, cudaMemcpyHostToDevice, s));
+    if (hp->loss_sum) COPY_TRY(cudaMemcpyAsync(base + o_sum, hp->loss_sum, sizeof(double), cudaMemcpyHostToDevice, s));
+    if (int rc = ctcb_loss_grad(&d, base + o_ws, ws_bytes, s)) return rc;
+    COPY_TRY(cudaMemcpyAsync(hp->loss, base + o_loss, sizeof(float) * B, cudaMemcpyDeviceToHost, s));
+    if (need_grad) COPY_TRY(cudaMemcpyAsync(hp->grad, base + o_grad, n_log, cudaMemcpyDeviceToHost, s));
+    if (hp->loss_sum) COPY_TRY(cudaMemcpyAsync(hp->loss_sum, base + o_sum, sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (hp->status) COPY_TRY(cudaMemcpyAsync(hp->status, base + o_stat, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
+#undef COPY_TRY
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return CTCB_OK;
+}
+
+int ctcb_greedy_decode(const float* logits, int64_t stride_t, int64_t stride_b, const void* data_lengths,
+                       int32_t data_lengths_dtype, int32_t T, int32_t B, int32_t V, int32_t blank,
+                       int32_t* out_tokens, int32_t* out_lengths, void* stream) {
+    if (!logits || !out_tokens || !out_lengths) return fail(CTCB_INVALID_VALUE, "NULL argument");
+    if (T <= 0 || B <= 0 || V <= 0) return fail(CTCB_INVALID_VALUE, "bad shape");
+    if (!is_device_ptr(logits) || !is_device_ptr(out_tokens)) return fail(CTCB_INVALID_VALUE, "buffers must be CUDA device memory");
+    const size_t smem = sizeof(int) * (size_t)T;
+    if (smem > 200 * 1024) return fail(CTCB_UNSUPPORTED, "T=%d too long for the decode kernel", T);
+    if (smem > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(ctcb::k_greedy_decode), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ctcb::k_greedy_decode<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(logits, stride_t, stride_b, data_lengths,
+                                                                                data_lengths_dtype, T, B, V, blank,
+                                                                                out_tokens, out_lengths);
+    CUDA_TRY(cudaGetLastError());
+    return CTCB_OK;
+}
+
+// ---- NCCL loss-sum allreduce (dlopen, no link-time dependency) ----------------------------
+int ctcb_loss_sum_allreduce(void* nccl_comm, double* dev_values, int32_t count, void* stream) {
+    typedef int (*allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+    static allreduce_fn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {getenv("CTCB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            if (!n) continue;
+            if (void* h = dlopen(n, RTLD_NOW | RTLD_GLOBAL)) {
+                fn = reinterpret_cast<allreduce_fn>(dlsym(h, "ncclAllReduce"));
+                if (fn) break;
+            }
+        }
+    });
+    if (!fn) return fail(CTCB_UNSUPPORTED, "ncclAllReduce could not be resolved (set CTCB_NCCL_LIB)");
+    if (!nccl_comm || !dev_values || count <= 0) return fail(CTCB_INVALID_VALUE, "bad allreduce arguments");
+    const int ncclFloat64 = 8, ncclSum = 0;
+    const int rc = fn(dev_values, dev_values, (size_t)count, ncclFloat64, ncclSum, nccl_comm, static_cast<cudaStream_t>(stream));
+    if (rc != 0) return fail(CTCB_EXECUTION_FAILED, "ncclAllReduce returned %d", rc);
+    return CTCB_OK;
+}
+
+// ---- DLPack entry ---------------------------------------------------------------------------
+namespace {
+int dl_dtype(const DLTensor& t, int* out) {
+    if (t.dtype.lanes != 1) return 1;
+    if (t.dtype.code == kDLInt && t.dtype.bits == 32) { *out = CTCB_I32; return 0; }
+    if (t.dtype.code == kDLInt && t.dtype.bits == 64) { *out = CTCB_I64; return 0; }
+    if (t.dtype.code == kDLFloat && t.dtype.bits == 32) { *out = CTCB_F32; return 0; }
+    if (t.dtype.code == kDLFloat && t.dtype.bits == 64) { *out = CTCB_F64; return 0; }
+    return 1;
+}
+inline void* dl_data(const DLTensor& t) { return static_cast<char*>(t.data) + t.byte_offset; }
+inline int64_t dl_stride(const DLTensor& t, int axis) {
+    if (t.strides) return t.strides[axis];
+    int64_t s = 1;
+    for (int i = t.ndim - 1; i > axis; --i) s *= t.shape[i];
+    return s;
+}
+bool dl_cuda(const DLTensor& t) { return t.device.device_type == kDLCUDA || t.device.device_type == kDLCUDAManaged; }
+bool dl_vec_ok(const DLManagedTensor* m, int64_t B) {
+    if (!m) return true;
+    const DLTensor& t = m->dl_tensor;
+    return dl_cuda(t) && t.ndim == 1 && t.shape[0] == B && dl_stride(t, 0) == 1;
+}
+}  // namespace
+
+int ctcb_loss_grad_dlpack(const DLManagedTensor* logits, const DLManagedTensor* labels,
+                          const DLManagedTensor* data_lengths, const DLManagedTensor* label_lengths,
+                          const DLManagedTensor* head_grad, DLManagedTensor* loss, DLManagedTensor* grad,
+                          DLManagedTensor* loss_sum, int32_t blank_last, int32_t layout_flags, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+    g_launches = 0;
+    if (!logits || !labels || !loss) return fail(CTCB_INVALID_VALUE, "logits, labels and loss are required");
+    const DLTensor& x = logits->dl_tensor;
+    const DLTensor& y = labels->dl_tensor;
+    if (!dl_cuda(x) || !dl_cuda(y) || !dl_cuda(loss->dl_tensor))
+        return fail(CTCB_INVALID_VALUE, "tensors must live on a CUDA device (there is no CPU path)");
+    if (x.ndim != 3 || x.dtype.code != kDLFloat || x.dtype.bits != 32 || x.dtype.lanes != 1)
+        return fail(CTCB_INVALID_VALUE, "logits must be a 3-d float32 tensor");
+    if (dl_stride(x, 2) != 1 && x.shape[2] != 1) return fail(CTCB_INVALID_VALUE, "logits need unit stride on the vocabulary axis");
+    if (y.ndim != 2) return fail(CTCB_INVALID_VALUE, "labels must be 2-d");
+    const bool ntc = (layout_flags & CTCB_LAYOUT_NTC) != 0, tn = (layout_flags & CTCB_LABEL_TN) != 0;
+    ctcb_problem_t p{};
+    const int ta = ntc ? 1 : 0, ba = ntc ? 0 : 1;
+    p.T = (int32_t)x.shape[ta]; p.B = (int32_t)x.shape[ba]; p.V = (int32_t)x.shape[2];
+    p.logits = static_cast<const float*>(dl_data(x));
+    p.logits_stride_t = dl_stride(x, ta); p.logits_stride_b = dl_stride(x, ba);
+    const int lb = tn ? 1 : 0, ll = tn ? 0 : 1;
+    if (y.shape[lb] != p.B) return fail(CTCB_INVALID_VALUE, "labels batch %lld != logits batch %d", (long long)y.shape[lb], p.B);
+    p.Lmax = (int32_t)y.shape[ll];
+    p.labels = dl_data(y);
+    if (dl_dtype(y, &p.label_dtype)) return fail(CTCB_INVALID_VALUE, "labels must be int32/int64/float32/float64");
+    p.label_stride_b = dl_stride(y, lb); p.label_stride_l = dl_stride(y, ll);
+    p.blank = blank_last ? p.V - 1 : 0;
+    p.label_pad = blank_last ? -1 : 0;
+    if (!dl_vec_ok(data_lengths, p.B) || !dl_vec_ok(label_lengths, p.B) || !dl_vec_ok(head_grad, p.B) || !dl_vec_ok(loss, p.B))
+        return fail(CTCB_INVALID_VALUE, "length/head/loss vectors must be contiguous CUDA (B,) tensors");
+    if (data_lengths) {
+        p.data_lengths = dl_data(data_lengths->dl_tensor);
+        if (dl_dtype(data_lengths->dl_tensor, &p.data_lengths_dtype)) return fail(CTCB_INVALID_VALUE, "bad data_lengths dtype");
+    }
+    if (label_lengths) {
+        p.label_lengths = dl_data(label_lengths->dl_tensor);
+        if (dl_dtype(label_lengths->dl_tensor, &p.label_lengths_dtype)) return fail(CTCB_INVALID_VALUE, "bad label_lengths dtype");
+    }
+    if (head_grad) {
+        const DLTensor& h = head_grad->dl_tensor;
+        if (h.dtype.code != kDLFloat || h.dtype.bits != 32) return fail(CTCB_INVALID_VALUE, "head_grad must be float32");
+        p.head_grad = static_cast<const float*>(dl_data(h));
+    }
+    {
+        const DLTensor& l = loss->dl_tensor;
+        if (l.dtype.code != kDLFloat || l.dtype.bits != 32) return fail(CTCB_INVALID_VALUE, "loss must be float32");
+        p.loss = static_cast<float*>(dl_data(l));
+    }
+    if (grad) {
+        const DLTensor& g = grad->dl_tensor;
+        if (!dl_cuda(g) || g.ndim != 3 || g.dtype.code != kDLFloat || g.dtype.bits != 32)
+            return fail(CTCB_INVALID_VALUE, "grad must be a 3-d float32 CUDA tensor");
+        for (int i = 0; i < 3; ++i)
+            if (g.shape[i] != x.shape[i]) return fail(CTCB_INVALID_VALUE, "grad shape differs from logits");
+        if (dl_stride(g, 2) != 1 && g.shape[2] != 1) return fail(CTCB_INVALID_VALUE, "grad needs unit stride on the vocabulary axis");
+        p.grad = static_cast<float*>(dl_data(g));
+        p.grad_stride_t = dl_stride(g, ta); p.grad_stride_b = dl_stride(g, ba);
+    }
+    if (loss_sum) {
+        const DLTensor& s = loss_sum->dl_tensor;
+        if (!dl_cuda(s) || s.dtype.code != kDLFloat || s.dtype.bits != 64) return fail(CTCB_INVALID_VALUE, "loss_sum must be a float64 CUDA scalar");
+        p.loss_sum = static_cast<double*>(dl_data(s));
+    }
+    const int phase = (layout_flags >> 8) & 3;   // 0: fused, 1: forward (keep history), 2: backward
+    if (phase == 1) return enqueue(&p, workspace, workspace_bytes, stream, PH_FORWARD, (layout_flags & CTCB_KEEP_FOR_BACKWARD) != 0);
+    if (phase == 2) return enqueue(&p, workspace, workspace_bytes, stream, PH_BACKWARD, true);
+    return enqueue(&p, workspace, workspace_bytes, stream, p.grad ? (PH_FORWARD | PH_BACKWARD) : PH_FORWARD, p.grad != nullptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,262 @@
+"""The raw operator surface of the reference's CTC path on torch CUDA tensors.
+
+``ctc_loss`` mirrors ``mx.nd.contrib.ctc_loss`` exactly as the reference calls it at
+/root/reference/scripts/swbd/loss.py:134-139 (same argument names, meaning and defaults;
+alias ``CTCLoss`` like upstream).  torch is only plumbing here: device memory, the current
+stream and autograd bookkeeping.  All arithmetic happens in libctcb.so's sm_100a kernels,
+reached through ctypes with either DLPack structs (default, ``handoff='dlpack'``) or raw
+pointers (``handoff='pointer'``); without the built library or without a CUDA tensor the
+call raises -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+from torch.utils import dlpack as _dlpack
+
+from . import _lib
+
+__all__ = ["ctc_loss", "CTCLoss", "ctc_loss_and_grad", "greedy_decode", "workspace_bytes"]
+
+_DT = {torch.int32: _lib.DT_I32, torch.int64: _lib.DT_I64, torch.float32: _lib.DT_F32, torch.float64: _lib.DT_F64}
+_HANDOFF = os.environ.get("CTCB_HANDOFF", "dlpack")
+
+_PyCapsule_GetPointer = ctypes.pythonapi.PyCapsule_GetPointer
+_PyCapsule_GetPointer.restype = ctypes.c_void_p
+_PyCapsule_GetPointer.argtypes = [ctypes.py_object, ctypes.c_char_p]
+
+
+def workspace_bytes(T, B, V, Lmax, need_grad=True):
+    return _lib.workspace_bytes(T, B, V, Lmax, need_grad)
+
+
+def _as_index_tensor(x, device, name):
+    """labels / lengths: any float or int dtype (the reference delivers float32,
+    reader_kaldi_io.py:33-35, batchify.py:78-82); other dtypes are cast to float32/int64."""
+    if x is None:
+        return None
+    if not isinstance(x, torch.Tensor):
+        x = torch.as_tensor(x)
+    if x.device != device:
+        raise ValueError("%s is on %s but data is on %s" % (name, x.device, device))
+    if x.dtype not in _DT:
+        x = x.to(torch.float32 if x.dtype.is_floating_point else torch.int64)
+    return x
+
+
+def _check_data(data):
+    if not isinstance(data, torch.Tensor):
+        raise TypeError("data must be a torch.Tensor")
+    if not data.is_cuda:
+        raise RuntimeError("gluon_e2e_asr_b200.ctc_loss has no CPU path: data must be a CUDA tensor")
+    if data.dim() != 3:
+        raise ValueError("data must be 3-d, got shape %s" % (tuple(data.shape),))
+    if data.dtype != torch.float32:
+        raise TypeError("data must be float32 (the reference's logits dtype), got %s" % data.dtype)
+    if data.shape[2] > 1 and data.stride(2) != 1:
+        data = data.contiguous()
+    return data
+
+
+class _Call:
+    """One operator call, prepared once and handed to the library through either hand-off."""
+
+    def __init__(self, data, label, data_lengths, label_lengths, blank_last, ntc, tn):
+        self.data = data
+        self.ntc, self.tn, self.blank_last = ntc, tn, blank_last
+        dev = data.device
+        self.label = _as_index_tensor(label, dev, "label")
+        if self.label.dim() != 2:
+            raise ValueError("label must be 2-d")
+        self.data_lengths = _as_index_tensor(data_lengths, dev, "data_lengths")
+        self.label_lengths = _as_index_tensor(label_lengths, dev, "label_lengths")
+        ta, ba = (1, 0) if ntc else (0, 1)
+        self.T, self.B, self.V = data.shape[ta], data.shape[ba], data.shape[2]
+        lb, ll = (1, 0) if tn else (0, 1)
+        if self.label.shape[lb] != self.B:
+            raise ValueError("label batch %d != data batch %d" % (self.label.shape[lb], self.B))
+        self.Lmax = self.label.shape[ll]
+        for n, v in (("data_lengths", self.data_lengths), ("label_lengths", self.label_lengths)):
+            if v is not None:
+                if v.dim() != 1 or v.shape[0] != self.B:
+                    raise ValueError("%s must have shape (%d,)" % (n, self.B))
+        if self.data_lengths is not None:
+            self.data_lengths = self.data_lengths.contiguous()
+        if self.label_lengths is not None:
+            self.label_lengths = self.label_lengths.contiguous()
+        self._axes = (ta, ba, lb, ll)
+
+    def flags(self):
+        return (_lib.LAYOUT_NTC if self.ntc else 0) | (_lib.LABEL_TN if self.tn else 0)
+
+    def problem(self, loss, grad=None, head=None, loss_sum=None, status=None):
+        ta, ba, lb, ll = self._axes
+        p = _lib.Problem()
+        p.T, p.B, p.V, p.Lmax = self.T, self.B, self.V, self.Lmax
+        p.blank = self.V - 1 if self.blank_last else 0
+        p.label_pad = -1 if self.blank_last else 0
+        d = self.data
+        p.logits, p.logits_stride_t, p.logits_stride_b = d.data_ptr(), d.stride(ta), d.stride(ba)
+        if grad is not None:
+            p.grad, p.grad_stride_t, p.grad_stride_b = grad.data_ptr(), grad.stride(ta), grad.stride(ba)
+        lab = self.label
+        p.labels, p.label_dtype = lab.data_ptr(), _DT[lab.dtype]
+        p.label_stride_b, p.label_stride_l = lab.stride(lb), lab.stride(ll)
+        if self.data_lengths is not None:
+            p.data_lengths, p.data_lengths_dtype = self.data_lengths.data_ptr(), _DT[self.data_lengths.dtype]
+        if self.label_lengths is not None:
+            p.label_lengths, p.label_lengths_dtype = self.label_lengths.data_ptr(), _DT[self.label_lengths.dtype]
+        if head is not None:
+            p.head_grad = head.data_ptr()
+        p.loss = loss.data_ptr()
+        if loss_sum is not None:
+            p.loss_sum = loss_sum.data_ptr()
+        if status is not None:
+            p.status = status.data_ptr()
+        return p
+
+    def run(self, phase, ws, loss, grad=None, head=None, loss_sum=None, status=None, keep=False, handoff=None):
+        lib = _lib.load()
+        stream = torch.cuda.current_stream(self.data.device).cuda_stream
+        handoff = handoff or _HANDOFF
+        with torch.cuda.device(self.data.device):
+            if handoff == "dlpack" and status is None:
+                caps = []
+
+                def cap(t):
+                    if t is None:
+                        return None
+                    c = _dlpack.to_dlpack(t)
+                    caps.append(c)               # keeps the DLManagedTensor alive for the call
+                    return _PyCapsule_GetPointer(c, b"dltensor")
+                flags = self.flags() | phase | (_lib.KEEP_FOR_BACKWARD if keep else 0)
+                rc = lib.ctcb_loss_grad_dlpack(cap(self.data), cap(self.label), cap(self.data_lengths),
+                                               cap(self.label_lengths), cap(head), cap(loss), cap(grad),
+                                               cap(loss_sum), 1 if self.blank_last else 0, flags,
+                                               ws.data_ptr(), ws.numel(), stream)
+                del caps
+            else:
+                p = self.problem(loss, grad, head, loss_sum, status)
+                if phase == _lib.PHASE_FORWARD:
+                    rc = lib.ctcb_forward(ctypes.byref(p), 1 if keep else 0, ws.data_ptr(), ws.numel(), stream)
+                elif phase == _lib.PHASE_BACKWARD:
+                    rc = lib.ctcb_backward(ctypes.byref(p), ws.data_ptr(), ws.numel(), stream)
+                else:
+                    rc = lib.ctcb_loss_grad(ctypes.byref(p), ws.data_ptr(), ws.numel(), stream)
+        _lib.check(rc)
+
+
+def _alloc_ws(call, need_grad):
+    n = _lib.workspace_bytes(call.T, call.B, call.V, call.Lmax, need_grad)
+    return torch.empty((n,), dtype=torch.uint8, device=call.data.device)
+
+
+class _CtcLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, data, label, data_lengths, label_lengths, blank_last, ntc, tn):
+        call = _Call(data, label, data_lengths, label_lengths, blank_last, ntc, tn)
+        need = ctx.needs_input_grad[0]
+        ws = _alloc_ws(call, need)
+        loss = torch.empty((call.B,), dtype=torch.float32, device=data.device)
+        call.run(_lib.PHASE_FORWARD, ws, loss, keep=need)
+        ctx.call, ctx.ws = call, ws
+        return loss
+
+    @staticmethod
+    def backward(ctx, head):
+        call, ws = ctx.call, ctx.ws
+        if ws is None:
+            raise RuntimeError("ctc_loss: backward called twice (the workspace is released after the first)")
+        head = head.to(torch.float32).contiguous()
+        grad = torch.empty_like(call.data)          # same layout as the logits: no swapaxes backward
+        loss_scratch = torch.empty((call.B,), dtype=torch.float32, device=head.device)
+        call.run(_lib.PHASE_BACKWARD, ws, loss_scratch, grad=grad, head=head)
+        ctx.ws = None
+        return grad, None, None, None, None, None, None
+
+
+def _blank_last(blank_label):
+    if blank_label not in ("first", "last"):
+        raise ValueError("blank_label must be 'first' or 'last', got %r" % (blank_label,))
+    return blank_label == "last"
+
+
+def ctc_loss(data, label, data_lengths=None, label_lengths=None, use_data_lengths=False,
+             use_label_lengths=False, blank_label="first"):
+    """``mx.nd.contrib.ctc_loss`` as called at scripts/swbd/loss.py:134-139.
+
+    data (T, B, V) float32 CUDA logits (softmax is inside); label (B, Lmax) any numeric dtype,
+    truncated to int; lengths (B,) used only when the matching ``use_*`` flag is set
+    (otherwise T, resp. the first padding value: 0 for blank_label='first', -1 for 'last').
+    Returns the per-utterance negative log-likelihood (B,); differentiable w.r.t. ``data``.
+    """
+    data = _check_data(data)
+    if use_data_lengths and data_lengths is None:
+        raise ValueError("use_data_lengths=True needs data_lengths")
+    if use_label_lengths and label_lengths is None:
+        raise ValueError("use_label_lengths=True needs label_lengths")
+    return _CtcLossFn.apply(data, label, data_lengths if use_data_lengths else None,
+                            label_lengths if use_label_lengths else None,
+                            _blank_last(blank_label), False, False)
+
+
+CTCLoss = ctc_loss   # upstream alias: mx.nd.contrib.CTCLoss
+
+
+def _ctc_loss_layout(pred, label, pred_lengths, label_lengths, blank_label, layout, label_layout):
+    pred = _check_data(pred)
+    return _CtcLossFn.apply(pred, label, pred_lengths, label_lengths, _blank_last(blank_label),
+                            layout == "NTC", label_layout == "TN")
+
+
+_ws_cache = {}
+
+
+def ctc_loss_and_grad(pred, label, pred_lengths=None, label_lengths=None, head_grad=None,
+                      blank_label="first", layout="NTC", label_layout="NT", loss_sum=None,
+                      status=None, out_loss=None, out_grad=None, handoff=None):
+    """Fused forward+backward (one ``ctcb_loss_grad`` call): returns (loss (B,), grad like pred).
+
+    ``head_grad`` (B,) is the upstream gradient of each loss (``1/B`` for the reference's
+    ``.mean().backward()``, train_ctc_ce.py:363-366); ``loss_sum`` an optional float64 device
+    scalar accumulated in place.  The workspace is cached per (device, stream, shape).
+    """
+    pred = _check_data(pred)
+    call = _Call(pred, label, pred_lengths, label_lengths, _blank_last(blank_label),
+                 layout == "NTC", label_layout == "TN")
+    dev = pred.device
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream, call.T, call.B, call.V, call.Lmax)
+    ws = _ws_cache.get(key)
+    if ws is None:
+        ws = _ws_cache[key] = _alloc_ws(call, True)
+    loss = out_loss if out_loss is not None else torch.empty((call.B,), dtype=torch.float32, device=dev)
+    grad = out_grad if out_grad is not None else torch.empty_like(pred)
+    if head_grad is not None:
+        head_grad = head_grad.to(torch.float32).contiguous()
+    call.run(_lib.PHASE_FUSED, ws, loss, grad=grad, head=head_grad, loss_sum=loss_sum, status=status,
+             handoff=handoff)
+    return loss, grad
+
+
+def greedy_decode(pred, pred_lengths=None, blank=0, layout="NTC"):
+    """Greedy CTC decode of train_ctc_ce.py:149-160: argmax over V, collapse repeats, drop
+    blank.  Returns (tokens (B,T) int32 -- prefix valid, lengths (B,) int32) on pred's device."""
+    pred = _check_data(pred)
+    ta, ba = (1, 0) if layout == "NTC" else (0, 1)
+    T, B, V = pred.shape[ta], pred.shape[ba], pred.shape[2]
+    pl = _as_index_tensor(pred_lengths, pred.device, "pred_lengths")
+    if pl is not None:
+        pl = pl.contiguous()
+    toks = torch.zeros((B, T), dtype=torch.int32, device=pred.device)
+    lens = torch.empty((B,), dtype=torch.int32, device=pred.device)
+    lib = _lib.load()
+    with torch.cuda.device(pred.device):
+        rc = lib.ctcb_greedy_decode(pred.data_ptr(), pred.stride(ta), pred.stride(ba),
+                                    pl.data_ptr() if pl is not None else None,
+                                    _DT[pl.dtype] if pl is not None else 0, T, B, V, blank,
+                                    toks.data_ptr(), lens.data_ptr(),
+                                    torch.cuda.current_stream(pred.device).cuda_stream)
+    _lib.check(rc)
+    return toks, lens

@@ -1,0 +1,139 @@
+/* ctcb.h -- C ABI of libctcb.so, the B200 (sm_100a) CTC training-loss path.
+ *
+ * This is the drop-in boundary for ONE path of Hex-Lee/gluon-e2e-asr: the CTC loss
+ * forward+backward that scripts/swbd/train_ctc_ce.py:143 and :363 reach through
+ * scripts/swbd/loss.py:121-139 (`CtcLoss.hybrid_forward`) ->
+ * `mx.nd.contrib.ctc_loss(data, label, data_lengths, label_lengths, use_data_lengths,
+ * use_label_lengths, blank_label)`  (loss.py:134-139).  Every entry point below names the
+ * reference interface it replaces.  The library has no Python, torch or MXNet types in
+ * its signatures: plain pointers, sizes, strides and (optionally) DLPack structs.
+ *
+ * Conventions
+ *   - return 0 (CTCB_OK) on success, a ctcb_status_t otherwise; the message is in
+ *     ctcb_last_error() (thread-local).  No exception, abort or host sync crosses the ABI.
+ *   - all device entry points are ASYNCHRONOUS: they enqueue on `stream` (a cudaStream_t
+ *     passed as void*; NULL = the legacy default stream) and return.  Labels and lengths
+ *     are read on the device -- unlike the reference operator there is no D2H copy of
+ *     labels/lengths and no `.asscalar()` (train_ctc_ce.py:367-368).
+ *   - the caller owns every buffer including the workspace; the library borrows them for
+ *     the duration of the enqueued work.
+ *   - there is no CPU fallback: a missing CUDA device or non-device pointer is an error.
+ */
+#ifndef CTCB_H_
+#define CTCB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTCB_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+    CTCB_OK = 0,
+    CTCB_INVALID_VALUE = 1,       /* bad dtype / device / shape / stride / alignment / NULL */
+    CTCB_WORKSPACE_TOO_SMALL = 2,
+    CTCB_EXECUTION_FAILED = 3,    /* a CUDA launch or runtime error */
+    CTCB_MEMOPS_FAILED = 4,       /* allocation or copy failed (host-buffer entry only) */
+    CTCB_UNSUPPORTED = 5          /* e.g. no sm_100 device, NCCL not loadable */
+} ctcb_status_t;
+
+/* element types accepted for labels and lengths: the reference's data pipeline delivers
+ * float32 for all three (reader_kaldi_io.py:33-35, gluonE2EASR/data/batchify.py:78-82);
+ * values are truncated toward zero like the operator's own cast. */
+typedef enum { CTCB_I32 = 0, CTCB_I64 = 1, CTCB_F32 = 2, CTCB_F64 = 3 } ctcb_dtype_t;
+
+/* per-utterance status bits written to ctcb_problem_t.status (optional) */
+#define CTCB_UTT_INFEASIBLE   1  /* L + repeats > T (or T == 0): loss 0, grad 0 */
+#define CTCB_UTT_BAD_LABEL    2  /* a label was < 0, >= V or == blank: clamped / treated as is */
+#define CTCB_UTT_LEN_CLAMPED  4  /* data_length > T or label_length > Lmax: clamped */
+
+/* One CTC problem = one call of the reference operator (loss.py:134-139).
+ * All pointers are DEVICE pointers for ctcb_loss_grad(), HOST pointers for
+ * ctcb_loss_grad_host().  Strides are in ELEMENTS; the vocabulary axis of logits/grad has
+ * stride 1.  layout 'TNC' (the operator's): stride_t = B*V, stride_b = V;
+ * layout 'NTC' (the model's, model.py:421-424): stride_t = V, stride_b = T*V -- the
+ * reference's materialising swapaxes (loss.py:123-124) and its backward are not needed. */
+typedef struct ctcb_problem {
+    int32_t T, B, V, Lmax;          /* Lmax = label row length (may be 0) */
+    int32_t blank;                  /* 0 for blank_label='first' (loss.py:139), V-1 for 'last' */
+    int32_t label_pad;              /* padding value that ends a label row when label_lengths
+                                       is NULL: 0 for 'first', -1 for 'last' (row a3) */
+    const float* logits;            /* unnormalised activations, fp32 */
+    int64_t logits_stride_t, logits_stride_b;
+    float* grad;                    /* d(sum_b head[b]*loss[b])/d logits; NULL = forward only */
+    int64_t grad_stride_t, grad_stride_b;
+    const void* labels;             /* (B, Lmax), label_dtype */
+    int32_t label_dtype;            /* ctcb_dtype_t */
+    int64_t label_stride_b, label_stride_l; /* 'NT': (Lmax, 1); 'TN' (loss.py:125-126): (1, B) */
+    const void* data_lengths;       /* (B,) or NULL (= T; use_data_lengths=False) */
+    int32_t data_lengths_dtype;
+    const void* label_lengths;      /* (B,) or NULL (= first label_pad; use_label_lengths=False) */
+    int32_t label_lengths_dtype;
+    const float* head_grad;         /* (B,) upstream gradient of each loss, NULL = 1 */
+    float* loss;                    /* (B,) negative log-likelihood per utterance */
+    double* loss_sum;               /* optional device scalar: += sum_b loss[b] (feeds the
+                                       loss-sum allreduce, replaces train_ctc_ce.py:367-368) */
+    int32_t* status;                /* optional (B,) CTCB_UTT_* bits */
+} ctcb_problem_t;
+
+/* library identity; replaces nothing (sanity check for the binding) */
+int ctcb_version(void);
+const char* ctcb_last_error(void);
+
+/* Workspace the caller must provide for a (T,B,V,Lmax) problem.  need_grad=0 sizes the
+ * forward-only (evaluation, train_ctc_ce.py:143) path.  Precedent: warp-ctc's
+ * get_workspace_size(). */
+int ctcb_workspace_bytes(int32_t T, int32_t B, int32_t V, int32_t Lmax, int32_t need_grad,
+                         size_t* out_bytes);
+
+/* The operator: loss (and gradient when p->grad != NULL) of one batch, device buffers.
+ * Replaces mx.nd.contrib.ctc_loss forward + backward (loss.py:134-139; SURVEY section 8
+ * rows a3-a8).  Workspace must be 256-byte aligned device memory. */
+int ctcb_loss_grad(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
+/* The same work split the way an autograd engine calls it (MXNet's operator stores its
+ * gradient in Forward and scales it in Backward; here Forward keeps the
+ * alpha/beta history in the workspace and Backward writes head_grad * G once):
+ *   ctcb_forward   loss only (p->grad, p->head_grad ignored).  keep_for_backward != 0 also
+ *                  runs the beta walker and keeps the history; the workspace must then be
+ *                  sized with need_grad=1 and left untouched until ctcb_backward has run.
+ *   ctcb_backward  gradient from a workspace filled by ctcb_forward(keep_for_backward=1) of
+ *                  the SAME problem; reads p->head_grad, writes p->grad. */
+int ctcb_forward(const ctcb_problem_t* p, int32_t keep_for_backward, void* workspace,
+                 size_t workspace_bytes, void* stream);
+int ctcb_backward(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes,
+                  void* stream);
+
+/* Same operator with HOST buffers (what a `ctx=mx.cpu()` caller of the reference holds):
+ * copies inputs host->device, runs ctcb_loss_grad, copies loss (and grad) back and
+ * synchronises.  Device scratch is cached per device and grown on demand.  Used by
+ * bench.py's end-to-end leg. */
+int ctcb_loss_grad_host(const ctcb_problem_t* p, int device);
+
+/* Greedy CTC decode of train_ctc_ce.py:149-160 / decode_ctc.py:123-143 (next-row scope,
+ * SURVEY 8f rank 2): per utterance argmax over V for t < length, collapse repeats, drop
+ * `blank`.  out_tokens (B, T) int32 (prefix valid), out_lengths (B,) int32.  Device buffers. */
+int ctcb_greedy_decode(const float* logits, int64_t stride_t, int64_t stride_b,
+                       const void* data_lengths, int32_t data_lengths_dtype,
+                       int32_t T, int32_t B, int32_t V, int32_t blank,
+                       int32_t* out_tokens, int32_t* out_lengths, void* stream);
+
+/* Sum of `count` doubles across the ranks of an NCCL communicator, in place, on `stream`
+ * (ncclAllReduce, ncclSum).  NCCL is resolved with dlopen at first use, so libctcb.so has
+ * no link-time NCCL dependency.  Replaces the host-side `+=` of `.asscalar()` values
+ * (train_ctc_ce.py:367-368). */
+int ctcb_loss_sum_allreduce(void* nccl_comm, double* dev_values, int32_t count, void* stream);
+
+/* Introspection for tests/bench: number of kernel launches the last ctcb_loss_grad on this
+ * thread enqueued, and the walker configuration it chose. */
+int ctcb_last_launch_count(void);
+int ctcb_last_walk_config(int32_t* pairs_per_lane, int32_t* warps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTCB_H_ */

@@ -1,0 +1,278 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the fp64 oracle, the
+committed golden vectors and size-independent properties.  Bar (BASELINE.json north_star):
+per-utterance loss and logit gradient within rtol 1e-4 / atol 1e-5 of the oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle import ctc_oracle as O
+from tests.synth import CONFIGS, make_batch
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-4, 1e-5
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _to(dev, d, int_labels=False):
+    out = {k: torch.tensor(v, device=dev) for k, v in d.items()}
+    if int_labels:
+        out["label"] = out["label"].to(torch.int32)
+    return out
+
+
+def _run_block(dev, d, layout="NTC", label_layout="NT", blank_label="first", head=None, lengths=True):
+    from gluon_e2e_asr_b200 import CtcLoss
+    t = _to(dev, d)
+    pred = t["pred"] if layout == "NTC" else t["pred"].transpose(0, 1).contiguous()
+    pred.requires_grad_(True)
+    lab = t["label"] if label_layout == "NT" else t["label"].t().contiguous()
+    blk = CtcLoss(layout=layout, label_layout=label_layout, blank_label=blank_label)
+    loss = blk(pred, lab, t["pred_lengths"] if lengths else None, t["label_lengths"] if lengths else None)
+    h = torch.ones_like(loss) if head is None else torch.tensor(head, device=dev, dtype=torch.float32)
+    (loss * h).sum().backward()
+    g = pred.grad
+    if layout == "TNC":
+        g = g.transpose(0, 1)
+    return loss.detach().cpu().numpy(), g.cpu().numpy()
+
+
+def _oracle(d, blank_label="first", head=None, lengths=True):
+    o = O.CtcLossOracle("NTC", "NT", blank_label)
+    return o(d["pred"], d["label"], d["pred_lengths"] if lengths else None,
+             d["label_lengths"] if lengths else None, head_grad=head)
+
+
+def _check(loss, grad, lo, go, name=""):
+    np.testing.assert_allclose(loss, lo, rtol=RTOL, atol=ATOL, err_msg=name + " loss")
+    np.testing.assert_allclose(grad, go, rtol=RTOL, atol=ATOL, err_msg=name + " grad")
+
+
+def test_kats_through_the_block(dev, golden_dir):
+    from gluon_e2e_asr_b200 import CtcLoss
+    with open(os.path.join(golden_dir, "kat.json")) as f:
+        kats = json.load(f)
+    for k in kats:
+        data = torch.tensor(np.array(k["data"], np.float32), device=dev)
+        lab = torch.tensor(np.array(k["label"], np.float32), device=dev)
+        blk = CtcLoss(layout=k["layout"], label_layout="NT", blank_label=k["blank_label"])
+        loss = blk(data, lab).cpu().numpy()
+        np.testing.assert_allclose(loss, k["expect"], rtol=max(k["rtol"], 2e-6), err_msg=k["name"])
+        # int32 labels give the same answer (upstream runs both)
+        loss_i = blk(data, lab.to(torch.int32)).cpu().numpy()
+        np.testing.assert_array_equal(loss, loss_i)
+
+
+def test_raw_operator_surface(dev, golden_dir):
+    """ctc_loss(data TNC, label, data_lengths, label_lengths, use_*, blank_label) -- loss.py:134-139."""
+    from gluon_e2e_asr_b200 import CTCLoss, ctc_loss
+    assert CTCLoss is ctc_loss
+    d = make_batch(5, 37, 9, 6, seed=11)
+    t = _to(dev, d)
+    data = t["pred"].transpose(0, 1).contiguous().requires_grad_(True)
+    loss = ctc_loss(data, t["label"], t["pred_lengths"], t["label_lengths"], True, True, "first")
+    loss.sum().backward()
+    lo, go, ok = _oracle(d)
+    assert ok.all()
+    _check(loss.detach().cpu().numpy(), data.grad.transpose(0, 1).cpu().numpy(), lo, go, "raw op")
+    # lengths passed but flags False -> ignored: T frames, labels end at the first 0
+    loss2 = ctc_loss(data.detach(), t["label"], t["pred_lengths"], t["label_lengths"]).cpu().numpy()
+    lo2, _, _ = _oracle(d, lengths=False)
+    np.testing.assert_allclose(loss2, lo2, rtol=RTOL, atol=ATOL)
+    with pytest.raises(ValueError):
+        ctc_loss(data.detach(), t["label"], None, None, True, False)
+    with pytest.raises(RuntimeError):
+        ctc_loss(data.detach().cpu(), t["label"].cpu())
+
+
+def test_torch_fp64_fixtures(dev, golden_dir):
+    from gluon_e2e_asr_b200 import ctc_loss_and_grad
+    z = np.load(os.path.join(golden_dir, "torch_fp64.npz"))
+    for name in sorted({k.split("/")[0] for k in z.files}):
+        c = {k.split("/")[1]: z[k] for k in z.files if k.startswith(name + "/")}
+        blank_label = "first" if int(c["blank"]) == 0 else "last"
+        data = torch.tensor(c["data"], device=dev)                        # TNC
+        loss, grad = ctc_loss_and_grad(data, torch.tensor(c["label"], device=dev),
+                                       torch.tensor(c["T_b"], device=dev), torch.tensor(c["L_b"], device=dev),
+                                       head_grad=torch.tensor(c["head"], device=dev, dtype=torch.float32),
+                                       blank_label=blank_label, layout="TNC")
+        _check(loss.cpu().numpy(), grad.cpu().numpy(), c["loss"], c["grad"], name)
+
+
+@pytest.mark.parametrize("cfg,seed,peaky", [("cfg1", 0, False), ("cfg1", 1, True), ("cfg2", 0, False),
+                                            ("cfg2", 2, True), ("cfg4", 0, False), ("cfg4", 1, True)])
+def test_configs_vs_oracle(dev, cfg, seed, peaky):
+    B, T, V, L = CONFIGS[cfg]
+    B = min(B, 8)                      # the oracle is a Python loop over T; keep it to seconds
+    d = make_batch(B, T, V, L, seed=seed, peaky=peaky)
+    head = np.random.default_rng(seed).uniform(0.5, 1.5, B)
+    loss, grad = _run_block(dev, d, head=head)
+    lo, go, ok = _oracle(d, head=head)
+    assert ok.all()
+    _check(loss, grad, lo, go, cfg)
+
+
+def test_cfg3_wide_vocab_vs_oracle(dev):
+    B, T, V, L = CONFIGS["cfg3"]
+    d = make_batch(3, T, V, L, seed=3)
+    loss, grad = _run_block(dev, d)
+    lo, go, ok = _oracle(d)
+    _check(loss, grad, lo, go, "cfg3")
+
+
+def test_layouts_and_label_dtypes_agree(dev):
+    d = make_batch(6, 50, 13, 10, seed=4)
+    base_l, base_g = _run_block(dev, d)
+    for layout, ll in (("TNC", "NT"), ("NTC", "TN"), ("TNC", "TN")):
+        l, g = _run_block(dev, d, layout=layout, label_layout=ll)
+        np.testing.assert_array_equal(l, base_l)
+        np.testing.assert_array_equal(g, base_g)
+    lo, go, _ = _oracle(d)
+    _check(base_l, base_g, lo, go, "layouts")
+
+
+def test_blank_last_and_inferred_lengths(dev):
+    d = make_batch(5, 40, 8, 7, seed=5, blank=7)
+    loss, grad = _run_block(dev, d, blank_label="last", lengths=False)
+    lo, go, ok = _oracle(d, blank_label="last", lengths=False)
+    # without pred_lengths every utterance has T frames: some may become infeasible -> both agree
+    _check(loss, grad, lo, go, "blank last")
+
+
+def test_edge_cases(dev):
+    from gluon_e2e_asr_b200 import ctc_loss_and_grad
+    rng = np.random.default_rng(9)
+    T, B, V, L = 12, 6, 7, 5
+    x = rng.standard_normal((B, T, V)).astype(np.float32)
+    lab = np.array([[1, 1, 1, 1, 1],      # all repeats: needs 9 frames
+                    [1, 2, 3, 4, 5],
+                    [0, 0, 0, 0, 0],      # empty label (L=0)
+                    [3, 3, 2, 2, 1],      # infeasible with T_b = 6 (needs 7)
+                    [6, 5, 4, 3, 2],      # T_b == L_b: single path
+                    [2, 2, 0, 0, 0]], np.float32)
+    Tb = np.array([9, 12, 7, 6, 5, 3], np.float32)
+    Lb = np.array([5, 5, 0, 5, 5, 2], np.float32)
+    d = dict(pred=x, label=lab, pred_lengths=Tb, label_lengths=Lb)
+    t = _to(dev, d)
+    status = torch.zeros((B,), dtype=torch.int32, device=dev)
+    loss, grad = ctc_loss_and_grad(t["pred"], t["label"], t["pred_lengths"], t["label_lengths"], status=status)
+    lo, go, ok = _oracle(d)
+    assert list(ok) == [True, True, True, False, True, True]
+    _check(loss.cpu().numpy(), grad.cpu().numpy(), lo, go, "edge")
+    st = status.cpu().numpy()
+    assert st[3] & 1 and not (st[[0, 1, 2, 4, 5]] & 1).any()
+    assert np.all(grad.cpu().numpy()[3] == 0) and loss[3].item() == 0
+    # padded frames are exactly zero
+    g = grad.cpu().numpy()
+    for b in range(B):
+        assert np.all(g[b, int(Tb[b]):] == 0)
+
+
+def test_properties_at_full_size(dev):
+    """cfg2 / cfg5-sized batches without the oracle: row sums, padding zeros, batch == single,
+    head-gradient linearity, determinism."""
+    from gluon_e2e_asr_b200 import ctc_loss_and_grad
+    B, T, V, L = CONFIGS["cfg2"]
+    d = make_batch(B, T, V, L, seed=6)
+    t = _to(dev, d)
+    args = (t["pred"], t["label"], t["pred_lengths"], t["label_lengths"])
+    loss, grad = ctc_loss_and_grad(*args)
+    loss, grad = loss.clone(), grad.clone()
+    assert torch.isfinite(loss).all() and torch.isfinite(grad).all()
+    Tb = t["pred_lengths"].long()
+    mask = torch.arange(T, device=dev)[None, :] < Tb[:, None]
+    assert grad[~mask].abs().max().item() == 0
+    assert grad.sum(-1)[mask].abs().max().item() < 5e-6          # sum_v G = 0 on valid frames
+    # determinism: same bits on a second run
+    loss2, grad2 = ctc_loss_and_grad(*args)
+    assert torch.equal(loss, loss2) and torch.equal(grad, grad2)
+    # linearity in head_grad
+    head = torch.linspace(0.5, 2.0, B, device=dev)
+    _, gh = ctc_loss_and_grad(*args, head_grad=head)
+    torch.testing.assert_close(gh, grad * head[:, None, None], rtol=1e-6, atol=1e-9)
+    # batch == single utterance
+    for b in (0, B // 2, B - 1):
+        l1, g1 = ctc_loss_and_grad(t["pred"][b:b + 1], t["label"][b:b + 1], t["pred_lengths"][b:b + 1],
+                                   t["label_lengths"][b:b + 1])
+        assert torch.equal(l1[0], loss[b]) and torch.equal(g1[0], grad[b])
+
+
+def test_autograd_path_equals_fused_path_and_handoffs(dev):
+    from gluon_e2e_asr_b200 import CtcLoss, ctc_loss_and_grad
+    d = make_batch(7, 80, 46, 20, seed=8)
+    t = _to(dev, d)
+    blk = CtcLoss()
+    pred = t["pred"].clone().requires_grad_(True)
+    loss = blk(pred, t["label"], t["pred_lengths"], t["label_lengths"])
+    loss.mean().backward()
+    head = torch.full((7,), 1.0 / 7, device=dev)
+    for handoff in ("dlpack", "pointer"):
+        lf, gf = ctc_loss_and_grad(t["pred"], t["label"], t["pred_lengths"], t["label_lengths"], head_grad=head,
+                                   handoff=handoff)
+        assert torch.equal(lf, loss.detach()) and torch.equal(gf, pred.grad)
+    # forward-only (evaluation path, train_ctc_ce.py:143): same loss, no history kept
+    with torch.no_grad():
+        le = blk(t["pred"], t["label"], t["pred_lengths"], t["label_lengths"])
+    assert torch.equal(le, loss.detach())
+
+
+def test_loss_sum_and_host_entry(dev):
+    import ctypes
+    from gluon_e2e_asr_b200 import _lib, ctc_loss_and_grad
+    d = make_batch(4, 30, 11, 6, seed=10)
+    t = _to(dev, d)
+    s = torch.zeros((), dtype=torch.float64, device=dev)
+    loss, grad = ctc_loss_and_grad(t["pred"], t["label"], t["pred_lengths"], t["label_lengths"], loss_sum=s)
+    assert abs(s.item() - loss.double().sum().item()) < 1e-4
+    # host-buffer entry: numpy in, numpy out
+    x = np.ascontiguousarray(d["pred"]); g = np.empty_like(x); l = np.empty((4,), np.float32)
+    p = _lib.Problem()
+    p.T, p.B, p.V, p.Lmax, p.blank, p.label_pad = 30, 4, 11, 6, 0, 0
+    p.logits, p.logits_stride_t, p.logits_stride_b = x.ctypes.data, 11, 30 * 11
+    p.grad, p.grad_stride_t, p.grad_stride_b = g.ctypes.data, 11, 30 * 11
+    lab = np.ascontiguousarray(d["label"]); p.labels, p.label_dtype = lab.ctypes.data, _lib.DT_F32
+    p.label_stride_b, p.label_stride_l = 6, 1
+    p.data_lengths, p.data_lengths_dtype = d["pred_lengths"].ctypes.data, _lib.DT_F32
+    p.label_lengths, p.label_lengths_dtype = d["label_lengths"].ctypes.data, _lib.DT_F32
+    p.loss = l.ctypes.data
+    _lib.check(_lib.load().ctcb_loss_grad_host(ctypes.byref(p), 0))
+    np.testing.assert_array_equal(l, loss.cpu().numpy())
+    np.testing.assert_array_equal(g, grad.cpu().numpy())
+
+
+def test_errors_do_not_fall_back(dev):
+    import ctypes
+    from gluon_e2e_asr_b200 import _lib
+    p = _lib.Problem()
+    rc = _lib.load().ctcb_loss_grad(ctypes.byref(p), None, 0, None)
+    assert rc == _lib.CTCB_INVALID_VALUE and b"bad shape" in _lib.load().ctcb_last_error()
+    x = np.zeros((2, 3, 4), np.float32); l = np.zeros((2,), np.float32)
+    p.T, p.B, p.V, p.Lmax = 3, 2, 4, 0
+    p.logits, p.loss = x.ctypes.data, l.ctypes.data           # host pointers on the device entry
+    ws = torch.empty((1 << 20,), dtype=torch.uint8, device=dev)
+    rc = _lib.load().ctcb_loss_grad(ctypes.byref(p), ws.data_ptr(), ws.numel(), None)
+    assert rc == _lib.CTCB_INVALID_VALUE
+    p.logits = ws.data_ptr(); p.loss = ws.data_ptr() + 4096
+    rc = _lib.load().ctcb_loss_grad(ctypes.byref(p), ws.data_ptr() + 8192, 16, None)
+    assert rc == _lib.CTCB_WORKSPACE_TOO_SMALL
+
+
+def test_greedy_decode(dev):
+    from gluon_e2e_asr_b200 import greedy_decode
+    d = make_batch(6, 70, 46, 15, seed=12, peaky=True)
+    t = _to(dev, d)
+    toks, lens = greedy_decode(t["pred"], t["pred_lengths"])
+    ref = O.greedy_decode(d["pred"], d["pred_lengths"])
+    toks, lens = toks.cpu().numpy(), lens.cpu().numpy()
+    for b in range(6):
+        assert list(toks[b, :lens[b]]) == ref[b]
