@@ -1,0 +1,479 @@
+#!/usr/bin/env python
+"""bench.py -- CTC fwd+bwd valid frames/s on B200 (BASELINE.json metric), one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl reference]
+
+A *step* is one pass of the hot path (log-softmax, alpha/beta recursion, gradient to the
+logits) over one synthetic batch.  N=1 runs BASELINE.json configs[1] (cfg2: B=32, T=500,
+V=46, L<=120, variable lengths).  N>1 (torchrun) gives every rank its own cfg2-shaped shard of
+utterances -- the path has no data-path collective; the per-step float64 loss-sum all-reduce
+(NCCL) runs on a side stream -- and reports the aggregate ("scaling": "weak").
+
+`value`  : device-resident inputs, the 3-kernel step replayed from CUDA graphs, CUDA events
+           around exactly K steps, max over ranks.
+`e2e`    : same metric through the public API (CtcLoss(...)(pred, ...).mean().backward()) with
+           pinned HOST inputs: H2D of logits/labels/lengths and D2H of the loss vector are
+           inside the timed region of every step.
+`roofline`: dominant kernel (k_walk) against the measured HBM copy peak.
+`cpu_baseline`: the oracle's C restatement of the reference's CPU operator, timed on this
+           box's host cores on a bounded sample (N=1, rank 0 only).
+`--impl reference`: the same C restatement as the measured arm (the reference's MXNet
+           operator is not installable here -- DESIGN.md section 3), all host threads.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+from tests.synth import CONFIGS, make_batch
+
+METRIC = "ctc_fwd_bwd_valid_frames_per_sec"
+UNIT = "frames/s"
+L2_BYTES = 126 * 1024 * 1024
+
+
+def algorithmic_bytes(V, T, B, Tb, Lb):
+    """read valid logits once + write the dense gradient once + labels/lengths/loss."""
+    return 4 * V * int(Tb.sum()) + 4 * V * B * T + 4 * int(Lb.sum()) + 12 * B
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """NVML samples of SM clock and throttle reasons while the timed region runs."""
+
+    def __init__(self, index, period=0.004):
+        super().__init__(daemon=True)
+        self.period, self.samples, self.reasons, self.max_mhz = period, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def sample(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+                     0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+            for bit, n in names.items():
+                if r & bit:
+                    self.reasons.add(n)
+        except Exception:
+            pass
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            self.sample()
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=1.0)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cuda_local_index():
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    return None if vis else 0
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle's C restatement on the host cores
+# ------------------------------------------------------------------------------------------
+def cpu_step_fn(d):
+    from oracle import ctc_ref
+    B = d["pred"].shape[0]
+    head = np.full((B,), 1.0 / B, np.float32)
+    g = np.empty_like(d["pred"])
+    lab = d["label"].astype(np.int32)
+
+    def step():
+        # NTC logits addressed through strides (no swapaxes copy: a favour to the baseline),
+        # softmax + alpha + beta + grad + head scaling, OpenMP over the minibatch
+        return ctc_ref.ctc_ref(d["pred"], lab, d["pred_lengths"], d["label_lengths"], blank=0, head_grad=head,
+                               layout="NTC", dtype=np.float32, out_grad=g)
+    return step, ctc_ref.max_threads()
+
+
+def time_cpu(d, steps, warmup, budget_s=None):
+    step, cores = cpu_step_fn(d)
+    for _ in range(warmup):
+        step()
+    ts = []
+    t_start = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+        if budget_s is not None and time.perf_counter() - t_start > budget_s and len(ts) >= 3:
+            break
+    return ts, cores
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    name = args.workload
+    B, T, V, L = CONFIGS[name]
+    d = make_batch(B, T, V, L, seed=0)
+    frames = float(d["pred_lengths"].sum())
+    ts, cores = time_cpu(d, args.steps, max(args.warmup, 1))
+    ms = 1e3 * sum(ts) / len(ts)
+    val = frames / (ms * 1e-3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": len(ts), "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": name, "B": B, "T": T, "V": V, "Lmax": L, "valid_frames_per_step": frames,
+                   "note": "C restatement of the reference's CPU CTC operator (oracle/ctc_ref.c, fp32, OpenMP over the "
+                           "minibatch); MXNet itself is not installable in this image"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d full %s steps (B=%d)" % (len(ts), name, B)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# CUDA arm
+# ------------------------------------------------------------------------------------------
+def run_cuda(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from gluon_e2e_asr_b200 import CtcLoss, _lib
+    from gluon_e2e_asr_b200 import ops
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device and no CPU fallback for the measured arm")
+    _lib.load()
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    name = args.workload
+    B, T, V, L = CONFIGS[name]
+    blk = CtcLoss(layout="NTC", label_layout="NT")
+    head = torch.full((B,), 1.0 / B, device=dev)
+
+    # input sets: rotate over enough distinct (logits, grad) buffers to exceed L2
+    per_set = 2 * 4 * B * T * V
+    nset = max(2, min(64, (2 * L2_BYTES + per_set - 1) // per_set + 1))
+    sets = []
+    for i in range(nset):
+        d = make_batch(B, T, V, L, seed=1000 * rank + i)
+        sets.append({
+            "np": d,
+            "pred": torch.tensor(d["pred"], device=dev), "label": torch.tensor(d["label"], device=dev),
+            "pl": torch.tensor(d["pred_lengths"], device=dev), "ll": torch.tensor(d["label_lengths"], device=dev),
+            "loss": torch.empty((B,), device=dev), "grad": torch.empty((B, T, V), device=dev),
+            "frames": float(d["pred_lengths"].sum()),
+        })
+    loss_sum = torch.zeros((), dtype=torch.float64, device=dev)
+
+    def step_eager(s):
+        ops.ctc_loss_and_grad(s["pred"], s["label"], s["pl"], s["ll"], head_grad=head, loss_sum=loss_sum,
+                              out_loss=s["loss"], out_grad=s["grad"], handoff="pointer")
+
+    stream = torch.cuda.Stream(dev)
+    comm_stream = torch.cuda.Stream(dev)
+    graphs = []
+    with torch.cuda.stream(stream):
+        for s in sets[:2]:
+            step_eager(s)
+        torch.cuda.synchronize()
+        launches_per_step = _lib.last_launch_count()
+        walk_cfg = _lib.last_walk_config()
+        for s in sets:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                step_eager(s)
+            graphs.append(g)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    red_buf = torch.zeros((3,), dtype=torch.float64, device=dev)
+
+    def run_steps(k, graph=True, allreduce=True):
+        frames = 0.0
+        with torch.cuda.stream(stream):
+            for i in range(k):
+                s = sets[i % nset]
+                if graph:
+                    graphs[i % nset].replay()
+                else:
+                    step_eager(s)
+                frames += s["frames"]
+                if world > 1 and allreduce:
+                    # scalar loss-sum all-reduce on a side stream: never blocks the next step
+                    ev = torch.cuda.Event()
+                    ev.record(stream)
+                    comm_stream.wait_event(ev)
+                    with torch.cuda.stream(comm_stream):
+                        red_buf[0].copy_(loss_sum, non_blocking=True)
+                        dist.all_reduce(red_buf)
+            stream.wait_stream(comm_stream)
+        return frames
+
+    # ---- value: K steps, device-resident inputs ------------------------------------------
+    barrier()
+    run_steps(args.warmup)
+    barrier()
+    sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else 0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    e0.record(stream)
+    frames = run_steps(args.steps)
+    e1.record(stream)
+    sampler.sample()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total, frames], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_total, frames_all = tmax[0].item(), tsum[1].item()
+    else:
+        frames_all = frames
+    value = frames_all / (ms_total * 1e-3)
+    ms_per_step = ms_total / args.steps
+
+    # eager (no CUDA graph) timing of the same steps, for the record
+    barrier()
+    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    run_steps(min(args.warmup, 5), graph=False, allreduce=False)
+    ee0.record(stream)
+    n_eager = min(args.steps, 200)
+    run_steps(n_eager, graph=False, allreduce=False)
+    ee1.record(stream)
+    torch.cuda.synchronize()
+    eager_ms = ee0.elapsed_time(ee1) / n_eager
+
+    # ---- e2e: public API, pinned host inputs, H2D + D2H inside the timed region ----------
+    hsets = []
+    for s in sets[:min(nset, 8)]:
+        d = s["np"]
+        hsets.append({k: torch.from_numpy(d[k]).pin_memory() for k in ("pred", "label", "pred_lengths", "label_lengths")})
+    h2d = sum(int(v.numel() * v.element_size()) for v in hsets[0].values())
+    loss_host = torch.empty((B,), dtype=torch.float32).pin_memory()
+    d2h = int(loss_host.numel() * 4)
+
+    def e2e_step(h):
+        pred = h["pred"].to(dev, non_blocking=True).requires_grad_(True)
+        lab = h["label"].to(dev, non_blocking=True)
+        pl = h["pred_lengths"].to(dev, non_blocking=True)
+        ll = h["label_lengths"].to(dev, non_blocking=True)
+        loss = blk(pred, lab, pl, ll)
+        loss.mean().backward()
+        loss_host.copy_(loss.detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()       # the step's result is on the host
+        return pred.grad
+
+    e2e_steps = max(10, min(args.steps, 200))
+    for i in range(max(3, min(args.warmup, 10))):
+        e2e_step(hsets[i % len(hsets)])
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    e2e_frames = 0.0
+    for i in range(e2e_steps):
+        e2e_step(hsets[i % len(hsets)])
+        e2e_frames += sets[i % len(hsets)]["frames"]
+    f1.record()
+    torch.cuda.synchronize()
+    e2e_ms = f0.elapsed_time(f1)
+    te = torch.tensor([e2e_ms, e2e_frames], dtype=torch.float64, device=dev)
+    if world > 1:
+        a = te.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
+        b = te.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        e2e_ms, e2e_frames = a[0].item(), b[1].item()
+    e2e_value = e2e_frames / (e2e_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel: per-kernel CUDA events inside the library -------
+    import ctypes
+    kms = np.zeros((3,), np.float64)
+    nrep = 20
+    kbuf = (ctypes.c_float * 8)()
+    nk = ctypes.c_int32(0)
+    alg = 0.0
+    with torch.cuda.stream(stream):
+        for i in range(nrep + 3):
+            s = sets[i % nset]
+            call = ops._Call(s["pred"], s["label"], s["pl"], s["ll"], False, True, False)
+            ws = ops._ws_cache[(dev.index, stream.cuda_stream, call.T, call.B, call.V, call.Lmax)]
+            p = call.problem(s["loss"], s["grad"], head)
+            _lib.check(_lib.load().ctcb_loss_grad_timed(ctypes.byref(p), ws.data_ptr(), ws.numel(), stream.cuda_stream,
+                                                        kbuf, ctypes.byref(nk)))
+            if i >= 3:
+                kms += np.array(list(kbuf)[:3])
+                alg += algorithmic_bytes(V, T, B, s["np"]["pred_lengths"], s["np"]["label_lengths"])
+    kms /= nrep
+    alg /= nrep
+    knames = ["k_emit", "k_walk", "k_grad"]
+    dom = int(np.argmax(kms))
+    peak, peak_src = measured_peak()
+    achieved = alg / (kms[dom] * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            with open(tp) as f:
+                traffic = json.load(f).get(name, {}).get(knames[dom])
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "hbm", "kernel": knames[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": alg,
+        "kernel_ms": {k: float(v) for k, v in zip(knames, kms)},
+        "step_achieved": alg / (ms_per_step * 1e-3) / 1e9, "step_frac": alg / (ms_per_step * 1e-3) / 1e9 / peak,
+        "note": "V=46 path is recursion-latency bound (T dependent steps per utterance, 2B CTAs), not HBM bound: "
+                "SURVEY.md 8d / DESIGN.md section 5",
+    }
+
+    # ---- other workloads, same run (N=1 only): context numbers, not the headline ----------
+    others = []
+    if world == 1 and not args.no_others:
+        for oname in ("cfg1", "cfg3", "cfg4", "cfg5"):
+            if oname == name:
+                continue
+            try:
+                others.append(measure_other(torch, ops, dev, oname, peak))
+            except Exception as exc:  # noqa: BLE001
+                others.append({"workload": oname, "error": str(exc)[:200]})
+
+    cpu_baseline = None
+    if rank == 0 and world == 1:
+        ts, cores = time_cpu(sets[0]["np"], 1000, 2, budget_s=12.0)
+        cms = 1e3 * sum(ts) / len(ts)
+        cpu_baseline = {"value": sets[0]["frames"] / (cms * 1e-3), "unit": UNIT, "cores": cores, "kind": "port",
+                        "ms_per_step": cms,
+                        "sample": "%d full %s steps (B=%d) of oracle/ctc_ref.c fp32, OpenMP over the minibatch" % (len(ts), name, B)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name if world == 1 else "%s per rank (global B=%d)" % (name, B * world),
+                       "B_per_gpu": B, "T": T, "V": V, "Lmax": L, "layout": "NTC", "lengths": "variable",
+                       "valid_frames_per_step": frames_all / args.steps,
+                       "utterances_per_sec": B * world / (ms_per_step * 1e-3),
+                       "l2": "inputs rotate over %d buffer sets (%.0f MB logits+grad > 126 MB L2)" % (nset, nset * per_set / 1e6),
+                       "launch": "%d kernels per step replayed from a CUDA graph; eager_ms_per_step=%.4f" % (launches_per_step, eager_ms),
+                       "walker": {"pairs_per_lane": walk_cfg[0], "warps": walk_cfg[1]},
+                       "collective": "none on the data path; float64 loss-sum all-reduce per step on a side stream" if world > 1 else "none"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
+                    "api": "CtcLoss(layout='NTC',label_layout='NT')(pred,label,pred_lengths,label_lengths).mean().backward()"},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": roofline,
+        }
+        if cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline
+        if others:
+            line["other_workloads"] = others
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def measure_other(torch, ops, dev, oname, peak, steps=20, warmup=3):
+    B, T, V, L = CONFIGS[oname]
+    per_set = 2 * 4 * B * T * V
+    nset = max(2, min(8, (2 * L2_BYTES + per_set - 1) // per_set + 1))
+    sets = []
+    for i in range(nset):
+        d = make_batch(B, T, V, L, seed=50 + i, full_lengths=(oname == "cfg5"))
+        sets.append((torch.tensor(d["pred"], device=dev), torch.tensor(d["label"], device=dev),
+                     torch.tensor(d["pred_lengths"], device=dev), torch.tensor(d["label_lengths"], device=dev),
+                     torch.empty((B,), device=dev), torch.empty((B, T, V), device=dev),
+                     float(d["pred_lengths"].sum()), algorithmic_bytes(V, T, B, d["pred_lengths"], d["label_lengths"])))
+    head = torch.full((B,), 1.0 / B, device=dev)
+
+    def step(s):
+        ops.ctc_loss_and_grad(s[0], s[1], s[2], s[3], head_grad=head, out_loss=s[4], out_grad=s[5], handoff="pointer")
+    for i in range(warmup):
+        step(sets[i % nset])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    frames = alg = 0.0
+    for i in range(steps):
+        s = sets[i % nset]
+        step(s)
+        frames += s[6]; alg += s[7]
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    ops._ws_cache.clear()
+    del sets
+    torch.cuda.empty_cache()
+    return {"workload": oname, "B": B, "T": T, "V": V, "Lmax": L, "ms_per_step": ms / steps,
+            "value": frames / (ms * 1e-3), "unit": UNIT, "step_achieved_gbs": alg / (ms * 1e-3) / 1e9,
+            "step_frac": alg / (ms * 1e-3) / 1e9 / peak, "launch": "eager"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--no-others", action="store_true", help="skip the context measurements of the other configs")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if args.steps > 50:
+            args.steps = 50          # each step is a full CPU pass (tens of ms); keep the run to minutes
+        run_reference(args, rank, world)
+        return
+    run_cuda(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

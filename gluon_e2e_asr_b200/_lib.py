@@ -20,7 +20,7 @@ PHASE_FUSED, PHASE_FORWARD, PHASE_BACKWARD = 0 << 8, 1 << 8, 2 << 8
 EXPORTS = (
     "ctcb_version", "ctcb_last_error", "ctcb_workspace_bytes", "ctcb_loss_grad", "ctcb_forward",
     "ctcb_backward", "ctcb_loss_grad_host", "ctcb_greedy_decode", "ctcb_loss_sum_allreduce",
-    "ctcb_last_launch_count", "ctcb_last_walk_config", "ctcb_loss_grad_dlpack",
+    "ctcb_last_launch_count", "ctcb_last_walk_config", "ctcb_loss_grad_dlpack", "ctcb_loss_grad_timed",
 )
 
 
@@ -67,6 +67,7 @@ def load():
     lib.ctcb_loss_grad.argtypes = [PP, vp, sz, vp]
     lib.ctcb_forward.argtypes = [PP, i32, vp, sz, vp]
     lib.ctcb_backward.argtypes = [PP, vp, sz, vp]
+    lib.ctcb_loss_grad_timed.argtypes = [PP, vp, sz, vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32)]
     lib.ctcb_loss_grad_host.argtypes = [PP, ctypes.c_int]
     lib.ctcb_greedy_decode.argtypes = [vp, i64, i64, vp, i32, i32, i32, i32, i32, vp, vp, vp]
     lib.ctcb_loss_sum_allreduce.argtypes = [vp, vp, i32, vp]

@@ -21,6 +21,8 @@ namespace {
 thread_local char g_err[512] = "";
 thread_local int g_launches = 0;
 thread_local int g_walk_p = 0, g_walk_nw = 0;
+thread_local cudaEvent_t* g_prof_events = nullptr;   // when set: one event recorded after every launch
+thread_local int g_prof_count = 0;
 
 int fail(int code, const char* fmt, ...) {
     va_list ap; va_start(ap, fmt);
@@ -46,7 +48,7 @@ struct Layout {
 Layout make_layout(int T, int B, int /*V*/, int Lmax, int need_grad) {
     Layout l{};
     l.Lp = (int)align_up((size_t)(Lmax > 0 ? Lmax : 1), 4);
-    l.W = (int)align_up((size_t)Lmax + 1, 4);
+    l.W = (int)align_up((size_t)Lmax + 1, 2);     // int2 entries per emission row (16-byte rows)
     l.HP = Lmax + 1;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
@@ -57,7 +59,7 @@ Layout make_layout(int T, int B, int /*V*/, int Lmax, int need_grad) {
     l.off_nxt = take(sizeof(int) * (size_t)B * l.Lp);
     l.off_first = take(sizeof(int) * (size_t)B * l.Lp);
     l.off_fr = take(sizeof(float2) * (size_t)B * T);
-    l.off_E = take(sizeof(float) * (size_t)B * T * l.W);
+    l.off_E = take(sizeof(int2) * (size_t)B * T * l.W);
     if (need_grad) {
         l.off_hA = take(sizeof(int4) * (size_t)B * T * l.HP);
         l.off_hB = take(sizeof(int4) * (size_t)B * T * l.HP);
@@ -76,7 +78,7 @@ ctcb::Workspace carve(const Layout& l, void* ws) {
     w.nxt = reinterpret_cast<int*>(base + l.off_nxt);
     w.first = reinterpret_cast<int*>(base + l.off_first);
     w.fr = reinterpret_cast<float2*>(base + l.off_fr);
-    w.E = reinterpret_cast<float*>(base + l.off_E);
+    w.E = reinterpret_cast<int2*>(base + l.off_E);
     w.hA = reinterpret_cast<int4*>(base + l.off_hA);
     w.hB = reinterpret_cast<int4*>(base + l.off_hB);
     w.Lp = l.Lp; w.W = l.W; w.HP = l.HP;
@@ -87,13 +89,13 @@ ctcb::Workspace carve(const Layout& l, void* ws) {
 struct WalkCfg { int P, NW; };
 
 using WalkFn = void (*)(ctcb::WalkArgs);
-struct WalkEntry { int P, NW; WalkFn fn; };
-#define WALK(P_, NW_) {P_, NW_, ctcb::k_walk<P_, NW_>}
+struct WalkEntry { int P, NW; WalkFn fn[2][2]; };   // [G == 16][HIST]
+#define WALK(P_, NW_) {P_, NW_, {{ctcb::k_walk<P_, NW_, 8, false>, ctcb::k_walk<P_, NW_, 8, true>}, \
+                                 {ctcb::k_walk<P_, NW_, 16, false>, ctcb::k_walk<P_, NW_, 16, true>}}}
 const WalkEntry kWalkTable[] = {
-    WALK(1, 1),  WALK(2, 1),  WALK(1, 2),  WALK(1, 4),  WALK(2, 2),  WALK(4, 1),
-    WALK(1, 8),  WALK(2, 4),  WALK(4, 2),  WALK(1, 16), WALK(2, 8),  WALK(4, 4),
-    WALK(1, 32), WALK(2, 16), WALK(4, 8),  WALK(2, 32), WALK(4, 16), WALK(4, 32),
-    WALK(8, 16), WALK(8, 32), WALK(16, 32),
+    WALK(1, 1),  WALK(2, 1),  WALK(1, 2),  WALK(1, 3),  WALK(1, 4),  WALK(2, 2),  WALK(4, 1),
+    WALK(1, 5),  WALK(1, 6),  WALK(1, 8),  WALK(2, 4),  WALK(4, 2),  WALK(1, 10), WALK(1, 12),
+    WALK(1, 16), WALK(2, 8),  WALK(4, 4),  WALK(2, 16), WALK(4, 8),  WALK(4, 16),
 };
 #undef WALK
 
@@ -110,22 +112,26 @@ const WalkEntry* choose_walk(int pairs) {
         const WalkEntry* e = find_walk(atoi(ep), atoi(en));
         if (e && e->P * e->NW * 32 >= pairs) return e;
     }
-    static const WalkCfg pref[] = {{1, 1}, {1, 2}, {1, 4}, {2, 4}, {2, 8}, {4, 8}, {4, 16}, {4, 32}, {8, 32}, {16, 32}};
+    static const WalkCfg pref[] = {{1, 1}, {1, 2}, {1, 3}, {1, 4}, {1, 5}, {1, 6}, {1, 8}, {1, 10}, {1, 12}, {1, 16},
+                                   {2, 16}, {4, 16}};
     for (const auto& c : pref)
         if (c.P * c.NW * 32 >= pairs) return find_walk(c.P, c.NW);
     return nullptr;
 }
 
-int pick_kb(int W) {
-    if (W <= 256) return 16;
-    if (W <= 512) return 8;
-    if (W <= 1024) return 4;
-    if (W <= 2048) return 2;
-    return 1;
+size_t walk_smem(int G, int W, int NW, int stages) {
+    return (size_t)stages * G * W * sizeof(int2) + 2 * ctcb::kStages * sizeof(uint64_t) +
+           (size_t)NW * 2 * G * 8 + (size_t)NW * sizeof(int) + 16;
 }
 
-size_t walk_smem(int KB, int W, int NW) {
-    return (size_t)ctcb::kStages * KB * W * sizeof(float) + ctcb::kStages * sizeof(uint64_t) + 2 * (size_t)NW * sizeof(int2);
+// group size (steps between control points = frames per emission block) and ring depth
+bool pick_group(int W, int NW, int* G, int* stages) {
+    const char* eg = getenv("CTCB_WALK_G");
+    const int want = eg ? atoi(eg) : 16;
+    for (int g : {want == 8 ? 8 : 16, 8})
+        for (int s = ctcb::kStages; s >= 2; --s)
+            if (walk_smem(g, W, NW, s) <= 200 * 1024) { *G = g; *stages = s; return true; }
+    return false;
 }
 
 int pick_vec(const void* base, long long st_t, long long st_b, int V) {
@@ -148,8 +154,8 @@ int validate(const ctcb_problem_t* p) {
     if (!dt_ok(p->label_dtype) || (p->data_lengths && !dt_ok(p->data_lengths_dtype)) ||
         (p->label_lengths && !dt_ok(p->label_lengths_dtype)))
         return fail(CTCB_INVALID_VALUE, "unsupported label/length dtype");
-    if (p->Lmax + 1 > 16 * 32 * 32)
-        return fail(CTCB_UNSUPPORTED, "Lmax=%d exceeds the largest walker (16383 labels)", p->Lmax);
+    if (p->Lmax + 1 > 1700)
+        return fail(CTCB_UNSUPPORTED, "Lmax=%d exceeds the supported 1699 labels per utterance", p->Lmax);
     if ((long long)p->B > 65535) return fail(CTCB_UNSUPPORTED, "B=%d exceeds 65535 utterances per call", p->B);
     return CTCB_OK;
 }
@@ -198,6 +204,11 @@ namespace {
 // phase bits
 enum { PH_FORWARD = 1, PH_BACKWARD = 2 };
 
+inline void mark(cudaStream_t stream) {
+    ++g_launches;
+    if (g_prof_events && g_prof_count < 8) cudaEventRecord(g_prof_events[g_prof_count++], stream);
+}
+
 int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, void* stream_, int phases, bool keep_hist) {
     if (int rc = validate(p)) return rc;
     const bool need_grad = keep_hist || (phases & PH_BACKWARD);
@@ -220,24 +231,26 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
         const WalkEntry* we = choose_walk(p->Lmax + 1);
         if (!we) return fail(CTCB_UNSUPPORTED, "no walker configuration for Lmax=%d", p->Lmax);
         g_walk_p = we->P; g_walk_nw = we->NW;
-        const int KB = pick_kb(lay.W);
-        const size_t smem = walk_smem(KB, lay.W, we->NW);
-        if (smem > 227 * 1024) return fail(CTCB_UNSUPPORTED, "emission ring needs %zu bytes of shared memory", smem);
+        int G = 0, stages = 0;
+        if (!pick_group(lay.W, we->NW, &G, &stages))
+            return fail(CTCB_UNSUPPORTED, "Lmax=%d: the emission ring does not fit in shared memory", p->Lmax);
+        const size_t smem = walk_smem(G, lay.W, we->NW, stages);
+        const WalkFn wfn = we->fn[G == 16][need_grad ? 1 : 0];
+        const int vec = pick_vec(p->logits, p->logits_stride_t, p->logits_stride_b, p->V);
+        const size_t esm = (size_t)lay.Lp * sizeof(int);
         {
             std::lock_guard<std::mutex> lk(mu);
-            CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(we->fn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(wfn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
-        ctcb::k_prepare<<<p->B, 128, 0, stream>>>(dp, w);
-        ++g_launches;
-        switch (pick_vec(p->logits, p->logits_stride_t, p->logits_stride_b, p->V)) {
-            case 4: ctcb::k_logsoftmax_gather<4><<<fgrid, 128, 0, stream>>>(dp, w); break;
-            case 2: ctcb::k_logsoftmax_gather<2><<<fgrid, 128, 0, stream>>>(dp, w); break;
-            default: ctcb::k_logsoftmax_gather<1><<<fgrid, 128, 0, stream>>>(dp, w); break;
+        switch (vec) {
+            case 4: ctcb::k_emit<4><<<fgrid, 128, esm, stream>>>(dp, w); break;
+            case 2: ctcb::k_emit<2><<<fgrid, 128, esm, stream>>>(dp, w); break;
+            default: ctcb::k_emit<1><<<fgrid, 128, esm, stream>>>(dp, w); break;
         }
-        ++g_launches;
-        ctcb::WalkArgs wa{w, p->T, KB, p->loss, p->loss_sum, need_grad ? 1 : 0};
-        we->fn<<<dim3(p->B, need_grad ? 2 : 1), we->NW * 32, smem, stream>>>(wa);
-        ++g_launches;
+        mark(stream);
+        ctcb::WalkArgs wa{w, p->T, stages, p->loss, p->loss_sum, nullptr};
+        wfn<<<dim3(p->B, need_grad ? 2 : 1), (we->NW + 1) * 32, smem, stream>>>(wa);
+        mark(stream);
     }
     if (phases & PH_BACKWARD) {
         ctcb::GradArgs ga{dp, w};
@@ -245,19 +258,26 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
         int vec = pick_vec(p->logits, p->logits_stride_t, p->logits_stride_b, p->V);
         const int gvec = pick_vec(p->grad, p->grad_stride_t, p->grad_stride_b, p->V);
         if (gvec < vec) vec = gvec;
-        if (gsm > 200 * 1024) return fail(CTCB_UNSUPPORTED, "Lmax=%d too long for the gradient kernel", p->Lmax);
-        if (gsm > 48 * 1024) {
+        if (gsm > 48 * 1024) {      // only the generic (CH = 0) variants see label rows this long
             std::lock_guard<std::mutex> lk(mu);
-            CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(ctcb::k_grad<1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
-            CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(ctcb::k_grad<2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
-            CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(ctcb::k_grad<4>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
+            CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(ctcb::k_grad<1, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
+            CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(ctcb::k_grad<2, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
+            CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(ctcb::k_grad<4, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
         }
+        const int pairs = p->Lmax + 1;
+        const int ch = pairs <= 32 ? 1 : pairs <= 64 ? 2 : pairs <= 128 ? 4 : pairs <= 256 ? 8 : pairs <= 512 ? 16 : 0;
+#define GRAD_LAUNCH(V_, C_) ctcb::k_grad<V_, C_><<<fgrid, 128, gsm, stream>>>(ga)
+#define GRAD_CH(V_) switch (ch) { case 1: GRAD_LAUNCH(V_, 1); break; case 2: GRAD_LAUNCH(V_, 2); break; \
+                                  case 4: GRAD_LAUNCH(V_, 4); break; case 8: GRAD_LAUNCH(V_, 8); break;  \
+                                  case 16: GRAD_LAUNCH(V_, 16); break; default: GRAD_LAUNCH(V_, 0); break; }
         switch (vec) {
-            case 4: ctcb::k_grad<4><<<fgrid, 128, gsm, stream>>>(ga); break;
-            case 2: ctcb::k_grad<2><<<fgrid, 128, gsm, stream>>>(ga); break;
-            default: ctcb::k_grad<1><<<fgrid, 128, gsm, stream>>>(ga); break;
+            case 4: GRAD_CH(4); break;
+            case 2: GRAD_CH(2); break;
+            default: GRAD_CH(1); break;
         }
-        ++g_launches;
+#undef GRAD_CH
+#undef GRAD_LAUNCH
+        mark(stream);
     }
     CUDA_TRY(cudaGetLastError());
     return CTCB_OK;
@@ -269,6 +289,26 @@ int ctcb_loss_grad(const ctcb_problem_t* p, void* workspace, size_t workspace_by
     g_launches = 0;
     const bool need_grad = p && p->grad != nullptr;
     return enqueue(p, workspace, workspace_bytes, stream, need_grad ? (PH_FORWARD | PH_BACKWARD) : PH_FORWARD, need_grad);
+}
+
+int ctcb_loss_grad_timed(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, void* stream_,
+                         float* kernel_ms, int32_t* n_kernels) {
+    if (!kernel_ms || !n_kernels) return fail(CTCB_INVALID_VALUE, "kernel_ms / n_kernels is NULL");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    cudaEvent_t ev[9];
+    for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
+    CUDA_TRY(cudaEventRecord(ev[0], stream));
+    g_prof_events = ev + 1; g_prof_count = 0;
+    const int rc = ctcb_loss_grad(p, workspace, workspace_bytes, stream);
+    const int n = g_prof_count;
+    g_prof_events = nullptr; g_prof_count = 0;
+    if (rc == CTCB_OK) {
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        for (int i = 0; i < n; ++i) CUDA_TRY(cudaEventElapsedTime(&kernel_ms[i], ev[i], ev[i + 1]));
+        *n_kernels = n;
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    return rc;
 }
 
 int ctcb_forward(const ctcb_problem_t* p, int32_t keep_for_backward, void* workspace, size_t workspace_bytes, void* stream) {

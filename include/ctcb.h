@@ -108,6 +108,12 @@ int ctcb_forward(const ctcb_problem_t* p, int32_t keep_for_backward, void* works
 int ctcb_backward(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes,
                   void* stream);
 
+/* Measurement aid (bench.py's roofline leg): ctcb_loss_grad with a CUDA event recorded on
+ * `stream` after every kernel; synchronises and returns the per-kernel device times in launch
+ * order (k_emit, k_walk, k_grad).  kernel_ms must hold 8 floats. */
+int ctcb_loss_grad_timed(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes,
+                         void* stream, float* kernel_ms, int32_t* n_kernels);
+
 /* Same operator with HOST buffers (what a `ctx=mx.cpu()` caller of the reference holds):
  * copies inputs host->device, runs ctcb_loss_grad, copies loss (and grad) back and
  * synchronises.  Device scratch is cached per device and grown on demand.  Used by
