@@ -40,16 +40,70 @@ int fail(int code, const char* fmt, ...) {
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// ---- walker configuration -------------------------------------------------------------
+struct WalkCfg { int P, NW; };
+
+using WalkFn = void (*)(ctcb::WalkArgs);
+struct WalkEntry { int P, NW; WalkFn fn[2]; };   // [HIST]
+#define WALK(P_, NW_) {P_, NW_, {ctcb::k_walk<P_, NW_, false>, ctcb::k_walk<P_, NW_, true>}}
+const WalkEntry kWalkTable[] = {
+    WALK(1, 1), WALK(2, 1), WALK(4, 1), WALK(1, 2), WALK(2, 2), WALK(4, 2), WALK(1, 3), WALK(2, 3),
+    WALK(1, 4), WALK(2, 4), WALK(4, 4), WALK(2, 5), WALK(2, 6), WALK(1, 8), WALK(2, 8), WALK(4, 8),
+    WALK(2, 12), WALK(2, 16), WALK(4, 16),
+};
+#undef WALK
+
+const WalkEntry* find_walk(int P, int NW) {
+    for (const auto& e : kWalkTable) if (e.P == P && e.NW == NW) return &e;
+    return nullptr;
+}
+
+// default choice per capacity (pairs = Lmax+1); tuned on B200, see DESIGN.md section 5.
+// The choice is part of the workspace layout (history chunks are per walker warp).
+const WalkEntry* choose_walk(int pairs) {
+    const char* ep = getenv("CTCB_WALK_P");
+    const char* en = getenv("CTCB_WALK_NW");
+    if (ep && en) {
+        const WalkEntry* e = find_walk(atoi(ep), atoi(en));
+        if (e && e->P * e->NW * 32 >= pairs) return e;
+    }
+    static const WalkCfg pref[] = {{1, 1}, {2, 1}, {2, 2}, {2, 3}, {2, 4}, {2, 5}, {2, 6}, {2, 8}, {2, 12}, {2, 16}, {4, 16}};
+    for (const auto& c : pref)
+        if (c.P * c.NW * 32 >= pairs) return find_walk(c.P, c.NW);
+    return nullptr;
+}
+
+// emission ring depth: as deep as fits a modest budget (several walker CTAs share an SM)
+bool pick_stages(int W, int NW, int* stages) {
+    const char* es = getenv("CTCB_WALK_STAGES");
+    const size_t budget = 40 * 1024, hard = 200 * 1024;
+    for (int s = es ? atoi(es) : ctcb::kMaxStages; s >= 2; --s) {
+        if (s > ctcb::kMaxStages) continue;
+        const size_t need = ctcb::walk_smem_bytes(W, NW, s);
+        if (need <= budget || (s <= 3 && need <= hard)) { *stages = s; return true; }
+    }
+    return false;
+}
+
 struct Layout {
-    size_t off_Tb, off_Lb, off_flags, off_lab, off_nxt, off_first, off_fr, off_E, off_hA, off_hB, total;
-    int Lp, W, HP;
+    size_t off_Tb, off_Lb, off_flags, off_lab, off_nxt, off_first, off_fr, off_E, off_hA, off_hB, off_oA, off_oB, total;
+    int Lp, W, NB, dense, P, NW;
+    const WalkEntry* walk;
 };
 
-Layout make_layout(int T, int B, int /*V*/, int Lmax, int need_grad) {
+// dense emission table (the whole softmax row, label-indexed by the walkers) when the
+// vocabulary is not wider than the label row; gathered columns otherwise
+inline bool dense_table(int V, int Lmax) { return V <= Lmax + 1 || V <= 64; }
+
+Layout make_layout(int T, int B, int V, int Lmax, int need_grad) {
     Layout l{};
     l.Lp = (int)align_up((size_t)(Lmax > 0 ? Lmax : 1), 4);
-    l.W = (int)align_up((size_t)Lmax + 1, 2);     // int2 entries per emission row (16-byte rows)
-    l.HP = Lmax + 1;
+    l.dense = dense_table(V, Lmax) ? 1 : 0;
+    l.W = l.dense ? V : Lmax + 1;                 // columns per frame block (64 bytes each)
+    l.NB = (T + ctcb::kG - 1) / ctcb::kG;
+    l.walk = choose_walk(Lmax + 1);
+    l.P = l.walk ? l.walk->P : 1; l.NW = l.walk ? l.walk->NW : 1;
+    const size_t pairs = (size_t)l.NW * l.P * 32;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
     l.off_Tb = take(sizeof(int) * B);
@@ -59,10 +113,12 @@ Layout make_layout(int T, int B, int /*V*/, int Lmax, int need_grad) {
     l.off_nxt = take(sizeof(int) * (size_t)B * l.Lp);
     l.off_first = take(sizeof(int) * (size_t)B * l.Lp);
     l.off_fr = take(sizeof(float2) * (size_t)B * T);
-    l.off_E = take(sizeof(int2) * (size_t)B * T * l.W);
+    l.off_E = take(sizeof(double) * (size_t)B * l.NB * l.W * ctcb::kG);
     if (need_grad) {
-        l.off_hA = take(sizeof(int4) * (size_t)B * T * l.HP);
-        l.off_hB = take(sizeof(int4) * (size_t)B * T * l.HP);
+        l.off_hA = take(sizeof(double2) * (size_t)B * l.NB * ctcb::kG * pairs);
+        l.off_hB = take(sizeof(double2) * (size_t)B * l.NB * ctcb::kG * pairs);
+        l.off_oA = take(sizeof(int2) * (size_t)B * l.NB * pairs);
+        l.off_oB = take(sizeof(int2) * (size_t)B * l.NB * pairs);
     }
     l.total = o;
     return l;
@@ -78,60 +134,13 @@ ctcb::Workspace carve(const Layout& l, void* ws) {
     w.nxt = reinterpret_cast<int*>(base + l.off_nxt);
     w.first = reinterpret_cast<int*>(base + l.off_first);
     w.fr = reinterpret_cast<float2*>(base + l.off_fr);
-    w.E = reinterpret_cast<int2*>(base + l.off_E);
-    w.hA = reinterpret_cast<int4*>(base + l.off_hA);
-    w.hB = reinterpret_cast<int4*>(base + l.off_hB);
-    w.Lp = l.Lp; w.W = l.W; w.HP = l.HP;
+    w.E = reinterpret_cast<double*>(base + l.off_E);
+    w.hA = reinterpret_cast<double2*>(base + l.off_hA);
+    w.hB = reinterpret_cast<double2*>(base + l.off_hB);
+    w.oA = reinterpret_cast<int2*>(base + l.off_oA);
+    w.oB = reinterpret_cast<int2*>(base + l.off_oB);
+    w.Lp = l.Lp; w.W = l.W; w.NB = l.NB; w.dense = l.dense; w.P = l.P; w.NW = l.NW;
     return w;
-}
-
-// ---- walker configuration -------------------------------------------------------------
-struct WalkCfg { int P, NW; };
-
-using WalkFn = void (*)(ctcb::WalkArgs);
-struct WalkEntry { int P, NW; WalkFn fn[2][2]; };   // [G == 16][HIST]
-#define WALK(P_, NW_) {P_, NW_, {{ctcb::k_walk<P_, NW_, 8, false>, ctcb::k_walk<P_, NW_, 8, true>}, \
-                                 {ctcb::k_walk<P_, NW_, 16, false>, ctcb::k_walk<P_, NW_, 16, true>}}}
-const WalkEntry kWalkTable[] = {
-    WALK(1, 1),  WALK(2, 1),  WALK(1, 2),  WALK(1, 3),  WALK(1, 4),  WALK(2, 2),  WALK(4, 1),
-    WALK(1, 5),  WALK(1, 6),  WALK(1, 8),  WALK(2, 4),  WALK(4, 2),  WALK(1, 10), WALK(1, 12),
-    WALK(1, 16), WALK(2, 8),  WALK(4, 4),  WALK(2, 16), WALK(4, 8),  WALK(4, 16),
-};
-#undef WALK
-
-const WalkEntry* find_walk(int P, int NW) {
-    for (const auto& e : kWalkTable) if (e.P == P && e.NW == NW) return &e;
-    return nullptr;
-}
-
-// default choice per capacity (pairs = Lmax+1); tuned on B200, see DESIGN.md section 6
-const WalkEntry* choose_walk(int pairs) {
-    const char* ep = getenv("CTCB_WALK_P");
-    const char* en = getenv("CTCB_WALK_NW");
-    if (ep && en) {
-        const WalkEntry* e = find_walk(atoi(ep), atoi(en));
-        if (e && e->P * e->NW * 32 >= pairs) return e;
-    }
-    static const WalkCfg pref[] = {{1, 1}, {1, 2}, {1, 3}, {1, 4}, {1, 5}, {1, 6}, {1, 8}, {1, 10}, {1, 12}, {1, 16},
-                                   {2, 16}, {4, 16}};
-    for (const auto& c : pref)
-        if (c.P * c.NW * 32 >= pairs) return find_walk(c.P, c.NW);
-    return nullptr;
-}
-
-size_t walk_smem(int G, int W, int NW, int stages) {
-    return (size_t)stages * G * W * sizeof(int2) + 2 * ctcb::kStages * sizeof(uint64_t) +
-           (size_t)NW * 2 * G * 8 + (size_t)NW * sizeof(int) + 16;
-}
-
-// group size (steps between control points = frames per emission block) and ring depth
-bool pick_group(int W, int NW, int* G, int* stages) {
-    const char* eg = getenv("CTCB_WALK_G");
-    const int want = eg ? atoi(eg) : 16;
-    for (int g : {want == 8 ? 8 : 16, 8})
-        for (int s = ctcb::kStages; s >= 2; --s)
-            if (walk_smem(g, W, NW, s) <= 200 * 1024) { *G = g; *stages = s; return true; }
-    return false;
 }
 
 int pick_vec(const void* base, long long st_t, long long st_b, int V) {
@@ -154,8 +163,8 @@ int validate(const ctcb_problem_t* p) {
     if (!dt_ok(p->label_dtype) || (p->data_lengths && !dt_ok(p->data_lengths_dtype)) ||
         (p->label_lengths && !dt_ok(p->label_lengths_dtype)))
         return fail(CTCB_INVALID_VALUE, "unsupported label/length dtype");
-    if (p->Lmax + 1 > 1700)
-        return fail(CTCB_UNSUPPORTED, "Lmax=%d exceeds the supported 1699 labels per utterance", p->Lmax);
+    if (p->Lmax + 1 > 2048)
+        return fail(CTCB_UNSUPPORTED, "Lmax=%d exceeds the supported 2047 labels per utterance", p->Lmax);
     if ((long long)p->B > 65535) return fail(CTCB_UNSUPPORTED, "B=%d exceeds 65535 utterances per call", p->B);
     return CTCB_OK;
 }
@@ -228,27 +237,28 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
     const dim3 fgrid((p->T + ctcb::kFramesPerCta - 1) / ctcb::kFramesPerCta, p->B);
 
     if (phases & PH_FORWARD) {
-        const WalkEntry* we = choose_walk(p->Lmax + 1);
+        const WalkEntry* we = lay.walk;
         if (!we) return fail(CTCB_UNSUPPORTED, "no walker configuration for Lmax=%d", p->Lmax);
         g_walk_p = we->P; g_walk_nw = we->NW;
-        int G = 0, stages = 0;
-        if (!pick_group(lay.W, we->NW, &G, &stages))
-            return fail(CTCB_UNSUPPORTED, "Lmax=%d: the emission ring does not fit in shared memory", p->Lmax);
-        const size_t smem = walk_smem(G, lay.W, we->NW, stages);
-        const WalkFn wfn = we->fn[G == 16][need_grad ? 1 : 0];
+        int stages = 0;
+        if (!pick_stages(lay.W, we->NW, &stages))
+            return fail(CTCB_UNSUPPORTED, "Lmax=%d V=%d: the emission ring does not fit in shared memory", p->Lmax, p->V);
+        const size_t smem = ctcb::walk_smem_bytes(lay.W, we->NW, stages);
+        const WalkFn wfn = we->fn[need_grad ? 1 : 0];
         const int vec = pick_vec(p->logits, p->logits_stride_t, p->logits_stride_b, p->V);
         const size_t esm = (size_t)lay.Lp * sizeof(int);
         {
             std::lock_guard<std::mutex> lk(mu);
             CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(wfn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
+        const dim3 egrid((lay.NB + 3) / 4, p->B);
         switch (vec) {
-            case 4: ctcb::k_emit<4><<<fgrid, 128, esm, stream>>>(dp, w); break;
-            case 2: ctcb::k_emit<2><<<fgrid, 128, esm, stream>>>(dp, w); break;
-            default: ctcb::k_emit<1><<<fgrid, 128, esm, stream>>>(dp, w); break;
+            case 4: ctcb::k_emit<4><<<egrid, 128, esm, stream>>>(dp, w); break;
+            case 2: ctcb::k_emit<2><<<egrid, 128, esm, stream>>>(dp, w); break;
+            default: ctcb::k_emit<1><<<egrid, 128, esm, stream>>>(dp, w); break;
         }
         mark(stream);
-        ctcb::WalkArgs wa{w, p->T, stages, p->loss, p->loss_sum, nullptr};
+        ctcb::WalkArgs wa{w, p->T, stages, p->blank, p->loss, p->loss_sum, nullptr};
         wfn<<<dim3(p->B, need_grad ? 2 : 1), (we->NW + 1) * 32, smem, stream>>>(wa);
         mark(stream);
     }

@@ -4,20 +4,23 @@
 // (a5), alpha recursion (a6), beta recursion + per-label accumulation + gradient (a7),
 // head-gradient scaling (a8) of `mx.nd.contrib.ctc_loss` as called at
 // /root/reference/scripts/swbd/loss.py:134-139.  Not a port: the reference operator works
-// in fp32 log space; these kernels work in LINEAR space with an extended exponent
-// (fp32 mantissa + int32 exponent per lattice state), which needs no exp/log in the
-// T-sequential chain and is ~100x closer to the fp64 oracle.
+// in fp32 log space; these kernels work in the LINEAR domain on B200's full-rate FP64 pipe
+// (64 DFMA/clk/SM, 8.5-clk latency, measured: scripts/ubench/dp.cu) with one integer
+// exponent offset per lattice state that only changes when a state drifts by more than
+// 2^128 -- no exp/log and no exponent arithmetic inside the T-sequential chain
+// (DESIGN.md section 4).
 //
 // Kernels (one batch = three launches, all on the caller's stream):
-//   k_emit<VEC>          per frame: max / log2-sum-exp of the logits row and the emission
-//                        table E2[b][t][0..L_b] = (mantissa, exponent) of y_t(blank),
-//                        y_t(l_1..l_L) in an utterance-major, 16-byte-aligned layout that TMA
-//                        can stream; plus the per-utterance metadata (lengths, int labels,
-//                        repeats, feasibility, same-label chains for the gradient scatter).
+//   k_emit<VEC>          per frame: max / log2-sum-exp of the logits row; per block of 8
+//                        frames the emission table E[b][n][col][8] (fp64 softmax numerators,
+//                        frame-minor, one contiguous TMA-streamable block): the whole row when
+//                        V is small ("dense"), the gathered columns blank, l_1..l_L otherwise; plus the
+//                        per-utterance metadata (lengths, int labels, repeats, feasibility,
+//                        same-label chains for the gradient scatter).
 //   k_walk<P,NW,HIST>    grid (B, 2): the alpha walker and the (reversed) beta walker of one
-//                        utterance run concurrently on different SMs; E2 is staged through a
+//                        utterance run concurrently on different SMs; E is staged through a
 //                        shared-memory ring with cp.async.bulk (TMA) + mbarriers by a producer
-//                        warp; one (blank,label) state pair per lane slot, one warp shuffle
+//                        warp; P (blank,label) state pairs per lane, one 64-bit warp shuffle
 //                        per step, no CTA barrier (skewed wavefront across warps).
 //   k_grad<VEC,CH>       per frame: posterior state occupancy normalised per frame
 //                        (gamma = alpha*beta'/Z_t), scatter to label columns, fused
@@ -28,13 +31,15 @@
 
 namespace ctcb {
 
-constexpr int kZeroE = -(1 << 28);     // exponent of the "zero" state (value 2^-268435456)
-constexpr int kDClamp = -100;          // smallest relative exponent that is still added
+constexpr int kG = 8;                  // walker steps per group (= frames per emission block)
+constexpr int kD = 100;                // largest exponent step between neighbouring states
+constexpr int kDrift = 200;            // a state renormalises when it drifts past 2^+-kDrift
+constexpr int kZeroE = -(1 << 28);     // "natural exponent" of an exactly-zero state
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr double kLn2 = 0.6931471805599453094;
-constexpr float kMinLog2 = -1048576.0f;  // clamp of one frame's log2-probability
-constexpr int kStages = 4;             // emission ring depth (blocks of G frames), at most
-constexpr int kFramesPerCta = 16;      // k_logsoftmax_gather / k_grad: 4 warps x 4 frames
+constexpr float kMinLog2 = -100.0f;    // clamp of one frame's log2-probability (7.9e-31)
+constexpr int kMaxStages = 16;         // emission ring depth (blocks of kG frames), at most
+constexpr int kFramesPerCta = 16;      // k_emit / k_grad: 4 warps x 4 frames
 
 enum : int { UTT_INFEASIBLE = 1, UTT_BAD_LABEL = 2, UTT_LEN_CLAMPED = 4 };
 enum : int { DT_I32 = 0, DT_I64 = 1, DT_F32 = 2, DT_F64 = 3 };
@@ -56,10 +61,13 @@ struct Workspace {        // carved out of the caller's workspace by the host (c
     int* nxt;                         // (B, Lp) next position with the same label, or -1
     int* first;                       // (B, Lp) 1 when no earlier position has this label
     float2* fr;                       // (B, T) {row max, log2 sum exp2((x-max)*log2e)}
-    int2* E;                          // (B, T, W) split emissions {mantissa bits, exponent}: col 0 blank, col j label j
-    int4* hA;                         // (B, T, HP) alpha  {blank m, blank e, label m, label e}
-    int4* hB;                         // (B, T, HP) beta' in the reversed walker's coordinates
-    int Lp, W, HP;
+    double* E;                        // (B, NB, W, 8) emissions exp(x - rowmax) of frame block n = t / 8, frame-minor:
+                                      //   dense -> column v; else column 0 blank, column j label j
+    double2* hA;                      // (B, NB, NW, 8, PW) alpha_t {blank, label} of each state pair, relative to oA
+    double2* hB;                      // same for beta'_t in the reversed walker's pair coordinates, relative to oB
+    int2* oA;                         // (B, NB, NW*PW) exponent offsets {blank, label} valid for frame block n
+    int2* oB;
+    int Lp, W, NB, dense, P, NW;      // PW = 32*P pairs per walker warp
 };
 
 __device__ __forceinline__ long long load_as_int(const void* p, int dtype, long long i) {
@@ -74,9 +82,6 @@ __device__ __forceinline__ long long load_as_int(const void* p, int dtype, long 
 __device__ __forceinline__ float fast_ex2(float x) {
     float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
 }
-__device__ __forceinline__ float fast_lg2(float x) {
-    float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
-}
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -88,37 +93,37 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// m * 2^max(d, kDClamp) by adding to the exponent field.  Valid because every mantissa in
-// flight is a positive normal float >= 2^-17 (see the invariant in k_walk) and d <= 0.
-__device__ __forceinline__ float xscale(float m, int d) {
-    d = max(d, kDClamp);
-    return __int_as_float(__float_as_int(m) + d * (1 << 23));
+// ---- fp64 exponent-field helpers ------------------------------------------------------
+__device__ __forceinline__ int dexp11(double v) { return (__double2hiint(v) >> 20) & 0x7ff; }   // biased
+__device__ __forceinline__ int dexp(double v) { return dexp11(v) - 1023; }
+__device__ __forceinline__ double dmant(double v) {            // v with its exponent replaced by 0: [1,2)
+    return __hiloint2double((__double2hiint(v) & 0x000fffff) | 0x3ff00000, __double2loint(v));
 }
-
-// Same, but exactly 0 below 2^-64 (used off the critical chain, where "zero" states must
-// not leak into a frame's normaliser).
+// 2^d, exactly 0 for d <= -1023, 2^1023 for d >= 1023
+__device__ __forceinline__ double pow2c(int d) {
+    d = min(max(d, -1023), 1023);
+    return __hiloint2double((d + 1023) << 20, 0);
+}
+__device__ __forceinline__ double shfl_up_f64(double v) {
+    return __hiloint2double(__shfl_up_sync(0xffffffffu, __double2hiint(v), 1),
+                            __shfl_up_sync(0xffffffffu, __double2loint(v), 1));
+}
+// float m * 2^d, exactly 0 below 2^-64 (m is a positive normal float, d <= a few)
 __device__ __forceinline__ float xscale0(float m, int d) {
     return d < -64 ? 0.0f : __int_as_float(__float_as_int(m) + d * (1 << 23));
 }
 
-// log2-probability -> (mantissa in [2^-1/2, 2^1/2], integer exponent); one MUFU.EX2.
-__device__ __forceinline__ void split_log2(float l, float& m, int& e) {
-    const float magic = 12582912.0f;            // 1.5 * 2^23: rounds to nearest integer
-    l = fmaxf(l, kMinLog2);
-    float r = l + magic;
-    e = __float_as_int(r) - __float_as_int(magic);
-    m = fast_ex2(l - (r - magic));
-}
-
 // ---------------------------------------------------------------------------------------
-// k_emit<VEC>: grid (ceil(T/16), B), block 128, dynamic smem Lp ints; one warp per frame.
+// k_emit<VEC>: grid (ceil(NB/4), B), block 128, dynamic smem Lp ints; one warp per block of
+// kG = 8 frames.
 //
 // Rows a3/a4/a5 of SURVEY 8a in one launch: every CTA derives its utterance's lengths and
-// int labels itself (no dependency on a prepare kernel), computes {row max, log2 sum} per
-// frame and writes the emission table E2[b][t][0..L_b] = split(log2 y_t(blank | l_j)) as
-// (mantissa, exponent) pairs, ready for the walkers.  CTA x == 0 of each utterance also
-// publishes the per-utterance metadata (lengths, labels, repeats/feasibility, same-label
-// chains for the gradient scatter).
+// int labels itself; per frame {row max, log2 sum} (kept for the gradient's softmax); per
+// frame block the emission table in the frame-minor layout the walkers read with 128-bit
+// shared-memory loads: E[b][n][col][j] = exp(x_{8n+j}(v_col) - max_v x_{8n+j}(v)), i.e. the
+// softmax numerator -- the per-frame normaliser is common to all lattice states, cancels in
+// the posteriors and re-enters the loss as sum_t log2(sum).  CTA x == 0 of each utterance also
+// publishes the per-utterance metadata.
 // ---------------------------------------------------------------------------------------
 template <int VEC> struct VecT;
 template <> struct VecT<1> { using type = float; };
@@ -159,46 +164,62 @@ __global__ void __launch_bounds__(128) k_emit(Problem p, Workspace w) {
         __syncthreads();
         L = s_L;
     }
-    int bad = 0;
-    for (int j = tid; j < L; j += 128) {
-        long long v = load_as_int(p.labels, p.label_dtype, b * p.lst_b + j * p.lst_l);
-        if (v < 0 || v >= p.V || v == p.blank) bad = 1;
-        slab[j] = (int)(v < 0 ? 0 : (v >= p.V ? p.V - 1 : v));
+    if (!w.dense || blockIdx.x == 0) {
+        int bad = 0;
+        for (int j = tid; j < L; j += 128) {
+            long long v = load_as_int(p.labels, p.label_dtype, b * p.lst_b + j * p.lst_l);
+            if (v < 0 || v >= p.V || v == p.blank) bad = 1;
+            slab[j] = (int)(v < 0 ? 0 : (v >= p.V ? p.V - 1 : v));
+        }
+        if (bad) atomicOr(&s_flags, UTT_BAD_LABEL);
+        __syncthreads();
     }
-    if (bad) atomicOr(&s_flags, UTT_BAD_LABEL);
-    __syncthreads();
 
     const int nvec = p.V / VEC;
-#pragma unroll 1
-    for (int i = 0; i < kFramesPerCta / 4; ++i) {
-        const int t = blockIdx.x * kFramesPerCta + warp * (kFramesPerCta / 4) + i;
-        if (t >= Tb) break;
-        const float* row = p.logits + b * p.st_b + t * p.st_t;
-        const V_t* rowv = reinterpret_cast<const V_t*>(row);
-        float mx = -INFINITY;
-        for (int k = lane; k < nvec; k += 32) {
-            float x[VEC]; vec_get<VEC>(__ldg(rowv + k), x);
+    const int blk = blockIdx.x * 4 + warp, t0 = blk * kG;
+    if (t0 < Tb) {
+        float mxs[kG];
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) mx = fmaxf(mx, x[j]);
-        }
-        for (int v = nvec * VEC + lane; v < p.V; v += 32) mx = fmaxf(mx, __ldg(row + v));
-        mx = warp_max(mx);
-        float sum = 0.0f;
-        for (int k = lane; k < nvec; k += 32) {          // second pass hits L1
-            float x[VEC]; vec_get<VEC>(__ldg(rowv + k), x);
+        for (int j = 0; j < kG; ++j) {
+            const int t = t0 + j;
+            mxs[j] = 0.0f;
+            if (t >= Tb) continue;
+            const float* row = p.logits + b * p.st_b + t * p.st_t;
+            const V_t* rowv = reinterpret_cast<const V_t*>(row);
+            float mx = -INFINITY;
+            for (int k = lane; k < nvec; k += 32) {
+                float x[VEC]; vec_get<VEC>(__ldg(rowv + k), x);
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) sum += fast_ex2((x[j] - mx) * kLog2e);
+                for (int i = 0; i < VEC; ++i) mx = fmaxf(mx, x[i]);
+            }
+            for (int v = nvec * VEC + lane; v < p.V; v += 32) mx = fmaxf(mx, __ldg(row + v));
+            mx = warp_max(mx);
+            float sum = 0.0f;
+            for (int k = lane; k < nvec; k += 32) {          // second pass hits L1
+                float x[VEC]; vec_get<VEC>(__ldg(rowv + k), x);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) sum += fast_ex2((x[i] - mx) * kLog2e);
+            }
+            for (int v = nvec * VEC + lane; v < p.V; v += 32) sum += fast_ex2((__ldg(row + v) - mx) * kLog2e);
+            sum = warp_sum(sum);
+            if (lane == 0) w.fr[(size_t)b * p.T + t] = make_float2(mx, log2f(sum));
+            mxs[j] = mx;
         }
-        for (int v = nvec * VEC + lane; v < p.V; v += 32) sum += fast_ex2((__ldg(row + v) - mx) * kLog2e);
-        sum = warp_sum(sum);
-        const float lg2s = log2f(sum);
-        if (lane == 0) w.fr[(size_t)b * p.T + t] = make_float2(mx, lg2s);
-        int2* e = w.E + ((size_t)b * p.T + t) * w.W;
-        for (int j = lane; j <= L; j += 32) {
-            const int v = j == 0 ? p.blank : slab[j - 1];
-            float m; int ex;
-            split_log2(fmaf(__ldg(row + v) - mx, kLog2e, -lg2s), m, ex);
-            e[j] = make_int2(__float_as_int(m), ex);
+        const int ncol = w.dense ? p.V : L + 1;
+        double* eblk = w.E + ((size_t)b * w.NB + blk) * w.W * kG;
+        const float* rows = p.logits + b * p.st_b + (long long)t0 * p.st_t;
+        for (int col = lane; col < ncol; col += 32) {
+            const int v = w.dense ? col : (col == 0 ? p.blank : slab[col - 1]);
+            double y[kG];
+#pragma unroll
+            for (int j = 0; j < kG; ++j)
+                y[j] = t0 + j < Tb ? (double)fast_ex2(fmaxf((__ldg(rows + j * p.st_t + v) - mxs[j]) * kLog2e, kMinLog2)) : 0.0;
+            // 16-byte chunk c of a column sits at position c ^ ((col >> 1) & 3): eight lanes reading
+            // the same frames of eight different columns then hit eight different bank groups
+            double2* dst = reinterpret_cast<double2*>(eblk + (size_t)col * kG);
+            const int sx = (col >> 1) & 3;
+#pragma unroll
+            for (int j = 0; j < kG; j += 2) dst[(j / 2) ^ sx] = make_double2(y[j], y[j + 1]);
         }
     }
 
@@ -239,7 +260,7 @@ __global__ void __launch_bounds__(128) k_emit(Problem p, Workspace w) {
 }
 
 // ---------------------------------------------------------------------------------------
-// mbarrier / TMA (1-D bulk copy) helpers
+// mbarrier / TMA (1-D bulk copy) / shared-memory helpers
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -266,19 +287,27 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ int4 lds128_volatile(uint32_t addr) {
-    int4 v;
-    asm volatile("ld.volatile.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-    return v;
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr)); return v;
 }
-__device__ __forceinline__ void sts128_volatile(uint32_t addr, int4 v) {
-    asm volatile("st.volatile.shared.v4.s32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+__device__ __forceinline__ void sts_f64(uint32_t addr, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
-__device__ __forceinline__ int lds32_volatile(uint32_t addr) {
-    int v; asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v;
+__device__ __forceinline__ int lds_acquire(uint32_t addr) {
+    int v; asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v;
 }
-__device__ __forceinline__ void sts32_volatile(uint32_t addr, int v) {
-    asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+__device__ __forceinline__ void sts_release(uint32_t addr, int v) {
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ int lds_relaxed(uint32_t addr) {
+    int v; asm volatile("ld.relaxed.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v;
+}
+__device__ __forceinline__ void sts_s32(uint32_t addr, int v) {
+    asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ double2 lds_v2f64(uint32_t addr) {
+    double2 v; asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr)); return v;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -290,32 +319,40 @@ __device__ __forceinline__ void sts32_volatile(uint32_t addr, int v) {
 // is exactly the beta recursion -- and stores the sum BEFORE the emission is applied
 // (beta'_t), so that  sum_s alpha_t(s) beta'_t(S-1-s) = P(l|x)  for every t.
 //
-// Number format: value = m * 2^e, m fp32, e int32.  Invariants between renormalisations
-// (every block of KB <= 16 steps): emission mantissas are in [2^-1/2, 2^1/2]; a state's new
-// mantissa is >= 2^-1/2 times the mantissa of the term with the largest exponent and
-// <= 3 * 2^1/2 times the largest term, so with m in [1,2) after a renormalisation m stays in
-// [2^-8, 2^35] -- always a normal fp32, which xscale() relies on.  "Zero" is (1.0, kZeroE):
-// it never wins the max and enters sums scaled by 2^-100.  States beyond the utterance's
-// lattice are not masked: probability only flows towards higher states, so whatever they
-// hold never reaches a valid state, the loss or the stored history.
+// Number format.  A state's value is  v * 2^e : v an fp64 held in a register, e an int32
+// "offset" that is constant between renormalisations.  One step is, per pair,
+//     sb = prev*fb + b          sl = prev*fls + (b*flb + l)        b' = sb*y_blank   l' = sl*y_label
+// (5 FP64 ops) where prev is the neighbouring label state (warp shuffle) and fb, fls, flb are
+// the cached powers of two 2^(e_source - e_destination) (fls = 0 where the skip transition is
+// not allowed).  Emissions are in [2^-100, 1], so in one group of kG = 8 steps a value
+// shrinks by at most 2^-800 and grows by at most 3^8 * 2^(8 kD): it cannot leave the fp64
+// range when it starts a group within 2^+-kDrift of its offset.  At a group boundary a warp
+// renormalises only if some state drifted past 2^+-kDrift or its left neighbour's offsets
+// changed; otherwise the boundary costs one vote.  Renormalising moves every state's exponent
+// into its offset; if there are exactly-zero states (beyond the wavefront) or neighbouring
+// offsets more than 2^kD apart, a max-plus scan with decay kD per pair keeps every cached
+// factor <= 2^kD and gives the zero states the offset of the front.
+// States beyond the utterance's lattice are not masked: probability only flows towards higher
+// states, so whatever they hold never reaches a valid state, the loss or the stored history.
 //
-// Execution: NW walker warps + 1 producer warp; the step loop has NO CTA barrier and, in
-// full groups of 8 steps, no branch.
-//   * producer warp: streams E2 blocks (KB = 8 or 16 frames) into a shared-memory ring with
-//     cp.async.bulk (TMA) + full/empty mbarriers;
-//   * a single in-order warp per scheduler pays for every instruction and every branch, so
-//     steps run in groups of 8, fully unrolled: emission and neighbour loads are issued one
-//     step ahead, all control (ring hand-over, back-pressure, renormalisation) sits between
-//     groups;
+// Execution: NW walker warps + 1 producer warp; the step loop has NO CTA barrier.
+//   * producer warp: streams E frame blocks (kG frames, frame-minor) into a shared-memory ring
+//     with cp.async.bulk (TMA) + full/empty mbarriers; the alpha CTA's producer also sums
+//     log2(softmax denominator) over the utterance's frames for the loss;
+//   * walkers take a whole block of emissions into registers with 128-bit shared loads, run
+//     its 8 steps fully unrolled, and store the history with immediate offsets into the
+//     block's per-warp chunk;
 //   * walker warp w needs, per step, one value from warp w-1 (its last label state at the
-//     previous step).  Warp w-1 stores it into a 32-deep ring of (m, e) slots and, after
-//     each group, publishes its step count (release); warp w starts group j once warp w-1
-//     has finished group j (acquire).  Warps therefore run as a wavefront skewed by one group,
-//     each at the speed of its own dependent chain; warp w-1 never leads by more than two
-//     groups (ring depth).
+//     previous step).  Warp w-1 stores it into a 4-group-deep ring and, after each group,
+//     publishes its group count (release); warp w starts group j once warp w-1 has finished
+//     group j (acquire).  Warps therefore run as a wavefront skewed by one group, each at the
+//     speed of its own dependent chain.  Per group each warp also publishes {last label state,
+//     its offset, scan carry, front offset} for its right neighbour.
+// The beta walker's groups are aligned to the same frame blocks (its first group is the
+// partial one), so both histories and both offset tables are indexed by t / 8.
 // ---------------------------------------------------------------------------------------
 struct WalkArgs {
-    Workspace w; int T; int stages; float* loss; double* loss_sum;
+    Workspace w; int T; int stages; int blank; float* loss; double* loss_sum;
     long long* trace;      // debug only (scripts/ubench/walk_trace.cu); nullptr in the product
 };
 
@@ -326,49 +363,66 @@ struct WalkArgs {
 #define CTCB_TP(id) do { } while (0)
 #endif
 
-__device__ __forceinline__ int2 lds64(uint32_t addr) {
-    int2 v; asm volatile("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr)); return v;
-}
-__device__ __forceinline__ void sts64(uint32_t addr, int2 v) {
-    asm volatile("st.shared.v2.s32 [%0], {%1,%2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
-}
-__device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+struct HaloMeta { double lm; int el; int R; int F; int pad; };   // 24 bytes, 8-byte aligned
+constexpr int kHaloDepth = 4;                                    // groups a warp may lead its right neighbour by
 
-// G = steps per group = frames per emission block (8 or 16); the halo ring holds 2 groups.
-template <int P, int NW, int G, int DIR, bool HIST>
+__host__ __device__ inline size_t walk_smem_bytes(int W, int NW, int stages) {
+    return (size_t)stages * kG * W * sizeof(double) + 2 * kMaxStages * sizeof(uint64_t) +
+           (size_t)NW * kHaloDepth * kG * sizeof(double) + (size_t)NW * kHaloDepth * sizeof(HaloMeta) +
+           (size_t)NW * sizeof(int) + 32;
+}
+
+template <int P, int NW, int DIR, bool HIST>
 __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_raw, int Tb, int Lb) {
+    constexpr int PW = 32 * P;
+    constexpr unsigned FULL = 0xffffffffu;
     const Workspace& w = a.w;
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = w.W, NS = a.stages;
-    const int NQ = (Tb + G - 1) / G;
-    const uint32_t row_bytes = (uint32_t)W * 8u;
-    const uint32_t stage_bytes = (uint32_t)G * row_bytes;
+    const int NQ = (Tb + kG - 1) / kG;              // frame blocks of this utterance
+    const int rlast = Tb - (NQ - 1) * kG;           // frames in the last block, 1..8
+    const uint32_t stage_bytes = (uint32_t)W * kG * 8u;
 
     const uint32_t ring = smem_u32(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * stage_bytes);
-    uint64_t* empty = full + kStages;
-    const uint32_t halo = smem_u32(empty + kStages);               // [NW][2G] int2
-    const uint32_t prog = halo + NW * 2 * G * 8;                   // [NW] int: steps completed
+    uint64_t* empty = full + kMaxStages;
+    const uint32_t halo = smem_u32(empty + kMaxStages);                          // [NW][4][kG] double
+    const uint32_t meta = halo + NW * kHaloDepth * kG * 8;                       // [NW][4] HaloMeta
+    const uint32_t prog = meta + NW * kHaloDepth * (uint32_t)sizeof(HaloMeta);   // [NW] int: groups completed
+    const uint32_t lsum = (prog + NW * 4 + 7u) & ~7u;                            // double, then an int flag
 
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        sts_s32(lsum + 8, 0);
     }
-    if (tid < NW) sts32_volatile(prog + tid * 4, 0);
+    if (tid < NW) sts_s32(prog + tid * 4, 0);
     __syncthreads();
 
-    const int2* Eb = w.E + (size_t)b * a.T * W;
     if (warp == NW) {                           // ---- producer warp ----
+        const double* Eb = w.E + (size_t)b * w.NB * W * kG;
+        auto issue = [&](int n, int st) {       // block of walker group n into ring stage st
+            const int blk = DIR ? NQ - 1 - n : n;
+            mbar_expect_tx(&full[st], stage_bytes);
+            tma_load_1d(smem_raw + (size_t)st * stage_bytes, Eb + (size_t)blk * W * kG, stage_bytes, &full[st]);
+        };
+        const int npro = min(NS, NQ);
+        if (lane == 0) for (int n = 0; n < npro; ++n) issue(n, n);
+        if (DIR == 0) {                         // sum_t log2(softmax denominator), fixed order
+            double s = 0.0;
+            for (int t = lane; t < Tb; t += 32) s += (double)w.fr[(size_t)b * a.T + t].y;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                s += __hiloint2double(__shfl_xor_sync(FULL, __double2hiint(s), o), __shfl_xor_sync(FULL, __double2loint(s), o));
+            }
+            if (lane == 0) { sts_f64(lsum, s); sts_release(lsum + 8, 1); }
+        }
         if (lane == 0) {
-            int st = 0, ph = 0;                 // ph = (n / NS) & 1; the stage's previous use is ph ^ 1
-            for (int n = 0; n < NQ; ++n) {      // block n covers walker steps [n*G, ...)
-                if (n >= NS) mbar_wait(&empty[st], ph ^ 1);
-                const int k0 = n * G, nf = min(G, Tb - k0);
-                const int t0 = DIR ? Tb - k0 - nf : k0;
-                const uint32_t bytes = (uint32_t)nf * row_bytes;
-                mbar_expect_tx(&full[st], bytes);
-                tma_load_1d(smem_raw + (size_t)st * stage_bytes, Eb + (size_t)t0 * W, bytes, &full[st]);
+            int st = 0, ph = 1;                 // first re-use of stage 0 waits for its first release
+            for (int n = npro; n < NQ; ++n) {
+                mbar_wait(&empty[st], ph ^ 1);
+                issue(n, st);
                 if (++st == NS) { st = 0; ph ^= 1; }
             }
         }
@@ -378,129 +432,234 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
     // ---- walker warps ----
     const int* lab = w.lab + (size_t)b * w.Lp;
     const int g0 = tid * P;
-    bool vb[P]; int skcap[P]; uint32_t coff[P];
+    const uint32_t bcoli = w.dense ? (uint32_t)a.blank : 0u;
+    const uint32_t bcol = bcoli * (kG * 8u), bsx = ((bcoli >> 1) & 3u) * 16u;
+    bool skip[P]; uint32_t ccol[P], csx[P];
 #pragma unroll
     for (int p = 0; p < P; ++p) {
         const int g = g0 + p;
         const bool vl = g < Lb;
-        vb[p] = g <= Lb;
         const int cur = vl ? (DIR ? lab[Lb - 1 - g] : lab[g]) : -1;
         const int prv = (vl && g >= 1) ? (DIR ? lab[Lb - g] : lab[g - 1]) : -2;
-        skcap[p] = (vl && g >= 1 && cur != prv) ? INT_MAX : kZeroE;   // pe2 = min(pe, skcap)
-        coff[p] = (uint32_t)(vl ? (DIR ? Lb - g : g + 1) : 0) * 8u;
+        skip[p] = vl && g >= 1 && cur != prv;
+        const uint32_t ci = vl ? (w.dense ? (uint32_t)cur : (uint32_t)(DIR ? Lb - g : g + 1)) : bcoli;
+        ccol[p] = ci * (kG * 8u); csx[p] = ((ci >> 1) & 3u) * 16u;      // column base, chunk swizzle (see k_emit)
     }
-    float bm[P], lm[P]; int be[P], le[P];
+    double bm[P], lm[P], fb[P], fls[P], flb[P]; int eb[P], el[P];
 #pragma unroll
-    for (int p = 0; p < P; ++p) { bm[p] = 1.0f; lm[p] = 1.0f; be[p] = kZeroE; le[p] = kZeroE; }
-    if (tid == 0) be[0] = 0;                    // virtual alpha_{-1} = delta(s = 0)
+    for (int p = 0; p < P; ++p) {
+        bm[p] = 0.0; lm[p] = 0.0; eb[p] = 0; el[p] = 0;
+        fb[p] = 1.0; flb[p] = 1.0; fls[p] = skip[p] ? 1.0 : 0.0;
+    }
+    if (tid == 0) bm[0] = 1.0;                  // virtual alpha_{-1} = delta(s = 0)
 
-    int4* hptr = nullptr;
-    long long hstep = 0;
+    double2* hist = nullptr; int2* offs = nullptr;
     if (HIST) {
-        int4* hist = (DIR ? w.hB : w.hA) + (size_t)b * a.T * w.HP;
-        hptr = hist + (size_t)(DIR ? Tb - 1 : 0) * w.HP + g0;
-        hstep = DIR ? -(long long)w.HP : (long long)w.HP;
+        hist = (DIR ? w.hB : w.hA) + (((size_t)b * w.NB * NW + warp) * kG) * PW + lane * P;
+        offs = (DIR ? w.oB : w.oA) + (size_t)b * w.NB * NW * PW + g0;
     }
 
     const bool has_left = NW > 1 && warp > 0, has_right = NW > 1 && warp < NW - 1;
     const bool pub = has_right && lane == 31;
-    const uint32_t my_halo = halo + warp * 2 * G * 8;
-    const uint32_t nb_halo = halo + (warp > 0 ? warp - 1 : 0) * 2 * G * 8;
+    const uint32_t my_halo = halo + warp * kHaloDepth * kG * 8;
+    const uint32_t nb_halo = halo + (warp > 0 ? warp - 1 : 0) * kHaloDepth * kG * 8;
+    const uint32_t my_meta = meta + warp * kHaloDepth * (uint32_t)sizeof(HaloMeta);
+    const uint32_t nb_meta = meta + (warp > 0 ? warp - 1 : 0) * kHaloDepth * (uint32_t)sizeof(HaloMeta);
     const uint32_t nb_prog = prog + (warp > 0 ? warp - 1 : 0) * 4, rt_prog = prog + (warp + 1 < NW ? warp + 1 : warp) * 4;
-    float hal_m = 1.0f; int hal_e = kZeroE;     // neighbour's state for the coming step
+    double pm = 0.0;                            // left neighbour's label state for the coming step (lane 0: left warp's)
+    int c_el = 0, c_R = 0, c_F = 0;             // left warp's meta as of my last renormalisation
+    int Rout = 0, Fout = 0;                     // my scan carry / front offset for the right warp
 
-    float ymb, yml[P]; int yeb, yel[P];         // emissions of the current step
-    auto lds_emis = [&](uint32_t row, float& mb, int& eb, float (&ml)[P], int (&el)[P]) {
-        int2 v = lds64(row);
-        mb = __int_as_float(v.x); eb = v.y;
-#pragma unroll
-        for (int p = 0; p < P; ++p) { v = lds64(row + coff[p]); ml[p] = __int_as_float(v.x); el[p] = v.y; }
-    };
-
-    // one recursion step.  next_row: emission row of the next step; slot: halo slot of this step
-    auto step = [&](uint32_t next_row, uint32_t slot) {
-        float nmb, nml[P]; int neb, nel[P];
-        lds_emis(next_row, nmb, neb, nml, nel);
-        int2 hv = make_int2(0, 0);
-        if (has_left) hv = lds64(nb_halo + slot);
-        float nm = __shfl_up_sync(0xffffffffu, lm[P - 1], 1);
-        int ne = __shfl_up_sync(0xffffffffu, le[P - 1], 1);
-        if (lane == 0) { nm = hal_m; ne = hal_e; }
-#pragma unroll
-        for (int p = P - 1; p >= 0; --p) {
-            const float pm = p == 0 ? nm : lm[p - 1];
-            const int pe = p == 0 ? ne : le[p - 1];
-            const float obm = bm[p], olm = lm[p];
-            const int obe = be[p], ole = le[p];
-            const int Eb_ = max(obe, pe);
-            const float sb = xscale(obm, obe - Eb_) + xscale(pm, pe - Eb_);
-            const int pe2 = min(pe, skcap[p]);
-            const int El = max(max(ole, obe), pe2);
-            const float sl = xscale(olm, ole - El) + xscale(obm, obe - El) + xscale(pm, pe2 - El);
-            bm[p] = sb * ymb; be[p] = Eb_ + yeb;
-            lm[p] = sl * yml[p]; le[p] = El + yel[p];
-            if (HIST && vb[p]) {
-                if (DIR) hptr[p] = make_int4(__float_as_int(sb), Eb_, __float_as_int(sl), El);
-                else     hptr[p] = make_int4(__float_as_int(bm[p]), be[p], __float_as_int(lm[p]), le[p]);
-            }
-        }
-        if (HIST) hptr += hstep;
-        if (pub) sts64(my_halo + slot, make_int2(__float_as_int(lm[P - 1]), le[P - 1]));
-        if (has_left) { hal_m = __int_as_float(hv.x); hal_e = hv.y; }
-        ymb = nmb; yeb = neb;
-#pragma unroll
-        for (int p = 0; p < P; ++p) { yml[p] = nml[p]; yel[p] = nel[p]; }
-    };
-
-    const uint32_t row_inc = DIR ? (0u - row_bytes) : row_bytes;
     int st = 0, ph = 0;
     uint32_t stage_base = ring;
 #pragma unroll 1
     for (int n = 0; n < NQ; ++n) {
-        const int k0 = n * G, ns = min(G, Tb - k0), kend = k0 + ns;
+        const int blk = DIR ? NQ - 1 - n : n;
+        const int ns = blk == NQ - 1 ? rlast : kG;
+        const uint32_t par = (uint32_t)(n & (kHaloDepth - 1));
         CTCB_TP(0);
         // ---- between groups: everything that needs a branch ----
-        if (has_left) {                                         // left neighbour finished this group?
-            while (lds32_volatile(nb_prog) < kend) { }
-            fence_cta();
-        }
-        if (has_right) {                                        // do not lap the halo ring (2 groups deep)
-            while (lds32_volatile(rt_prog) < k0 - G) { }
-        }
+        if (has_left) { while (lds_acquire(nb_prog) < n + 1) { } }                    // left neighbour finished this group
+        if (has_right) { while (lds_relaxed(rt_prog) < n + 1 - kHaloDepth) { } }      // do not lap the halo ring
         CTCB_TP(1);
-        mbar_wait(&full[st], ph);
-        CTCB_TP(2);
-        const uint32_t row0 = stage_base + (DIR ? (uint32_t)(ns - 1) * row_bytes : 0u);
-        lds_emis(row0, ymb, yeb, yml, yel);
-        const uint32_t slot0 = (uint32_t)(n & 1) * (G * 8u);
-        CTCB_TP(3);
-        if (ns == G) {
+        // left neighbour's state for this group (written at ITS group-n boundary)
+        int m_el = 0, m_R = kZeroE, m_F = 0;
+        if (has_left) {
+            const uint32_t ma = nb_meta + par * (uint32_t)sizeof(HaloMeta);
+            const double hal = lds_f64(ma);
+            if (lane == 0) pm = hal;
+            m_el = lds_relaxed(ma + 8); m_R = lds_relaxed(ma + 12); m_F = lds_relaxed(ma + 16);
+        }
+        // renormalise?  (some state drifted past 2^+-kDrift, or the left neighbour's offsets moved)
+        bool trig = has_left && (m_el != c_el || m_R != c_R || m_F != c_F);
 #pragma unroll
-            for (int j = 0; j < G; ++j)
-                step(j + 1 < G ? row0 + (uint32_t)(j + 1) * row_inc : row0, slot0 + (uint32_t)j * 8u);
-        } else {
+        for (int p = 0; p < P; ++p) {
+            const unsigned xb = (unsigned)dexp11(bm[p]), xl = (unsigned)dexp11(lm[p]);
+            trig |= (xb != 0u && xb - (1023u - kDrift) > 2u * kDrift) || (xl != 0u && xl - (1023u - kDrift) > 2u * kDrift);
+        }
+        if (__any_sync(FULL, trig)) {
+            CTCB_TP(7);
+            c_el = m_el; c_R = m_R; c_F = m_F;
+            int natb[P], natl[P], am[P];
+            bool hard = false;
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                natb[p] = bm[p] != 0.0 ? eb[p] + dexp(bm[p]) : kZeroE;
+                natl[p] = lm[p] != 0.0 ? el[p] + dexp(lm[p]) : kZeroE;
+                am[p] = max(natb[p], natl[p]);
+                hard |= bm[p] == 0.0 || lm[p] == 0.0 || natb[p] - kD > natl[p];
+            }
+            {
+                int pa = __shfl_up_sync(FULL, am[P - 1], 1);
+                if (lane == 0) pa = m_R;
+#pragma unroll
+                for (int p = 0; p < P; ++p) { hard |= pa - kD > min(natb[p], natl[p]); pa = am[p]; }
+            }
+            if (__any_sync(FULL, hard)) {
+                // R(g) = max(a(g), R(g-1) - kD): in the lane, then across lanes (decay P*kD per lane)
+                int x = am[0], anymax = am[0];
+#pragma unroll
+                for (int p = 1; p < P; ++p) { x = max(am[p], x - kD); anymax = max(anymax, am[p]); }
+#pragma unroll
+                for (int i = 1; i < 32; i <<= 1) {
+                    const int y = __shfl_up_sync(FULL, x, i);
+                    if (lane >= i) x = max(x, y - i * P * kD);
+                }
+                x = max(max(x, m_R - (lane + 1) * P * kD), 2 * kZeroE);
+                int Rp = __shfl_up_sync(FULL, x, 1);
+                if (lane == 0) Rp = m_R;
+                const unsigned nz = __ballot_sync(FULL, anymax > kZeroE);
+                const int fl = nz ? 31 - __clz(nz) : -1;            // lane of the wavefront's last nonzero pair
+                int F = m_F;
+                if (nz) F = __shfl_sync(FULL, x, fl);
+                Fout = F;
+                Rout = (nz >> 31) ? __shfl_sync(FULL, x, 31) : kZeroE;
+                const bool beyond = lane > fl;                      // exactly-zero states beyond the front take F
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    const int base = Rp - kD;
+                    const int zoff = beyond ? F : base;
+                    const int neb = natb[p] > kZeroE ? max(natb[p], base) : zoff;
+                    const int nel = natl[p] > kZeroE ? max(natl[p], max(natb[p] - kD, base)) : (natb[p] > kZeroE ? neb : zoff);
+                    bm[p] *= pow2c(eb[p] - neb);
+                    lm[p] *= pow2c(el[p] - nel);
+                    eb[p] = neb; el[p] = nel;
+                    Rp = max(max(am[p], Rp - kD), 2 * kZeroE);
+                }
+            } else {
+                // plain drift: every exponent moves into its offset, no constraint is active
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    bm[p] = dmant(bm[p]); lm[p] = dmant(lm[p]);
+                    eb[p] = natb[p]; el[p] = natl[p];
+                }
+                Rout = __shfl_sync(FULL, am[P - 1], 31);
+                Fout = Rout;
+            }
+            {                                                   // values moved: refresh the pre-shuffled neighbour
+                const double q = shfl_up_f64(lm[P - 1]);
+                if (lane != 0) pm = q;
+            }
+            int ep = __shfl_up_sync(FULL, el[P - 1], 1);
+            if (lane == 0) ep = has_left ? m_el : eb[0];
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                fb[p] = pow2c(ep - eb[p]);
+                fls[p] = skip[p] ? pow2c(ep - el[p]) : 0.0;
+                flb[p] = pow2c(eb[p] - el[p]);
+                ep = el[p];
+            }
+        }
+        if (pub) {                                              // my state for the right neighbour's group n
+            const uint32_t ma = my_meta + par * (uint32_t)sizeof(HaloMeta);
+            sts_f64(ma, lm[P - 1]);
+            sts_s32(ma + 8, el[P - 1]); sts_s32(ma + 12, Rout); sts_s32(ma + 16, Fout);
+        }
+        double2* hch = nullptr;
+        if (HIST) {
+            int2* o = offs + (size_t)blk * NW * PW;
+#pragma unroll
+            for (int p = 0; p < P; ++p) o[p] = make_int2(eb[p], el[p]);
+            hch = hist + (size_t)blk * NW * kG * PW;
+        }
+        CTCB_TP(2);
+        mbar_wait(&full[st], ph);
+        // halo slot of walking-order step s: dir 0 s = j, dir 1 s = ns-1-j
+        const uint32_t hs_my = my_halo + par * (kG * 8u) + (DIR ? (uint32_t)(ns - 1) * 8u : 0u);
+        const uint32_t hs_nb = nb_halo + par * (kG * 8u) + (DIR ? (uint32_t)(ns - 1) * 8u : 0u);
+        // one recursion step on frame j of the block; so = halo slot offset of this step
+        // The shuffle that feeds pair 0 is issued one step AHEAD, right after the lane's last pair
+        // is updated: a warp issues in order, so a shuffle consumed in the step that issues it
+        // would expose its full latency on every step.
+        // A warp issues in order, so the source is written level by level (all pairs' first
+        // FMAs, then the second, then the emission products): three dependent FP64 levels per step.
+        auto step = [&](int j, uint32_t so, double yb, const double (&yl)[P]) {
+            double hv = 0.0;
+            if (has_left) hv = lds_f64(hs_nb + so);
+            double t0[P], sb[P], sl[P];
+#pragma unroll
+            for (int p = P - 1; p >= 0; --p) {
+                const double prev = p == 0 ? pm : lm[p - 1];
+                t0[p] = fma(bm[p], flb[p], lm[p]);
+                sb[p] = fma(prev, fb[p], bm[p]);
+            }
+#pragma unroll
+            for (int p = P - 1; p >= 0; --p) {
+                const double prev = p == 0 ? pm : lm[p - 1];
+                sl[p] = fma(prev, fls[p], t0[p]);
+            }
+#pragma unroll
+            for (int p = P - 1; p >= 0; --p) lm[p] = sl[p] * yl[p];
+            const double pm_next = shfl_up_f64(lm[P - 1]);
+            if (pub) sts_f64(hs_my + so, lm[P - 1]);
+#pragma unroll
+            for (int p = P - 1; p >= 0; --p) {
+                bm[p] = sb[p] * yb;
+                if (HIST) hch[j * PW + p] = DIR ? make_double2(sb[p], sl[p]) : make_double2(bm[p], lm[p]);
+            }
+            pm = pm_next;
+            if (lane == 0) pm = hv;
+        };
+        if (ns == kG) {
+            // the block's emissions: 8 frames of the blank column and of each of my label columns
+            double yb[kG], yl[kG][P];
+#pragma unroll
+            for (int j = 0; j < kG; j += 2) {
+                const double2 v = lds_v2f64(stage_base + bcol + ((j * 8u) ^ bsx));
+                yb[j] = v.x; yb[j + 1] = v.y;
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    const double2 u = lds_v2f64(stage_base + ccol[p] + ((j * 8u) ^ csx[p]));
+                    yl[j][p] = u.x; yl[j + 1][p] = u.y;
+                }
+            }
+            CTCB_TP(3);
+#pragma unroll
+            for (int jj = 0; jj < kG; ++jj) {
+                const int j = DIR ? kG - 1 - jj : jj;           // frame within the block
+                step(j, DIR ? 0u - (uint32_t)j * 8u : (uint32_t)j * 8u, yb[j], yl[j]);
+            }
+        } else {                                                // the utterance's partial block (once per walker)
+            CTCB_TP(3);
 #pragma unroll 1
-            for (int j = 0; j < ns; ++j)
-                step(j + 1 < ns ? row0 + (uint32_t)(j + 1) * row_inc : row0, slot0 + (uint32_t)j * 8u);
+            for (int jj = 0; jj < ns; ++jj) {
+                const int j = DIR ? ns - 1 - jj : jj;
+                double yl1[P];
+                const uint32_t jo = (uint32_t)(j >> 1) * 16u, jl = (uint32_t)(j & 1) * 8u;
+                const double yb1 = lds_f64(stage_base + bcol + (jo ^ bsx) + jl);
+#pragma unroll
+                for (int p = 0; p < P; ++p) yl1[p] = lds_f64(stage_base + ccol[p] + (jo ^ csx[p]) + jl);
+                step(j, DIR ? 0u - (uint32_t)j * 8u : (uint32_t)j * 8u, yb1, yl1);
+            }
         }
         CTCB_TP(4);
         if (NW > 1) {                                           // publish: halo slots, then the count
             __syncwarp();
-            if (lane == 31) { fence_cta(); sts32_volatile(prog + warp * 4, kend); }
+            if (lane == 31) sts_release(prog + warp * 4, n + 1);
         }
         CTCB_TP(5);
-        // renormalise mantissas to [1,2), hand the ring stage back to the producer
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-            int bits = __float_as_int(bm[p]);
-            be[p] = max(be[p] + (bits >> 23) - 127, kZeroE);
-            bm[p] = __int_as_float((bits & 0x007fffff) | 0x3f800000);
-            bits = __float_as_int(lm[p]);
-            le[p] = max(le[p] + (bits >> 23) - 127, kZeroE);
-            lm[p] = __int_as_float((bits & 0x007fffff) | 0x3f800000);
-        }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[st]);
+        if (lane == 0) mbar_arrive(&empty[st]);                  // hand the ring stage back to the producer
         CTCB_TP(6);
         stage_base += stage_bytes;
         if (++st == NS) { st = 0; ph ^= 1; stage_base = ring; }
@@ -508,18 +667,14 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
 
     if (DIR == 0) {
         // P(l|x) = alpha_{T-1}(2L) + alpha_{T-1}(2L-1) = the blank sum of slot L_b at a
-        // virtual step T_b (hal_* already holds the neighbour's state after step T_b-1).
-        float nm = __shfl_up_sync(0xffffffffu, lm[P - 1], 1);
-        int ne = __shfl_up_sync(0xffffffffu, le[P - 1], 1);
-        if (lane == 0) { nm = hal_m; ne = hal_e; }
+        // virtual step T_b (pm already holds the neighbour's state after step T_b-1).
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             if (g0 + p == Lb) {
-                const float pm = p == 0 ? nm : lm[p - 1];
-                const int pe = p == 0 ? ne : le[p - 1];
-                const int Eb_ = max(be[p], pe);
-                const float sb = xscale(bm[p], be[p] - Eb_) + xscale(pm, pe - Eb_);
-                const double nll = -kLn2 * ((double)Eb_ + (double)log2f(sb));
+                const double prev = p == 0 ? pm : lm[p - 1];
+                const double sb = fma(prev, fb[p], bm[p]);
+                while (lds_acquire(lsum + 8) == 0) { }
+                const double nll = -kLn2 * ((double)eb[p] + log2(sb) - lds_f64(lsum));
                 a.loss[b] = (float)nll;
                 if (a.loss_sum) atomicAdd(a.loss_sum, nll);
             }
@@ -527,14 +682,14 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
     }
 }
 
-template <int P, int NW, int G, bool HIST>
+template <int P, int NW, bool HIST>
 __global__ void __launch_bounds__((NW + 1) * 32) k_walk(WalkArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int b = blockIdx.x;
     const int flags = a.w.flags[b], Tb = a.w.Tb[b], Lb = a.w.Lb[b];
     if (flags & UTT_INFEASIBLE) return;
-    if (blockIdx.y == 0) walk_dir<P, NW, G, 0, HIST>(a, smem_raw, Tb, Lb);
-    else                 walk_dir<P, NW, G, 1, HIST>(a, smem_raw, Tb, Lb);
+    if (blockIdx.y == 0) walk_dir<P, NW, 0, HIST>(a, smem_raw, Tb, Lb);
+    else                 walk_dir<P, NW, 1, HIST>(a, smem_raw, Tb, Lb);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -555,17 +710,31 @@ __device__ __forceinline__ void zero_row(float* row, int V, int lane) {
     for (int v = nvec * VEC + lane; v < V; v += 32) row[v] = 0.0f;
 }
 
+// weight (mantissa product as float in [1,4), total exponent) of alpha*beta' for one state
+__device__ __forceinline__ void state_weight(double av, int ao, double bv, int bo, float& wgt, int& e) {
+    if (av == 0.0 || bv == 0.0) { wgt = 0.0f; e = INT_MIN / 2; return; }
+    wgt = __double2float_rn(dmant(av) * dmant(bv));
+    e = dexp(av) + dexp(bv) + ao + bo;
+}
+
+// One frame's view of a walker history: pair g lives in warp chunk g / PW at g % PW.
+struct FrameHist {
+    const double2* h; const int2* o; int lgPW, chunk;    // chunk = kG * PW
+    __device__ __forceinline__ double2 val(int g) const { return h[(g >> lgPW) * chunk + (g & ((1 << lgPW) - 1))]; }
+    __device__ __forceinline__ int2 off(int g) const { return o[g]; }
+};
+
 // alpha history of pair g and beta' history re-expressed in the forward pair coordinates:
 // blank of pair g <-> reversed-walker blank of slot L-g; label of pair g <-> reversed-walker
 // label of slot L-1-g.
-__device__ __forceinline__ void load_pair(const int4* A, const int4* Bh, int g, int Lb,
+__device__ __forceinline__ void load_pair(const FrameHist& A, const FrameHist& Bh, int g, int Lb,
                                           float& wb, int& eb, float& wl, int& el) {
-    const int4 av = A[g];
-    const int4 bb = Bh[Lb - g];
-    wb = __int_as_float(av.x) * __int_as_float(bb.x); eb = av.y + bb.y;
+    const double2 av = A.val(g); const int2 ao = A.off(g);
+    const double2 bb = Bh.val(Lb - g); const int2 bo = Bh.off(Lb - g);
+    state_weight(av.x, ao.x, bb.x, bo.x, wb, eb);
     if (g < Lb) {
-        const int4 bl = Bh[Lb - 1 - g];
-        wl = __int_as_float(av.z) * __int_as_float(bl.z); el = av.w + bl.w;
+        const double2 bl = Bh.val(Lb - 1 - g); const int2 blo = Bh.off(Lb - 1 - g);
+        state_weight(av.y, ao.y, bl.y, blo.y, wl, el);
     } else { wl = 0.0f; el = INT_MIN / 2; }
 }
 
@@ -583,6 +752,7 @@ __global__ void __launch_bounds__(128) k_grad(GradArgs a) {
     const int* nxt = w.nxt + (size_t)b * w.Lp;
     const int* fst = w.first + (size_t)b * w.Lp;
     const int nvec = p.V / VEC;
+    const int PW = 32 * w.P, lgPW = 31 - __clz(PW);
     constexpr int NCH = CH > 0 ? CH : 1;
 #pragma unroll 1
     for (int i = 0; i < kFramesPerCta / 4; ++i) {
@@ -590,8 +760,10 @@ __global__ void __launch_bounds__(128) k_grad(GradArgs a) {
         if (t >= p.T) break;
         float* grow = p.grad + b * p.gst_b + t * p.gst_t;
         if (t >= Tb || infeasible) { zero_row<VEC>(grow, p.V, lane); continue; }
-        const int4* A = w.hA + ((size_t)b * p.T + t) * w.HP;
-        const int4* Bh = w.hB + ((size_t)b * p.T + t) * w.HP;
+        const size_t blk = (size_t)b * w.NB + t / kG;
+        const size_t hoff = (blk * w.NW * kG + (t % kG)) * PW, ooff = blk * w.NW * PW;
+        const FrameHist A{w.hA + hoff, w.oA + ooff, lgPW, kG * PW};
+        const FrameHist Bh{w.hB + hoff, w.oB + ooff, lgPW, kG * PW};
         float zb = 0.0f, zl = 0.0f;
         if (CH > 0) {
             // single pass: products and exponents stay in registers
