@@ -113,7 +113,7 @@ Layout make_layout(int T, int B, int V, int Lmax, int need_grad) {
     l.off_nxt = take(sizeof(int) * (size_t)B * l.Lp);
     l.off_first = take(sizeof(int) * (size_t)B * l.Lp);
     l.off_fr = take(sizeof(float2) * (size_t)B * T);
-    l.off_E = take(sizeof(double) * (size_t)B * l.NB * l.W * ctcb::kG);
+    l.off_E = take(sizeof(double) * (size_t)B * l.NB * l.W * ctcb::kEC);
     if (need_grad) {
         l.off_hA = take(sizeof(double2) * (size_t)B * l.NB * ctcb::kG * pairs);
         l.off_hB = take(sizeof(double2) * (size_t)B * l.NB * ctcb::kG * pairs);
@@ -234,7 +234,6 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
     const ctcb::Problem dp = to_device_problem(p);
     const ctcb::Workspace w = carve(lay, workspace);
     static std::mutex mu;
-    const dim3 fgrid((p->T + ctcb::kFramesPerCta - 1) / ctcb::kFramesPerCta, p->B);
 
     if (phases & PH_FORWARD) {
         const WalkEntry* we = lay.walk;
@@ -251,12 +250,21 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
             std::lock_guard<std::mutex> lk(mu);
             CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(wfn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
-        const dim3 egrid((lay.NB + 3) / 4, p->B);
+        const dim3 egrid((lay.NB + 3) / 4 + 1, p->B);   // + the metadata CTA of each utterance
+        // NQ: vector loads per lane that hold one logits row in registers (0 = two-pass)
+        const int units = (p->V / vec + 31) / 32;
+        const int nq = units <= 1 ? 1 : units <= 2 ? 2 : units <= 4 ? 4 : units <= 8 ? 8 : units <= 16 ? 16 : 0;
+#define EMIT_LAUNCH(V_, Q_) ctcb::k_emit<V_, Q_><<<egrid, 128, esm, stream>>>(dp, w)
+#define EMIT_NQ(V_) switch (nq) { case 1: EMIT_LAUNCH(V_, 1); break; case 2: EMIT_LAUNCH(V_, 2); break; \
+                                  case 4: EMIT_LAUNCH(V_, 4); break; case 8: EMIT_LAUNCH(V_, 8); break;  \
+                                  case 16: EMIT_LAUNCH(V_, 16); break; default: EMIT_LAUNCH(V_, 0); break; }
         switch (vec) {
-            case 4: ctcb::k_emit<4><<<egrid, 128, esm, stream>>>(dp, w); break;
-            case 2: ctcb::k_emit<2><<<egrid, 128, esm, stream>>>(dp, w); break;
-            default: ctcb::k_emit<1><<<egrid, 128, esm, stream>>>(dp, w); break;
+            case 4: EMIT_NQ(4); break;
+            case 2: EMIT_NQ(2); break;
+            default: EMIT_NQ(1); break;
         }
+#undef EMIT_NQ
+#undef EMIT_LAUNCH
         mark(stream);
         ctcb::WalkArgs wa{w, p->T, stages, p->blank, p->loss, p->loss_sum, nullptr};
         wfn<<<dim3(p->B, need_grad ? 2 : 1), (we->NW + 1) * 32, smem, stream>>>(wa);
@@ -264,29 +272,29 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
     }
     if (phases & PH_BACKWARD) {
         ctcb::GradArgs ga{dp, w};
-        const size_t gsm = 4 * (size_t)lay.Lp * sizeof(float);
+        const size_t gsm = (3 + 4) * (size_t)lay.Lp * sizeof(float);
+        if (gsm > 200 * 1024) return fail(CTCB_UNSUPPORTED, "Lmax=%d too long for the gradient kernel", p->Lmax);
         int vec = pick_vec(p->logits, p->logits_stride_t, p->logits_stride_b, p->V);
         const int gvec = pick_vec(p->grad, p->grad_stride_t, p->grad_stride_b, p->V);
         if (gvec < vec) vec = gvec;
-        if (gsm > 48 * 1024) {      // only the generic (CH = 0) variants see label rows this long
-            std::lock_guard<std::mutex> lk(mu);
-            CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(ctcb::k_grad<1, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
-            CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(ctcb::k_grad<2, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
-            CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(ctcb::k_grad<4, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
-        }
         const int pairs = p->Lmax + 1;
         const int ch = pairs <= 32 ? 1 : pairs <= 64 ? 2 : pairs <= 128 ? 4 : pairs <= 256 ? 8 : pairs <= 512 ? 16 : 0;
-#define GRAD_LAUNCH(V_, C_) ctcb::k_grad<V_, C_><<<fgrid, 128, gsm, stream>>>(ga)
-#define GRAD_CH(V_) switch (ch) { case 1: GRAD_LAUNCH(V_, 1); break; case 2: GRAD_LAUNCH(V_, 2); break; \
-                                  case 4: GRAD_LAUNCH(V_, 4); break; case 8: GRAD_LAUNCH(V_, 8); break;  \
-                                  case 16: GRAD_LAUNCH(V_, 16); break; default: GRAD_LAUNCH(V_, 0); break; }
-        switch (vec) {
-            case 4: GRAD_CH(4); break;
-            case 2: GRAD_CH(2); break;
-            default: GRAD_CH(1); break;
-        }
+        const int units = (p->V / vec + 31) / 32;
+        const int xq = units <= 1 ? 1 : units <= 2 ? 2 : units <= 4 ? 4 : 0;
+        const dim3 ggrid((p->T + ctcb::kGradFrames - 1) / ctcb::kGradFrames, p->B);
+        using GradFn = void (*)(ctcb::GradArgs);
+        GradFn gfn = nullptr;
+#define GRAD_X(V_, C_) (xq == 1 ? ctcb::k_grad<V_, C_, 1> : xq == 2 ? ctcb::k_grad<V_, C_, 2> : xq == 4 ? ctcb::k_grad<V_, C_, 4> : ctcb::k_grad<V_, C_, 0>)
+#define GRAD_CH(V_) (ch == 1 ? GRAD_X(V_, 1) : ch == 2 ? GRAD_X(V_, 2) : ch == 4 ? GRAD_X(V_, 4) : ch == 8 ? GRAD_X(V_, 8) : \
+                     ch == 16 ? GRAD_X(V_, 16) : GRAD_X(V_, 0))
+        gfn = vec == 4 ? GRAD_CH(4) : vec == 2 ? GRAD_CH(2) : GRAD_CH(1);
 #undef GRAD_CH
-#undef GRAD_LAUNCH
+#undef GRAD_X
+        if (gsm > 48 * 1024) {
+            std::lock_guard<std::mutex> lk(mu);
+            CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(gfn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
+        }
+        gfn<<<ggrid, 128, gsm, stream>>>(ga);
         mark(stream);
     }
     CUDA_TRY(cudaGetLastError());

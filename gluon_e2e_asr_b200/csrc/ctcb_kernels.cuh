@@ -32,6 +32,8 @@
 namespace ctcb {
 
 constexpr int kG = 8;                  // walker steps per group (= frames per emission block)
+constexpr int kEC = 10;                // doubles per emission column: 8 frames + 16 bytes of padding, so that
+                                       // 128-bit shared loads of different columns spread over all banks
 constexpr int kD = 100;                // largest exponent step between neighbouring states
 constexpr int kDrift = 200;            // a state renormalises when it drifts past 2^+-kDrift
 constexpr int kZeroE = -(1 << 28);     // "natural exponent" of an exactly-zero state
@@ -39,7 +41,6 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr double kLn2 = 0.6931471805599453094;
 constexpr float kMinLog2 = -100.0f;    // clamp of one frame's log2-probability (7.9e-31)
 constexpr int kMaxStages = 16;         // emission ring depth (blocks of kG frames), at most
-constexpr int kFramesPerCta = 16;      // k_emit / k_grad: 4 warps x 4 frames
 
 enum : int { UTT_INFEASIBLE = 1, UTT_BAD_LABEL = 2, UTT_LEN_CLAMPED = 4 };
 enum : int { DT_I32 = 0, DT_I64 = 1, DT_F32 = 2, DT_F64 = 3 };
@@ -61,9 +62,9 @@ struct Workspace {        // carved out of the caller's workspace by the host (c
     int* nxt;                         // (B, Lp) next position with the same label, or -1
     int* first;                       // (B, Lp) 1 when no earlier position has this label
     float2* fr;                       // (B, T) {row max, log2 sum exp2((x-max)*log2e)}
-    double* E;                        // (B, NB, W, 8) emissions exp(x - rowmax) of frame block n = t / 8, frame-minor:
+    double* E;                        // (B, NB, W, kEC) emissions exp(x - rowmax) of frame block n = t / 8, frame-minor:
                                       //   dense -> column v; else column 0 blank, column j label j
-    double2* hA;                      // (B, NB, NW, 8, PW) alpha_t {blank, label} of each state pair, relative to oA
+    double2* hA;                      // (B, NB, 8, NW*PW) alpha_t {blank, label} of each state pair, relative to oA
     double2* hB;                      // same for beta'_t in the reversed walker's pair coordinates, relative to oB
     int2* oA;                         // (B, NB, NW*PW) exponent offsets {blank, label} valid for frame block n
     int2* oB;
@@ -122,7 +123,7 @@ __device__ __forceinline__ float xscale0(float m, int d) {
 // frame block the emission table in the frame-minor layout the walkers read with 128-bit
 // shared-memory loads: E[b][n][col][j] = exp(x_{8n+j}(v_col) - max_v x_{8n+j}(v)), i.e. the
 // softmax numerator -- the per-frame normaliser is common to all lattice states, cancels in
-// the posteriors and re-enters the loss as sum_t log2(sum).  CTA x == 0 of each utterance also
+// the posteriors and re-enters the loss as sum_t log2(sum).  one extra CTA per utterance
 // publishes the per-utterance metadata.
 // ---------------------------------------------------------------------------------------
 template <int VEC> struct VecT;
@@ -136,7 +137,15 @@ template <> __device__ __forceinline__ void vec_get<1>(const float& v, float (&o
 template <> __device__ __forceinline__ void vec_get<2>(const float2& v, float (&o)[2]) { o[0] = v.x; o[1] = v.y; }
 template <> __device__ __forceinline__ void vec_get<4>(const float4& v, float (&o)[4]) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
 
-template <int VEC>
+template <int VEC> __device__ __forceinline__ typename VecT<VEC>::type vec_fill(float v);
+template <> __device__ __forceinline__ float vec_fill<1>(float v) { return v; }
+template <> __device__ __forceinline__ float2 vec_fill<2>(float v) { return make_float2(v, v); }
+template <> __device__ __forceinline__ float4 vec_fill<4>(float v) { return make_float4(v, v, v, v); }
+
+// NQ = VEC-wide loads per lane that cover one logits row (power of two, <= 16): the rows of
+// F = 16/NQ frames (at most 8) are held in registers, so every global load of those frames is
+// in flight before the first reduction.  NQ = 0: rows too wide for registers, two passes.
+template <int VEC, int NQ>
 __global__ void __launch_bounds__(128) k_emit(Problem p, Workspace w) {
     using V_t = typename VecT<VEC>::type;
     extern __shared__ int slab[];                 // Lp ints: this utterance's labels
@@ -164,7 +173,8 @@ __global__ void __launch_bounds__(128) k_emit(Problem p, Workspace w) {
         __syncthreads();
         L = s_L;
     }
-    if (!w.dense || blockIdx.x == 0) {
+    const bool meta_cta = blockIdx.x == gridDim.x - 1;       // one extra CTA per utterance: metadata only
+    if (!w.dense || meta_cta) {
         int bad = 0;
         for (int j = tid; j < L; j += 128) {
             long long v = load_as_int(p.labels, p.label_dtype, b * p.lst_b + j * p.lst_l);
@@ -177,78 +187,122 @@ __global__ void __launch_bounds__(128) k_emit(Problem p, Workspace w) {
 
     const int nvec = p.V / VEC;
     const int blk = blockIdx.x * 4 + warp, t0 = blk * kG;
-    if (t0 < Tb) {
+    if (!meta_cta && t0 < Tb) {
         float mxs[kG];
+        const float* rows = p.logits + b * p.st_b + (long long)t0 * p.st_t;
+        if (NQ > 0) {
+            constexpr int NQ1 = NQ > 0 ? NQ : 1;
+            constexpr int F = NQ1 >= 16 ? 1 : (NQ1 >= 8 ? 2 : (NQ1 >= 4 ? 4 : 8));
 #pragma unroll
-        for (int j = 0; j < kG; ++j) {
-            const int t = t0 + j;
-            mxs[j] = 0.0f;
-            if (t >= Tb) continue;
-            const float* row = p.logits + b * p.st_b + t * p.st_t;
-            const V_t* rowv = reinterpret_cast<const V_t*>(row);
-            float mx = -INFINITY;
-            for (int k = lane; k < nvec; k += 32) {
-                float x[VEC]; vec_get<VEC>(__ldg(rowv + k), x);
+            for (int jf = 0; jf < kG; jf += F) {
+                V_t x[F][NQ1]; float xt[F];
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) mx = fmaxf(mx, x[i]);
+                for (int f = 0; f < F; ++f) {                   // every load of F frames in flight
+                    const bool valid = t0 + jf + f < Tb;
+                    const float* row = rows + (jf + f) * p.st_t;
+                    const V_t* rowv = reinterpret_cast<const V_t*>(row);
+#pragma unroll
+                    for (int q = 0; q < NQ1; ++q) {
+                        const int k = q * 32 + lane;
+                        x[f][q] = (valid && k < nvec) ? __ldg(rowv + k) : vec_fill<VEC>(-INFINITY);
+                    }
+                    xt[f] = (VEC > 1 && valid && nvec * VEC + lane < p.V) ? __ldg(row + nvec * VEC + lane) : -INFINITY;
+                }
+                float mx[F], sum[F];
+#pragma unroll
+                for (int f = 0; f < F; ++f) {
+                    float m = xt[f];
+#pragma unroll
+                    for (int q = 0; q < NQ1; ++q) { float e[VEC]; vec_get<VEC>(x[f][q], e);
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) m = fmaxf(m, e[i]); }
+                    mx[f] = m;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int f = 0; f < F; ++f) mx[f] = fmaxf(mx[f], __shfl_xor_sync(0xffffffffu, mx[f], o));
+#pragma unroll
+                for (int f = 0; f < F; ++f) {
+                    float sacc = fast_ex2((xt[f] - mx[f]) * kLog2e);          // ex2(-inf) = 0 for absent elements
+#pragma unroll
+                    for (int q = 0; q < NQ1; ++q) { float e[VEC]; vec_get<VEC>(x[f][q], e);
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) sacc += fast_ex2((e[i] - mx[f]) * kLog2e); }
+                    sum[f] = sacc;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int f = 0; f < F; ++f) sum[f] += __shfl_xor_sync(0xffffffffu, sum[f], o);
+#pragma unroll
+                for (int f = 0; f < F; ++f) {
+                    mxs[jf + f] = mx[f];
+                    if (lane == f && t0 + jf + f < Tb) w.fr[(size_t)b * p.T + t0 + jf + f] = make_float2(mx[f], log2f(sum[f]));
+                }
             }
-            for (int v = nvec * VEC + lane; v < p.V; v += 32) mx = fmaxf(mx, __ldg(row + v));
-            mx = warp_max(mx);
-            float sum = 0.0f;
-            for (int k = lane; k < nvec; k += 32) {          // second pass hits L1
-                float x[VEC]; vec_get<VEC>(__ldg(rowv + k), x);
+        } else {
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) sum += fast_ex2((x[i] - mx) * kLog2e);
+            for (int j = 0; j < kG; ++j) {
+                const int t = t0 + j;
+                mxs[j] = 0.0f;
+                if (t >= Tb) continue;
+                const float* row = rows + j * p.st_t;
+                const V_t* rowv = reinterpret_cast<const V_t*>(row);
+                float mx = -INFINITY;
+                for (int k = lane; k < nvec; k += 32) {
+                    float x[VEC]; vec_get<VEC>(__ldg(rowv + k), x);
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) mx = fmaxf(mx, x[i]);
+                }
+                for (int v = nvec * VEC + lane; v < p.V; v += 32) mx = fmaxf(mx, __ldg(row + v));
+                mx = warp_max(mx);
+                float sum = 0.0f;
+                for (int k = lane; k < nvec; k += 32) {          // second pass hits L1/L2
+                    float x[VEC]; vec_get<VEC>(__ldg(rowv + k), x);
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) sum += fast_ex2((x[i] - mx) * kLog2e);
+                }
+                for (int v = nvec * VEC + lane; v < p.V; v += 32) sum += fast_ex2((__ldg(row + v) - mx) * kLog2e);
+                sum = warp_sum(sum);
+                if (lane == 0) w.fr[(size_t)b * p.T + t] = make_float2(mx, log2f(sum));
+                mxs[j] = mx;
             }
-            for (int v = nvec * VEC + lane; v < p.V; v += 32) sum += fast_ex2((__ldg(row + v) - mx) * kLog2e);
-            sum = warp_sum(sum);
-            if (lane == 0) w.fr[(size_t)b * p.T + t] = make_float2(mx, log2f(sum));
-            mxs[j] = mx;
         }
         const int ncol = w.dense ? p.V : L + 1;
-        double* eblk = w.E + ((size_t)b * w.NB + blk) * w.W * kG;
-        const float* rows = p.logits + b * p.st_b + (long long)t0 * p.st_t;
+        double* eblk = w.E + ((size_t)b * w.NB + blk) * w.W * kEC;
         for (int col = lane; col < ncol; col += 32) {
             const int v = w.dense ? col : (col == 0 ? p.blank : slab[col - 1]);
-            double y[kG];
+            float xv[kG];
 #pragma unroll
-            for (int j = 0; j < kG; ++j)
-                y[j] = t0 + j < Tb ? (double)fast_ex2(fmaxf((__ldg(rows + j * p.st_t + v) - mxs[j]) * kLog2e, kMinLog2)) : 0.0;
-            // 16-byte chunk c of a column sits at position c ^ ((col >> 1) & 3): eight lanes reading
-            // the same frames of eight different columns then hit eight different bank groups
-            double2* dst = reinterpret_cast<double2*>(eblk + (size_t)col * kG);
-            const int sx = (col >> 1) & 3;
+            for (int j = 0; j < kG; ++j) xv[j] = t0 + j < Tb ? __ldg(rows + j * p.st_t + v) : 0.0f;
+            double2* dst = reinterpret_cast<double2*>(eblk + (size_t)col * kEC);
 #pragma unroll
-            for (int j = 0; j < kG; j += 2) dst[(j / 2) ^ sx] = make_double2(y[j], y[j + 1]);
+            for (int j = 0; j < kG; j += 2) {
+                const double y0 = t0 + j < Tb ? (double)fast_ex2(fmaxf((xv[j] - mxs[j]) * kLog2e, kMinLog2)) : 0.0;
+                const double y1 = t0 + j + 1 < Tb ? (double)fast_ex2(fmaxf((xv[j + 1] - mxs[j + 1]) * kLog2e, kMinLog2)) : 0.0;
+                dst[j / 2] = make_double2(y0, y1);
+            }
         }
     }
 
-    if (blockIdx.x != 0) return;
-    // ---- per-utterance metadata (one CTA per utterance) ----
+    if (!meta_cta) return;
+    // ---- per-utterance metadata ----
     int* lab = w.lab + (size_t)b * w.Lp;
     int* nxt = w.nxt + (size_t)b * w.Lp;
     int* fst = w.first + (size_t)b * w.Lp;
     int rep = 0;
+    // same-label chains: every thread scans for its position's next / previous occurrence
     for (int j = tid; j < L; j += 128) {
-        lab[j] = slab[j];
-        if (j > 0 && slab[j - 1] == slab[j]) ++rep;
+        const int v = slab[j];
+        lab[j] = v;
+        if (j > 0 && slab[j - 1] == v) ++rep;
+        int n = -1, f = 1;
+        for (int k = j + 1; k < L; ++k) if (slab[k] == v) { n = k; break; }
+        for (int k = j - 1; k >= 0; --k) if (slab[k] == v) { f = 0; break; }
+        nxt[j] = n; fst[j] = f;
     }
     if (rep) atomicAdd(&s_rep, rep);
-    // same-label chains: warp per position, ballot over 32 candidates at a time
-    for (int j = warp; j < L; j += 4) {
-        const int v = slab[j];
-        int f = 1, n = -1;
-        for (int c = 0; c <= (j >> 5) && f; ++c) {
-            const int k = c * 32 + lane;
-            if (__ballot_sync(0xffffffffu, k < j && slab[k] == v)) f = 0;
-        }
-        for (int c = j >> 5; c * 32 < L; ++c) {
-            const int k = c * 32 + lane;
-            const unsigned m = __ballot_sync(0xffffffffu, k > j && k < L && slab[k] == v);
-            if (m) { n = c * 32 + __ffs(m) - 1; break; }
-        }
-        if (lane == 0) { nxt[j] = n; fst[j] = f; }
-    }
     __syncthreads();
     if (tid == 0) {
         int flags = s_flags | lenflags;
@@ -367,7 +421,7 @@ struct HaloMeta { double lm; int el; int R; int F; int pad; };   // 24 bytes, 8-
 constexpr int kHaloDepth = 4;                                    // groups a warp may lead its right neighbour by
 
 __host__ __device__ inline size_t walk_smem_bytes(int W, int NW, int stages) {
-    return (size_t)stages * kG * W * sizeof(double) + 2 * kMaxStages * sizeof(uint64_t) +
+    return (size_t)stages * kEC * W * sizeof(double) + 2 * kMaxStages * sizeof(uint64_t) +
            (size_t)NW * kHaloDepth * kG * sizeof(double) + (size_t)NW * kHaloDepth * sizeof(HaloMeta) +
            (size_t)NW * sizeof(int) + 32;
 }
@@ -382,7 +436,7 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
     const int W = w.W, NS = a.stages;
     const int NQ = (Tb + kG - 1) / kG;              // frame blocks of this utterance
     const int rlast = Tb - (NQ - 1) * kG;           // frames in the last block, 1..8
-    const uint32_t stage_bytes = (uint32_t)W * kG * 8u;
+    const uint32_t stage_bytes = (uint32_t)W * kEC * 8u;
 
     const uint32_t ring = smem_u32(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * stage_bytes);
@@ -401,11 +455,11 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
     __syncthreads();
 
     if (warp == NW) {                           // ---- producer warp ----
-        const double* Eb = w.E + (size_t)b * w.NB * W * kG;
+        const double* Eb = w.E + (size_t)b * w.NB * W * kEC;
         auto issue = [&](int n, int st) {       // block of walker group n into ring stage st
             const int blk = DIR ? NQ - 1 - n : n;
             mbar_expect_tx(&full[st], stage_bytes);
-            tma_load_1d(smem_raw + (size_t)st * stage_bytes, Eb + (size_t)blk * W * kG, stage_bytes, &full[st]);
+            tma_load_1d(smem_raw + (size_t)st * stage_bytes, Eb + (size_t)blk * W * kEC, stage_bytes, &full[st]);
         };
         const int npro = min(NS, NQ);
         if (lane == 0) for (int n = 0; n < npro; ++n) issue(n, n);
@@ -432,9 +486,8 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
     // ---- walker warps ----
     const int* lab = w.lab + (size_t)b * w.Lp;
     const int g0 = tid * P;
-    const uint32_t bcoli = w.dense ? (uint32_t)a.blank : 0u;
-    const uint32_t bcol = bcoli * (kG * 8u), bsx = ((bcoli >> 1) & 3u) * 16u;
-    bool skip[P]; uint32_t ccol[P], csx[P];
+    const uint32_t bcol = (w.dense ? (uint32_t)a.blank : 0u) * (kEC * 8u);
+    bool skip[P]; uint32_t ccol[P];
 #pragma unroll
     for (int p = 0; p < P; ++p) {
         const int g = g0 + p;
@@ -442,8 +495,7 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
         const int cur = vl ? (DIR ? lab[Lb - 1 - g] : lab[g]) : -1;
         const int prv = (vl && g >= 1) ? (DIR ? lab[Lb - g] : lab[g - 1]) : -2;
         skip[p] = vl && g >= 1 && cur != prv;
-        const uint32_t ci = vl ? (w.dense ? (uint32_t)cur : (uint32_t)(DIR ? Lb - g : g + 1)) : bcoli;
-        ccol[p] = ci * (kG * 8u); csx[p] = ((ci >> 1) & 3u) * 16u;      // column base, chunk swizzle (see k_emit)
+        ccol[p] = vl ? (w.dense ? (uint32_t)cur : (uint32_t)(DIR ? Lb - g : g + 1)) * (kEC * 8u) : bcol;
     }
     double bm[P], lm[P], fb[P], fls[P], flb[P]; int eb[P], el[P];
 #pragma unroll
@@ -455,7 +507,7 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
 
     double2* hist = nullptr; int2* offs = nullptr;
     if (HIST) {
-        hist = (DIR ? w.hB : w.hA) + (((size_t)b * w.NB * NW + warp) * kG) * PW + lane * P;
+        hist = (DIR ? w.hB : w.hA) + (size_t)b * w.NB * kG * NW * PW + g0;
         offs = (DIR ? w.oB : w.oA) + (size_t)b * w.NB * NW * PW + g0;
     }
 
@@ -478,6 +530,14 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
         const int ns = blk == NQ - 1 ? rlast : kG;
         const uint32_t par = (uint32_t)(n & (kHaloDepth - 1));
         CTCB_TP(0);
+        // the block is in shared memory long before it is needed (the ring runs many blocks ahead)
+        mbar_wait(&full[st], ph);
+        // emissions of the group's first step; every later step's are requested one step ahead
+        const int j0 = DIR ? ns - 1 : 0;
+        double yb, yl[P];
+        yb = lds_f64(stage_base + bcol + (uint32_t)j0 * 8u);
+#pragma unroll
+        for (int p = 0; p < P; ++p) yl[p] = lds_f64(stage_base + ccol[p] + (uint32_t)j0 * 8u);
         // ---- between groups: everything that needs a branch ----
         if (has_left) { while (lds_acquire(nb_prog) < n + 1) { } }                    // left neighbour finished this group
         if (has_right) { while (lds_relaxed(rt_prog) < n + 1 - kHaloDepth) { } }      // do not lap the halo ring
@@ -490,13 +550,19 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
             if (lane == 0) pm = hal;
             m_el = lds_relaxed(ma + 8); m_R = lds_relaxed(ma + 12); m_F = lds_relaxed(ma + 16);
         }
-        // renormalise?  (some state drifted past 2^+-kDrift, or the left neighbour's offsets moved)
-        bool trig = has_left && (m_el != c_el || m_R != c_R || m_F != c_F);
+        // renormalise?  (some state drifted past 2^+-kDrift, or the left neighbour's offsets moved).
+        // Positive doubles order like their high words; an exact zero (high word 0) never triggers.
+        int bad = has_left ? ((m_el ^ c_el) | (m_R ^ c_R) | (m_F ^ c_F)) : 0;
+        {
+            constexpr unsigned LO = (1023u - kDrift) << 20, SPAN = (2u * kDrift + 1u) << 20;
 #pragma unroll
-        for (int p = 0; p < P; ++p) {
-            const unsigned xb = (unsigned)dexp11(bm[p]), xl = (unsigned)dexp11(lm[p]);
-            trig |= (xb != 0u && xb - (1023u - kDrift) > 2u * kDrift) || (xl != 0u && xl - (1023u - kDrift) > 2u * kDrift);
+            for (int p = 0; p < P; ++p) {
+                const unsigned hb = (unsigned)__double2hiint(bm[p]), hl = (unsigned)__double2hiint(lm[p]);
+                bad |= (int)(hb != 0u) & (int)(hb - LO >= SPAN);
+                bad |= (int)(hl != 0u) & (int)(hl - LO >= SPAN);
+            }
         }
+        const bool trig = bad != 0;
         if (__any_sync(FULL, trig)) {
             CTCB_TP(7);
             c_el = m_el; c_R = m_R; c_F = m_F;
@@ -580,10 +646,9 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
             int2* o = offs + (size_t)blk * NW * PW;
 #pragma unroll
             for (int p = 0; p < P; ++p) o[p] = make_int2(eb[p], el[p]);
-            hch = hist + (size_t)blk * NW * kG * PW;
+            hch = hist + (size_t)blk * kG * NW * PW;
         }
         CTCB_TP(2);
-        mbar_wait(&full[st], ph);
         // halo slot of walking-order step s: dir 0 s = j, dir 1 s = ns-1-j
         const uint32_t hs_my = my_halo + par * (kG * 8u) + (DIR ? (uint32_t)(ns - 1) * 8u : 0u);
         const uint32_t hs_nb = nb_halo + par * (kG * 8u) + (DIR ? (uint32_t)(ns - 1) * 8u : 0u);
@@ -593,8 +658,14 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
         // would expose its full latency on every step.
         // A warp issues in order, so the source is written level by level (all pairs' first
         // FMAs, then the second, then the emission products): three dependent FP64 levels per step.
-        auto step = [&](int j, uint32_t so, double yb, const double (&yl)[P]) {
-            double hv = 0.0;
+        // nj = frame of the NEXT step (its emissions are requested now), or -1 after the last one
+        auto step = [&](int j, int nj, uint32_t so) {
+            double hv = 0.0, nyb = 0.0, nyl[P];
+            if (nj >= 0) {
+                nyb = lds_f64(stage_base + bcol + (uint32_t)nj * 8u);
+#pragma unroll
+                for (int p = 0; p < P; ++p) nyl[p] = lds_f64(stage_base + ccol[p] + (uint32_t)nj * 8u);
+            }
             if (has_left) hv = lds_f64(hs_nb + so);
             double t0[P], sb[P], sl[P];
 #pragma unroll
@@ -615,41 +686,30 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
 #pragma unroll
             for (int p = P - 1; p >= 0; --p) {
                 bm[p] = sb[p] * yb;
-                if (HIST) hch[j * PW + p] = DIR ? make_double2(sb[p], sl[p]) : make_double2(bm[p], lm[p]);
+                if (HIST) hch[j * (NW * PW) + p] = DIR ? make_double2(sb[p], sl[p]) : make_double2(bm[p], lm[p]);
             }
             pm = pm_next;
             if (lane == 0) pm = hv;
-        };
-        if (ns == kG) {
-            // the block's emissions: 8 frames of the blank column and of each of my label columns
-            double yb[kG], yl[kG][P];
+            if (nj >= 0) {
+                yb = nyb;
 #pragma unroll
-            for (int j = 0; j < kG; j += 2) {
-                const double2 v = lds_v2f64(stage_base + bcol + ((j * 8u) ^ bsx));
-                yb[j] = v.x; yb[j + 1] = v.y;
-#pragma unroll
-                for (int p = 0; p < P; ++p) {
-                    const double2 u = lds_v2f64(stage_base + ccol[p] + ((j * 8u) ^ csx[p]));
-                    yl[j][p] = u.x; yl[j + 1][p] = u.y;
-                }
+                for (int p = 0; p < P; ++p) yl[p] = nyl[p];
             }
-            CTCB_TP(3);
+        };
+        CTCB_TP(3);
+        if (ns == kG) {
 #pragma unroll
             for (int jj = 0; jj < kG; ++jj) {
                 const int j = DIR ? kG - 1 - jj : jj;           // frame within the block
-                step(j, DIR ? 0u - (uint32_t)j * 8u : (uint32_t)j * 8u, yb[j], yl[j]);
+                const int nj = jj + 1 < kG ? (DIR ? j - 1 : j + 1) : -1;
+                step(j, nj, DIR ? 0u - (uint32_t)j * 8u : (uint32_t)j * 8u);
             }
         } else {                                                // the utterance's partial block (once per walker)
-            CTCB_TP(3);
 #pragma unroll 1
             for (int jj = 0; jj < ns; ++jj) {
                 const int j = DIR ? ns - 1 - jj : jj;
-                double yl1[P];
-                const uint32_t jo = (uint32_t)(j >> 1) * 16u, jl = (uint32_t)(j & 1) * 8u;
-                const double yb1 = lds_f64(stage_base + bcol + (jo ^ bsx) + jl);
-#pragma unroll
-                for (int p = 0; p < P; ++p) yl1[p] = lds_f64(stage_base + ccol[p] + (jo ^ csx[p]) + jl);
-                step(j, DIR ? 0u - (uint32_t)j * 8u : (uint32_t)j * 8u, yb1, yl1);
+                const int nj = jj + 1 < ns ? (DIR ? j - 1 : j + 1) : -1;
+                step(j, nj, DIR ? 0u - (uint32_t)j * 8u : (uint32_t)j * 8u);
             }
         }
         CTCB_TP(4);
@@ -693,7 +753,7 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_walk(WalkArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
-// k_grad<VEC,CH>: grid (ceil(T/16), B), block 128, one warp per frame.  Rows a7 (accumulation,
+// k_grad<VEC,CH,XQ>: grid (ceil(T/4), B), block 128, one warp per frame.  Rows a7 (accumulation,
 // gradient) and a8 (head-gradient scaling), written once in the caller's layout.
 // CH = register-resident chunks of 32 state pairs per lane (pairs <= 32*CH); CH = 0 is the
 // generic two-pass variant for longer label sequences.
@@ -717,10 +777,10 @@ __device__ __forceinline__ void state_weight(double av, int ao, double bv, int b
     e = dexp(av) + dexp(bv) + ao + bo;
 }
 
-// One frame's view of a walker history: pair g lives in warp chunk g / PW at g % PW.
+// One frame's view of a walker history: values and the frame block's exponent offsets per pair.
 struct FrameHist {
-    const double2* h; const int2* o; int lgPW, chunk;    // chunk = kG * PW
-    __device__ __forceinline__ double2 val(int g) const { return h[(g >> lgPW) * chunk + (g & ((1 << lgPW) - 1))]; }
+    const double2* h; const int2* o;
+    __device__ __forceinline__ double2 val(int g) const { return h[g]; }
     __device__ __forceinline__ int2 off(int g) const { return o[g]; }
 };
 
@@ -738,76 +798,112 @@ __device__ __forceinline__ void load_pair(const FrameHist& A, const FrameHist& B
     } else { wl = 0.0f; el = INT_MIN / 2; }
 }
 
-template <int VEC, int CH>
+constexpr int kGradFrames = 4;         // k_grad: one frame per warp
+
+// XQ = VEC-wide loads per lane that hold the frame's logits row in registers (issued before the
+// history loads so that one memory round trip covers both); 0 = row loaded when it is needed.
+template <int VEC, int CH, int XQ>
 __global__ void __launch_bounds__(128) k_grad(GradArgs a) {
     using V_t = typename VecT<VEC>::type;
     const Problem& p = a.p; const Workspace& w = a.w;
-    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int Tb = w.Tb[b], Lb = w.Lb[b];
     const bool infeasible = (w.flags[b] & UTT_INFEASIBLE) != 0;
     const float head = p.head ? p.head[b] : 1.0f;
-    extern __shared__ float gbuf_all[];
-    float* gbuf = gbuf_all + (size_t)warp * w.Lp;
-    const int* lab = w.lab + (size_t)b * w.Lp;
-    const int* nxt = w.nxt + (size_t)b * w.Lp;
-    const int* fst = w.first + (size_t)b * w.Lp;
+    extern __shared__ int gsm[];
+    int* s_lab = gsm; int* s_nxt = gsm + w.Lp; int* s_fst = gsm + 2 * w.Lp;
+    float* gbuf = reinterpret_cast<float*>(gsm + 3 * w.Lp) + (size_t)warp * w.Lp;
+    const int t = blockIdx.x * kGradFrames + warp;
+    const bool live = t < p.T && t < Tb && !infeasible;
     const int nvec = p.V / VEC;
-    const int PW = 32 * w.P, lgPW = 31 - __clz(PW);
+    constexpr int NXQ = XQ > 0 ? XQ : 1;
+    // everything that does not depend on the history is requested first
+    const float* xrow = p.logits + b * p.st_b + (long long)(t < p.T ? t : 0) * p.st_t;
+    const V_t* xv = reinterpret_cast<const V_t*>(xrow);
+    V_t xr[NXQ]; float2 fr = make_float2(0.0f, 0.0f);
+    if (live) {
+        fr = w.fr[(size_t)b * p.T + t];
+        if (XQ > 0) {
+#pragma unroll
+            for (int q = 0; q < NXQ; ++q) { const int k = q * 32 + lane; xr[q] = k < nvec ? __ldg(xv + k) : vec_fill<VEC>(0.0f); }
+        }
+    }
+    {
+        const int* lab = w.lab + (size_t)b * w.Lp;
+        const int* nxt = w.nxt + (size_t)b * w.Lp;
+        const int* fst = w.first + (size_t)b * w.Lp;
+        for (int j = tid; j < Lb; j += 128) { s_lab[j] = lab[j]; s_nxt[j] = nxt[j]; s_fst[j] = fst[j]; }
+    }
+    __syncthreads();
+    if (t >= p.T) return;
+    float* grow = p.grad + b * p.gst_b + (long long)t * p.gst_t;
+    if (!live) { zero_row<VEC>(grow, p.V, lane); return; }
+
+    const int pairs = 32 * w.P * w.NW;
     constexpr int NCH = CH > 0 ? CH : 1;
-#pragma unroll 1
-    for (int i = 0; i < kFramesPerCta / 4; ++i) {
-        const int t = blockIdx.x * kFramesPerCta + warp * (kFramesPerCta / 4) + i;
-        if (t >= p.T) break;
-        float* grow = p.grad + b * p.gst_b + t * p.gst_t;
-        if (t >= Tb || infeasible) { zero_row<VEC>(grow, p.V, lane); continue; }
-        const size_t blk = (size_t)b * w.NB + t / kG;
-        const size_t hoff = (blk * w.NW * kG + (t % kG)) * PW, ooff = blk * w.NW * PW;
-        const FrameHist A{w.hA + hoff, w.oA + ooff, lgPW, kG * PW};
-        const FrameHist Bh{w.hB + hoff, w.oB + ooff, lgPW, kG * PW};
-        float zb = 0.0f, zl = 0.0f;
-        if (CH > 0) {
-            // single pass: products and exponents stay in registers
-            float wb[NCH], wl[NCH]; int eb[NCH], el[NCH];
-            int emax = INT_MIN;
+    const size_t blk = (size_t)b * w.NB + t / kG;
+    const size_t hoff = (blk * kG + (t % kG)) * pairs, ooff = blk * pairs;
+    const FrameHist A{w.hA + hoff, w.oA + ooff};
+    const FrameHist Bh{w.hB + hoff, w.oB + ooff};
+    float zb = 0.0f, zl = 0.0f;
+    if (CH > 0) {
+        // single pass: products and exponents stay in registers
+        float wb[NCH], wl[NCH]; int eb[NCH], el[NCH];
+        int emax = INT_MIN;
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                const int g = c * 32 + lane;
-                if (g <= Lb) { load_pair(A, Bh, g, Lb, wb[c], eb[c], wl[c], el[c]); emax = max(emax, max(eb[c], el[c])); }
-                else { wb[c] = wl[c] = 0.0f; eb[c] = el[c] = INT_MIN / 2; }
-            }
-            emax = __reduce_max_sync(0xffffffffu, emax);
+        for (int c = 0; c < NCH; ++c) {
+            const int g = c * 32 + lane;
+            if (g <= Lb) { load_pair(A, Bh, g, Lb, wb[c], eb[c], wl[c], el[c]); emax = max(emax, max(eb[c], el[c])); }
+            else { wb[c] = wl[c] = 0.0f; eb[c] = el[c] = INT_MIN / 2; }
+        }
+        emax = __reduce_max_sync(0xffffffffu, emax);
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                const int g = c * 32 + lane;
-                if (g <= Lb) {
-                    zb += xscale0(wb[c], eb[c] - emax);
-                    if (g < Lb) { const float v = xscale0(wl[c], el[c] - emax); zl += v; gbuf[g] = v; }
-                }
-            }
-        } else {
-            int emax = INT_MIN;
-            for (int g = lane; g <= Lb; g += 32) {
-                float wb, wl; int eb, el;
-                load_pair(A, Bh, g, Lb, wb, eb, wl, el);
-                emax = max(emax, max(eb, el));
-            }
-            emax = __reduce_max_sync(0xffffffffu, emax);
-            for (int g = lane; g <= Lb; g += 32) {
-                float wb, wl; int eb, el;
-                load_pair(A, Bh, g, Lb, wb, eb, wl, el);
-                zb += xscale0(wb, eb - emax);
-                if (g < Lb) { const float v = xscale0(wl, el - emax); zl += v; gbuf[g] = v; }
+        for (int c = 0; c < NCH; ++c) {
+            const int g = c * 32 + lane;
+            if (g <= Lb) {
+                zb += xscale0(wb[c], eb[c] - emax);
+                if (g < Lb) { const float v = xscale0(wl[c], el[c] - emax); zl += v; gbuf[g] = v; }
             }
         }
-        zb = warp_sum(zb); zl = warp_sum(zl);
-        const float rZ = 1.0f / (zb + zl);
-        const float gblank = zb * rZ;
-        __syncwarp();
-        // dense row: head * softmax, blank column corrected in place
-        const float2 fr = w.fr[(size_t)b * p.T + t];
-        const float* xrow = p.logits + b * p.st_b + t * p.st_t;
-        const V_t* xv = reinterpret_cast<const V_t*>(xrow);
-        V_t* gv = reinterpret_cast<V_t*>(grow);
+    } else {
+        int emax = INT_MIN;
+        for (int g = lane; g <= Lb; g += 32) {
+            float wb, wl; int eb, el;
+            load_pair(A, Bh, g, Lb, wb, eb, wl, el);
+            emax = max(emax, max(eb, el));
+        }
+        emax = __reduce_max_sync(0xffffffffu, emax);
+        for (int g = lane; g <= Lb; g += 32) {
+            float wb, wl; int eb, el;
+            load_pair(A, Bh, g, Lb, wb, eb, wl, el);
+            zb += xscale0(wb, eb - emax);
+            if (g < Lb) { const float v = xscale0(wl, el - emax); zl += v; gbuf[g] = v; }
+        }
+    }
+    zb = warp_sum(zb); zl = warp_sum(zl);
+    const float rZ = 1.0f / (zb + zl);
+    const float gblank = zb * rZ;
+    __syncwarp();
+    // dense row: head * softmax, blank column corrected in place
+    V_t* gv = reinterpret_cast<V_t*>(grow);
+    if (XQ > 0) {
+#pragma unroll
+        for (int q = 0; q < NXQ; ++q) {
+            const int k = q * 32 + lane;
+            if (k < nvec) {
+                float x[VEC]; vec_get<VEC>(xr[q], x);
+                float y[VEC];
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    y[j] = fast_ex2(fmaf(x[j] - fr.x, kLog2e, -fr.y));
+                    if (k * VEC + j == p.blank) y[j] -= gblank;
+                    y[j] *= head;
+                }
+                V_t o; memcpy(&o, y, sizeof(o));
+                gv[k] = o;
+            }
+        }
+    } else {
         for (int k = lane; k < nvec; k += 32) {
             float x[VEC]; vec_get<VEC>(__ldg(xv + k), x);
             float y[VEC];
@@ -820,23 +916,22 @@ __global__ void __launch_bounds__(128) k_grad(GradArgs a) {
             V_t o; memcpy(&o, y, sizeof(o));
             gv[k] = o;
         }
-        for (int v = nvec * VEC + lane; v < p.V; v += 32) {
-            float y = fast_ex2(fmaf(__ldg(xrow + v) - fr.x, kLog2e, -fr.y));
-            if (v == p.blank) y -= gblank;
-            grow[v] = y * head;
-        }
-        __syncwarp();
-        // label columns: the first occurrence of each label value owns its column and sums
-        // the occupancy of every later occurrence (deterministic, no atomics)
-        for (int j = lane; j < Lb; j += 32) {
-            if (!fst[j]) continue;
-            float occ = 0.0f;
-            for (int k = j; k >= 0; k = nxt[k]) occ += gbuf[k];
-            const int v = lab[j];
-            const float y = fast_ex2(fmaf(__ldg(xrow + v) - fr.x, kLog2e, -fr.y));
-            grow[v] = head * (y - occ * rZ);
-        }
-        __syncwarp();
+    }
+    for (int v = nvec * VEC + lane; v < p.V; v += 32) {
+        float y = fast_ex2(fmaf(__ldg(xrow + v) - fr.x, kLog2e, -fr.y));
+        if (v == p.blank) y -= gblank;
+        grow[v] = y * head;
+    }
+    __syncwarp();
+    // label columns: the first occurrence of each label value owns its column and sums
+    // the occupancy of every later occurrence (deterministic, no atomics)
+    for (int j = lane; j < Lb; j += 32) {
+        if (!s_fst[j]) continue;
+        float occ = 0.0f;
+        for (int k = j; k >= 0; k = s_nxt[k]) occ += gbuf[k];
+        const int v = s_lab[j];
+        const float y = fast_ex2(fmaf(__ldg(xrow + v) - fr.x, kLog2e, -fr.y));
+        grow[v] = head * (y - occ * rZ);
     }
 }
 

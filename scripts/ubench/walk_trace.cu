@@ -22,13 +22,13 @@ int main(int argc, char** argv) {
     Workspace w{};
     cudaMalloc(&w.Tb, B * 4); cudaMalloc(&w.Lb, B * 4); cudaMalloc(&w.flags, B * 4);
     cudaMalloc(&w.lab, (size_t)B * Lp * 4);
-    cudaMalloc(&w.E, (size_t)B * NB * W * kG * 8); cudaMalloc(&w.hA, (size_t)B * NB * kG * PAIRS * 16); cudaMalloc(&w.hB, (size_t)B * NB * kG * PAIRS * 16);
+    cudaMalloc(&w.E, (size_t)B * NB * W * kEC * 8); cudaMalloc(&w.hA, (size_t)B * NB * kG * PAIRS * 16); cudaMalloc(&w.hB, (size_t)B * NB * kG * PAIRS * 16);
     cudaMalloc(&w.oA, (size_t)B * NB * PAIRS * 8); cudaMalloc(&w.oB, (size_t)B * NB * PAIRS * 8);
     cudaMalloc(&w.fr, (size_t)B * T * 8); cudaMemset(w.fr, 0, (size_t)B * T * 8);
     w.Lp = Lp; w.W = W; w.NB = NB; w.dense = 1; w.P = TP; w.NW = TNW;
     std::vector<int> Tb(B, T), Lb(B, L), fl(B, 0), lab((size_t)B * Lp);
     for (auto& x : lab) x = 1 + rand() % (V - 1);
-    std::vector<double> E((size_t)B * NB * W * kG);
+    std::vector<double> E((size_t)B * NB * W * kEC);
     for (auto& e : E) e = exp(-3.0 * rand() / RAND_MAX);
     cudaMemcpy(w.Tb, Tb.data(), B * 4, cudaMemcpyHostToDevice); cudaMemcpy(w.Lb, Lb.data(), B * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(w.flags, fl.data(), B * 4, cudaMemcpyHostToDevice); cudaMemcpy(w.lab, lab.data(), lab.size() * 4, cudaMemcpyHostToDevice);
