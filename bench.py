@@ -118,12 +118,15 @@ def cpu_step_fn(d):
     g = np.empty_like(d["pred"])
     lab = d["label"].astype(np.int32)
 
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1: ask explicitly)
+    cores = min(len(os.sched_getaffinity(0)), B) if hasattr(os, "sched_getaffinity") else ctc_ref.max_threads()
+
     def step():
         # NTC logits addressed through strides (no swapaxes copy: a favour to the baseline),
         # softmax + alpha + beta + grad + head scaling, OpenMP over the minibatch
         return ctc_ref.ctc_ref(d["pred"], lab, d["pred_lengths"], d["label_lengths"], blank=0, head_grad=head,
-                               layout="NTC", dtype=np.float32, out_grad=g)
-    return step, ctc_ref.max_threads()
+                               layout="NTC", dtype=np.float32, out_grad=g, num_threads=cores)
+    return step, cores
 
 
 def time_cpu(d, steps, warmup, budget_s=None):
@@ -181,6 +184,7 @@ def run_cuda(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=dev)
 
     name = args.workload
@@ -365,8 +369,8 @@ def run_cuda(args, rank, world, local_rank):
         "algorithmic_bytes_per_launch": alg,
         "kernel_ms": {k: float(v) for k, v in zip(knames, kms)},
         "step_achieved": alg / (ms_per_step * 1e-3) / 1e9, "step_frac": alg / (ms_per_step * 1e-3) / 1e9 / peak,
-        "note": "V=46 path is recursion-latency bound (T dependent steps per utterance, 2B CTAs), not HBM bound: "
-                "SURVEY.md 8d / DESIGN.md section 5",
+        "note": "fp32 logits/gradient in HBM, fp64 linear-domain lattice recursion; the V=46 path is recursion-latency "
+                "bound (T dependent steps per utterance, 2B CTAs), not HBM bound: SURVEY.md 8d / DESIGN.md sections 5-6",
     }
 
     # ---- other workloads, same run (N=1 only): context numbers, not the headline ----------
@@ -392,7 +396,7 @@ def run_cuda(args, rank, world, local_rank):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": "f64", "data": "synthetic",
             "config": {"workload": name if world == 1 else "%s per rank (global B=%d)" % (name, B * world),
                        "B_per_gpu": B, "T": T, "V": V, "Lmax": L, "layout": "NTC", "lengths": "variable",
                        "valid_frames_per_step": frames_all / args.steps,

@@ -21,6 +21,7 @@ EXPORTS = (
     "ctcb_version", "ctcb_last_error", "ctcb_workspace_bytes", "ctcb_loss_grad", "ctcb_forward",
     "ctcb_backward", "ctcb_loss_grad_host", "ctcb_greedy_decode", "ctcb_loss_sum_allreduce",
     "ctcb_last_launch_count", "ctcb_last_walk_config", "ctcb_loss_grad_dlpack", "ctcb_loss_grad_timed",
+    "ctcb_scale_rows",
 )
 
 
@@ -70,6 +71,7 @@ def load():
     lib.ctcb_loss_grad_timed.argtypes = [PP, vp, sz, vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32)]
     lib.ctcb_loss_grad_host.argtypes = [PP, ctypes.c_int]
     lib.ctcb_greedy_decode.argtypes = [vp, i64, i64, vp, i32, i32, i32, i32, i32, vp, vp, vp]
+    lib.ctcb_scale_rows.argtypes = [vp, i64, i64, i32, i32, i32, vp, vp]
     lib.ctcb_loss_sum_allreduce.argtypes = [vp, vp, i32, vp]
     lib.ctcb_last_walk_config.argtypes = [ctypes.POINTER(i32), ctypes.POINTER(i32)]
     lib.ctcb_loss_grad_dlpack.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, sz, vp]
@@ -86,10 +88,17 @@ def check(rc):
         raise CtcbError(rc, load().ctcb_last_error().decode("utf-8", "replace"))
 
 
+_ws_bytes = {}
+
+
 def workspace_bytes(T, B, V, Lmax, need_grad=True):
-    out = ctypes.c_size_t(0)
-    check(load().ctcb_workspace_bytes(T, B, V, Lmax, 1 if need_grad else 0, ctypes.byref(out)))
-    return out.value
+    key = (T, B, V, Lmax, bool(need_grad), os.environ.get("CTCB_WALK_P"), os.environ.get("CTCB_WALK_NW"))
+    n = _ws_bytes.get(key)
+    if n is None:
+        out = ctypes.c_size_t(0)
+        check(load().ctcb_workspace_bytes(T, B, V, Lmax, 1 if need_grad else 0, ctypes.byref(out)))
+        n = _ws_bytes[key] = out.value
+    return n
 
 
 def last_launch_count():

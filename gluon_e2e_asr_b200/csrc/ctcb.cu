@@ -416,6 +416,18 @@ int ctcb_loss_grad_host(const ctcb_problem_t* hp, int device) {
     return CTCB_OK;
 }
 
+int ctcb_scale_rows(float* grad, int64_t stride_t, int64_t stride_b, int32_t T, int32_t B, int32_t V,
+                    const float* head_grad, void* stream) {
+    if (!grad || !head_grad) return fail(CTCB_INVALID_VALUE, "NULL argument");
+    if (T <= 0 || B <= 0 || V <= 0) return fail(CTCB_INVALID_VALUE, "bad shape");
+    if (!is_device_ptr(grad) || !is_device_ptr(head_grad)) return fail(CTCB_INVALID_VALUE, "buffers must be CUDA device memory");
+    const long long rows = (long long)T * B;
+    ctcb::k_scale_rows<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(grad, stride_t, stride_b, T, B, V, head_grad);
+    CUDA_TRY(cudaGetLastError());
+    g_launches = 1;
+    return CTCB_OK;
+}
+
 int ctcb_greedy_decode(const float* logits, int64_t stride_t, int64_t stride_b, const void* data_lengths,
                        int32_t data_lengths_dtype, int32_t T, int32_t B, int32_t V, int32_t blank,
                        int32_t* out_tokens, int32_t* out_lengths, void* stream) {

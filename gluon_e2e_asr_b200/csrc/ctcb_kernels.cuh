@@ -936,6 +936,22 @@ __global__ void __launch_bounds__(128) k_grad(GradArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
+// k_scale_rows: grad[b,t,:] *= head[b] in place.  Row a8 (the operator's Backward: the
+// gradient stored by Forward times the head gradient) for callers that ran the fused
+// forward+gradient with head = 1.  grid (ceil(T*ceil(V/128)... ) flat over (b, t) rows.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_scale_rows(float* grad, long long gst_t, long long gst_b, int T, int B, int V,
+                                                    const float* head) {
+    const int rows_per_cta = 8, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long r = (long long)blockIdx.x * rows_per_cta + warp;
+    if (r >= (long long)T * B) return;
+    const int b = (int)(r / T), t = (int)(r % T);
+    const float h = head[b];
+    float* row = grad + b * gst_b + t * gst_t;
+    for (int v = lane; v < V; v += 32) row[v] *= h;
+}
+
+// ---------------------------------------------------------------------------------------
 // k_greedy_decode: grid B, block 256.  train_ctc_ce.py:149-160 (next-row scope).
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_greedy_decode(const float* logits, long long st_t, long long st_b,

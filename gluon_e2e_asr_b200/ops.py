@@ -153,6 +153,13 @@ def _alloc_ws(call, need_grad):
     return torch.empty((n,), dtype=torch.uint8, device=call.data.device)
 
 
+# Forward of a differentiable call: small problems run the fused forward+gradient once (the
+# gradient is stored like MXNet's operator stores it) and Backward only scales
+# it by the head gradient; large ones keep the alpha/beta history and write head*G once in
+# Backward, which saves a pass over the (T,B,V) gradient.
+_FUSE_IN_FORWARD_MAX_ELEMS = 8 * 1024 * 1024
+
+
 class _CtcLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, data, label, data_lengths, label_lengths, blank_last, ntc, tn):
@@ -160,17 +167,33 @@ class _CtcLossFn(torch.autograd.Function):
         need = ctx.needs_input_grad[0]
         ws = _alloc_ws(call, need)
         loss = torch.empty((call.B,), dtype=torch.float32, device=data.device)
-        call.run(_lib.PHASE_FORWARD, ws, loss, keep=need)
-        ctx.call, ctx.ws = call, ws
+        ctx.call = call
+        if need and data.numel() <= _FUSE_IN_FORWARD_MAX_ELEMS:
+            grad = torch.empty_like(data)           # same layout as the logits: no swapaxes backward
+            call.run(_lib.PHASE_FUSED, ws, loss, grad=grad)
+            ctx.grad, ctx.ws = grad, None
+        else:
+            call.run(_lib.PHASE_FORWARD, ws, loss, keep=need)
+            ctx.grad, ctx.ws = None, ws
         return loss
 
     @staticmethod
     def backward(ctx, head):
-        call, ws = ctx.call, ctx.ws
+        call = ctx.call
+        if head.dtype != torch.float32 or not head.is_contiguous():
+            head = head.to(torch.float32).contiguous()
+        if ctx.grad is not None:
+            grad, ctx.grad = ctx.grad, None
+            ta, ba = call._axes[0], call._axes[1]
+            with torch.cuda.device(grad.device):
+                _lib.check(_lib.load().ctcb_scale_rows(grad.data_ptr(), grad.stride(ta), grad.stride(ba), call.T, call.B,
+                                                       call.V, head.data_ptr(),
+                                                       torch.cuda.current_stream(grad.device).cuda_stream))
+            return grad, None, None, None, None, None, None
+        ws = ctx.ws
         if ws is None:
             raise RuntimeError("ctc_loss: backward called twice (the workspace is released after the first)")
-        head = head.to(torch.float32).contiguous()
-        grad = torch.empty_like(call.data)          # same layout as the logits: no swapaxes backward
+        grad = torch.empty_like(call.data)
         loss_scratch = torch.empty((call.B,), dtype=torch.float32, device=head.device)
         call.run(_lib.PHASE_BACKWARD, ws, loss_scratch, grad=grad, head=head)
         ctx.ws = None

@@ -120,6 +120,12 @@ int ctcb_loss_grad_timed(const ctcb_problem_t* p, void* workspace, size_t worksp
  * bench.py's end-to-end leg. */
 int ctcb_loss_grad_host(const ctcb_problem_t* p, int device);
 
+/* The operator's Backward for a caller that ran ctcb_loss_grad with head_grad = NULL in its
+ * Forward (what MXNet's operator does: Forward stores the gradient, Backward multiplies it by
+ * the head gradient -- SURVEY 8a row a8): grad[b, t, :] *= head_grad[b], in place. */
+int ctcb_scale_rows(float* grad, int64_t stride_t, int64_t stride_b, int32_t T, int32_t B, int32_t V,
+                    const float* head_grad, void* stream);
+
 /* Greedy CTC decode of train_ctc_ce.py:149-160 / decode_ctc.py:123-143 (next-row scope,
  * SURVEY 8f rank 2): per utterance argmax over V for t < length, collapse repeats, drop
  * `blank`.  out_tokens (B, T) int32 (prefix valid), out_lengths (B,) int32.  Device buffers. */

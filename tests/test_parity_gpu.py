@@ -220,6 +220,19 @@ def test_autograd_path_equals_fused_path_and_handoffs(dev):
         lf, gf = ctc_loss_and_grad(t["pred"], t["label"], t["pred_lengths"], t["label_lengths"], head_grad=head,
                                    handoff=handoff)
         assert torch.equal(lf, loss.detach()) and torch.equal(gf, pred.grad)
+    # the two differentiable paths (gradient stored in Forward and scaled in Backward, or history
+    # kept and head*G written once in Backward) give the same bits
+    from gluon_e2e_asr_b200 import ops
+    saved = ops._FUSE_IN_FORWARD_MAX_ELEMS
+    try:
+        ops._FUSE_IN_FORWARD_MAX_ELEMS = 0
+        pred2 = t["pred"].clone().requires_grad_(True)
+        loss2 = blk(pred2, t["label"], t["pred_lengths"], t["label_lengths"])
+        loss2.mean().backward()
+    finally:
+        ops._FUSE_IN_FORWARD_MAX_ELEMS = saved
+    assert torch.equal(loss2.detach(), loss.detach())
+    torch.testing.assert_close(pred2.grad, pred.grad, rtol=2e-7, atol=1e-12)
     # forward-only (evaluation path, train_ctc_ce.py:143): same loss, no history kept
     with torch.no_grad():
         le = blk(t["pred"], t["label"], t["pred_lengths"], t["label_lengths"])
