@@ -86,7 +86,7 @@ bool pick_stages(int W, int NW, int* stages) {
 }
 
 struct Layout {
-    size_t off_Tb, off_Lb, off_flags, off_lab, off_nxt, off_first, off_fr, off_E, off_hA, off_hB, off_oA, off_oB, total;
+    size_t off_Tb, off_Lb, off_flags, off_lab, off_ord, off_dl, off_nd, off_fr, off_E, off_hA, off_hB, off_oA, off_oB, total;
     int Lp, W, NB, dense, P, NW;
     const WalkEntry* walk;
 };
@@ -110,13 +110,14 @@ Layout make_layout(int T, int B, int V, int Lmax, int need_grad) {
     l.off_Lb = take(sizeof(int) * B);
     l.off_flags = take(sizeof(int) * B);
     l.off_lab = take(sizeof(int) * (size_t)B * l.Lp);
-    l.off_nxt = take(sizeof(int) * (size_t)B * l.Lp);
-    l.off_first = take(sizeof(int) * (size_t)B * l.Lp);
+    l.off_ord = take(sizeof(int) * (size_t)B * l.Lp);
+    l.off_dl = take(sizeof(int2) * (size_t)B * (l.Lp + 1));
+    l.off_nd = take(sizeof(int) * B);
     l.off_fr = take(sizeof(float2) * (size_t)B * T);
     l.off_E = take(sizeof(double) * (size_t)B * l.NB * l.W * ctcb::kEC);
     if (need_grad) {
-        l.off_hA = take(sizeof(double2) * (size_t)B * l.NB * ctcb::kG * pairs);
-        l.off_hB = take(sizeof(double2) * (size_t)B * l.NB * ctcb::kG * pairs);
+        l.off_hA = take(sizeof(int2) * (size_t)B * l.NB * ctcb::kG * pairs);
+        l.off_hB = take(sizeof(int2) * (size_t)B * l.NB * ctcb::kG * pairs);
         l.off_oA = take(sizeof(int2) * (size_t)B * l.NB * pairs);
         l.off_oB = take(sizeof(int2) * (size_t)B * l.NB * pairs);
     }
@@ -131,12 +132,13 @@ ctcb::Workspace carve(const Layout& l, void* ws) {
     w.Lb = reinterpret_cast<int*>(base + l.off_Lb);
     w.flags = reinterpret_cast<int*>(base + l.off_flags);
     w.lab = reinterpret_cast<int*>(base + l.off_lab);
-    w.nxt = reinterpret_cast<int*>(base + l.off_nxt);
-    w.first = reinterpret_cast<int*>(base + l.off_first);
+    w.ord = reinterpret_cast<int*>(base + l.off_ord);
+    w.dl = reinterpret_cast<int2*>(base + l.off_dl);
+    w.nd = reinterpret_cast<int*>(base + l.off_nd);
     w.fr = reinterpret_cast<float2*>(base + l.off_fr);
     w.E = reinterpret_cast<double*>(base + l.off_E);
-    w.hA = reinterpret_cast<double2*>(base + l.off_hA);
-    w.hB = reinterpret_cast<double2*>(base + l.off_hB);
+    w.hA = reinterpret_cast<int2*>(base + l.off_hA);
+    w.hB = reinterpret_cast<int2*>(base + l.off_hB);
     w.oA = reinterpret_cast<int2*>(base + l.off_oA);
     w.oB = reinterpret_cast<int2*>(base + l.off_oB);
     w.Lp = l.Lp; w.W = l.W; w.NB = l.NB; w.dense = l.dense; w.P = l.P; w.NW = l.NW;
@@ -245,7 +247,7 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
         const size_t smem = ctcb::walk_smem_bytes(lay.W, we->NW, stages);
         const WalkFn wfn = we->fn[need_grad ? 1 : 0];
         const int vec = pick_vec(p->logits, p->logits_stride_t, p->logits_stride_b, p->V);
-        const size_t esm = (size_t)lay.Lp * sizeof(int);
+        const size_t esm = 2 * (size_t)lay.Lp * sizeof(int);
         {
             std::lock_guard<std::mutex> lk(mu);
             CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(wfn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -272,7 +274,7 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
     }
     if (phases & PH_BACKWARD) {
         ctcb::GradArgs ga{dp, w};
-        const size_t gsm = (3 + 4) * (size_t)lay.Lp * sizeof(float);
+        const size_t gsm = ctcb::grad_smem_bytes(lay.Lp);
         if (gsm > 200 * 1024) return fail(CTCB_UNSUPPORTED, "Lmax=%d too long for the gradient kernel", p->Lmax);
         int vec = pick_vec(p->logits, p->logits_stride_t, p->logits_stride_b, p->V);
         const int gvec = pick_vec(p->grad, p->grad_stride_t, p->grad_stride_b, p->V);
@@ -281,7 +283,7 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
         const int ch = pairs <= 32 ? 1 : pairs <= 64 ? 2 : pairs <= 128 ? 4 : pairs <= 256 ? 8 : pairs <= 512 ? 16 : 0;
         const int units = (p->V / vec + 31) / 32;
         const int xq = units <= 1 ? 1 : units <= 2 ? 2 : units <= 4 ? 4 : 0;
-        const dim3 ggrid((p->T + ctcb::kGradFrames - 1) / ctcb::kGradFrames, p->B);
+        const dim3 ggrid(lay.NB, p->B);                  // one frame block per CTA
         using GradFn = void (*)(ctcb::GradArgs);
         GradFn gfn = nullptr;
 #define GRAD_X(V_, C_) (xq == 1 ? ctcb::k_grad<V_, C_, 1> : xq == 2 ? ctcb::k_grad<V_, C_, 2> : xq == 4 ? ctcb::k_grad<V_, C_, 4> : ctcb::k_grad<V_, C_, 0>)

@@ -59,13 +59,16 @@ struct Problem {          // device view of ctcb_problem_t
 struct Workspace {        // carved out of the caller's workspace by the host (ctcb.cu)
     int* Tb; int* Lb; int* flags;     // (B,)
     int* lab;                         // (B, Lp) int32 labels
-    int* nxt;                         // (B, Lp) next position with the same label, or -1
-    int* first;                       // (B, Lp) 1 when no earlier position has this label
+    int* ord;                         // (B, Lp) label positions sorted by (label value, position)
+    int2* dl;                         // (B, Lp+1) distinct labels in increasing order: {value, first index into ord};
+                                      //   entry nd is the sentinel {-1, L}
+    int* nd;                          // (B,) number of distinct labels
     float2* fr;                       // (B, T) {row max, log2 sum exp2((x-max)*log2e)}
     double* E;                        // (B, NB, W, kEC) emissions exp(x - rowmax) of frame block n = t / 8, frame-minor:
                                       //   dense -> column v; else column 0 blank, column j label j
-    double2* hA;                      // (B, NB, 8, NW*PW) alpha_t {blank, label} of each state pair, relative to oA
-    double2* hB;                      // same for beta'_t in the reversed walker's pair coordinates, relative to oB
+    int2* hA;                         // (B, NB, 8, NW*PW) alpha_t {blank, label} of each state pair, relative to oA:
+                                      //   the HIGH WORD of the walker's fp64 value (11-bit exponent, 20-bit mantissa)
+    int2* hB;                         // same for beta'_t in the reversed walker's pair coordinates, relative to oB
     int2* oA;                         // (B, NB, NW*PW) exponent offsets {blank, label} valid for frame block n
     int2* oB;
     int Lp, W, NB, dense, P, NW;      // PW = 32*P pairs per walker warp
@@ -148,7 +151,7 @@ template <> __device__ __forceinline__ float4 vec_fill<4>(float v) { return make
 template <int VEC, int NQ>
 __global__ void __launch_bounds__(128) k_emit(Problem p, Workspace w) {
     using V_t = typename VecT<VEC>::type;
-    extern __shared__ int slab[];                 // Lp ints: this utterance's labels
+    extern __shared__ int slab[];                 // 2*Lp ints: this utterance's labels, metadata scratch
     __shared__ int s_L, s_rep, s_flags;
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) { s_L = p.Lmax; s_rep = 0; s_flags = 0; }
@@ -288,26 +291,43 @@ __global__ void __launch_bounds__(128) k_emit(Problem p, Workspace w) {
 
     if (!meta_cta) return;
     // ---- per-utterance metadata ----
+    // The gradient kernel sums the occupancy of every occurrence of a label value into that
+    // value's column in a FIXED order (no atomics): positions sorted by (value, position), and
+    // the list of distinct values with the start of each run.  Ranks by counting (L <= 2047).
     int* lab = w.lab + (size_t)b * w.Lp;
-    int* nxt = w.nxt + (size_t)b * w.Lp;
-    int* fst = w.first + (size_t)b * w.Lp;
+    int* ord = w.ord + (size_t)b * w.Lp;
+    int2* dl = w.dl + (size_t)b * (w.Lp + 1);
+    int* s_run = slab + w.Lp;                      // start of the run a position opens, or -1
+    __shared__ int s_nd;
+    if (tid == 0) s_nd = 0;
     int rep = 0;
-    // same-label chains: every thread scans for its position's next / previous occurrence
     for (int j = tid; j < L; j += 128) {
         const int v = slab[j];
         lab[j] = v;
         if (j > 0 && slab[j - 1] == v) ++rep;
-        int n = -1, f = 1;
-        for (int k = j + 1; k < L; ++k) if (slab[k] == v) { n = k; break; }
-        for (int k = j - 1; k >= 0; --k) if (slab[k] == v) { f = 0; break; }
-        nxt[j] = n; fst[j] = f;
+        int lt = 0, eqb = 0;
+        for (int k = 0; k < L; ++k) { const int u = slab[k]; lt += u < v; eqb += (u == v) & (k < j); }
+        ord[lt + eqb] = j;
+        s_run[j] = eqb == 0 ? lt : -1;
     }
     if (rep) atomicAdd(&s_rep, rep);
+    __syncthreads();
+    int mine = 0;
+    for (int j = tid; j < L; j += 128) {
+        if (s_run[j] < 0) continue;
+        const int v = slab[j];
+        int d = 0;
+        for (int k = 0; k < L; ++k) d += (s_run[k] >= 0) & (slab[k] < v);
+        dl[d] = make_int2(v, s_run[j]);
+        ++mine;
+    }
+    if (mine) atomicAdd(&s_nd, mine);
     __syncthreads();
     if (tid == 0) {
         int flags = s_flags | lenflags;
         if (Tb <= 0 || L + s_rep > Tb) flags |= UTT_INFEASIBLE;
         w.Tb[b] = Tb; w.Lb[b] = L; w.flags[b] = flags;
+        w.nd[b] = s_nd; dl[s_nd] = make_int2(-1, L);
         if (p.status) p.status[b] = flags;
         if (flags & UTT_INFEASIBLE) p.loss[b] = 0.0f;   // defined behaviour, SURVEY 7.3-6
     }
@@ -505,7 +525,7 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
     }
     if (tid == 0) bm[0] = 1.0;                  // virtual alpha_{-1} = delta(s = 0)
 
-    double2* hist = nullptr; int2* offs = nullptr;
+    int2* hist = nullptr; int2* offs = nullptr;
     if (HIST) {
         hist = (DIR ? w.hB : w.hA) + (size_t)b * w.NB * kG * NW * PW + g0;
         offs = (DIR ? w.oB : w.oA) + (size_t)b * w.NB * NW * PW + g0;
@@ -641,7 +661,7 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
             sts_f64(ma, lm[P - 1]);
             sts_s32(ma + 8, el[P - 1]); sts_s32(ma + 12, Rout); sts_s32(ma + 16, Fout);
         }
-        double2* hch = nullptr;
+        int2* hch = nullptr;
         if (HIST) {
             int2* o = offs + (size_t)blk * NW * PW;
 #pragma unroll
@@ -684,9 +704,24 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
             const double pm_next = shfl_up_f64(lm[P - 1]);
             if (pub) sts_f64(hs_my + so, lm[P - 1]);
 #pragma unroll
-            for (int p = P - 1; p >= 0; --p) {
-                bm[p] = sb[p] * yb;
-                if (HIST) hch[j * (NW * PW) + p] = DIR ? make_double2(sb[p], sl[p]) : make_double2(bm[p], lm[p]);
+            for (int p = P - 1; p >= 0; --p) bm[p] = sb[p] * yb;
+            if (HIST) {
+                // history = the high words (exponent + 20 mantissa bits): the posteriors are ratios, the
+                // truncation bias cancels and what is left is < 2^-20 relative
+                int2 hw[P];
+#pragma unroll
+                for (int p = 0; p < P; ++p)
+                    hw[p] = DIR ? make_int2(__double2hiint(sb[p]), __double2hiint(sl[p]))
+                                : make_int2(__double2hiint(bm[p]), __double2hiint(lm[p]));
+                int2* dst = hch + j * (NW * PW);
+                if (P % 2 == 0) {
+#pragma unroll
+                    for (int p = 0; p < P; p += 2)
+                        *reinterpret_cast<int4*>(dst + p) = make_int4(hw[p].x, hw[p].y, hw[(p + 1) % P].x, hw[(p + 1) % P].y);
+                } else {
+#pragma unroll
+                    for (int p = 0; p < P; ++p) dst[p] = hw[p];
+                }
             }
             pm = pm_next;
             if (lane == 0) pm = hv;
@@ -753,10 +788,18 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_walk(WalkArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
-// k_grad<VEC,CH,XQ>: grid (ceil(T/4), B), block 128, one warp per frame.  Rows a7 (accumulation,
-// gradient) and a8 (head-gradient scaling), written once in the caller's layout.
+// k_grad<VEC,CH,XQ>: grid (NB, B), block 128: one frame block (kG = 8 frames) per CTA, two
+// frames per warp.  Rows a7 (accumulation, gradient) and a8 (head-gradient scaling), written
+// once in the caller's layout.
 // CH = register-resident chunks of 32 state pairs per lane (pairs <= 32*CH); CH = 0 is the
-// generic two-pass variant for longer label sequences.
+// generic two-pass variant for longer label sequences.  With CH <= 4 both frames of a warp are
+// in flight together (every global load of the two frames is issued before the first use).
+//
+// State weights come from the walkers' high-word history: mantissa (20 bits) -> float in
+// [1,2) by integer ops, exponent field + the frame block's offsets -> one integer per state;
+// gamma_t(s) = alpha_t(s) beta'_t(s) / Z_t is normalised per frame from those integers, so
+// nothing large is ever subtracted.  The offsets of alpha and beta' are combined once per
+// warp (they are constant over the frame block).
 // ---------------------------------------------------------------------------------------
 struct GradArgs { Problem p; Workspace w; };
 
@@ -770,168 +813,222 @@ __device__ __forceinline__ void zero_row(float* row, int V, int lane) {
     for (int v = nvec * VEC + lane; v < V; v += 32) row[v] = 0.0f;
 }
 
-// weight (mantissa product as float in [1,4), total exponent) of alpha*beta' for one state
-__device__ __forceinline__ void state_weight(double av, int ao, double bv, int bo, float& wgt, int& e) {
-    if (av == 0.0 || bv == 0.0) { wgt = 0.0f; e = INT_MIN / 2; return; }
-    wgt = __double2float_rn(dmant(av) * dmant(bv));
-    e = dexp(av) + dexp(bv) + ao + bo;
+constexpr int kNoState = INT_MIN / 2;
+
+// high word of a positive fp64 -> its 20 mantissa bits as a float in [1,2)
+__device__ __forceinline__ float hw_mant(int h) { return __int_as_float(((h & 0x000fffff) << 3) | 0x3f800000); }
+// weight (mantissa product in [1,4), total exponent) of alpha*beta' for one state
+__device__ __forceinline__ void hw_weight(int ha, int hb, int off, float& wgt, int& e) {
+    const bool zero = (ha == 0) | (hb == 0);
+    wgt = zero ? 0.0f : hw_mant(ha) * hw_mant(hb);
+    e = zero ? kNoState : (ha >> 20) + (hb >> 20) + off;
 }
 
-// One frame's view of a walker history: values and the frame block's exponent offsets per pair.
-struct FrameHist {
-    const double2* h; const int2* o;
-    __device__ __forceinline__ double2 val(int g) const { return h[g]; }
-    __device__ __forceinline__ int2 off(int g) const { return o[g]; }
-};
+constexpr int kGradFramesPerWarp = 2;  // 4 warps x 2 frames = one frame block per CTA
 
-// alpha history of pair g and beta' history re-expressed in the forward pair coordinates:
-// blank of pair g <-> reversed-walker blank of slot L-g; label of pair g <-> reversed-walker
-// label of slot L-1-g.
-__device__ __forceinline__ void load_pair(const FrameHist& A, const FrameHist& Bh, int g, int Lb,
-                                          float& wb, int& eb, float& wl, int& el) {
-    const double2 av = A.val(g); const int2 ao = A.off(g);
-    const double2 bb = Bh.val(Lb - g); const int2 bo = Bh.off(Lb - g);
-    state_weight(av.x, ao.x, bb.x, bo.x, wb, eb);
-    if (g < Lb) {
-        const double2 bl = Bh.val(Lb - 1 - g); const int2 blo = Bh.off(Lb - 1 - g);
-        state_weight(av.y, ao.y, bl.y, blo.y, wl, el);
-    } else { wl = 0.0f; el = INT_MIN / 2; }
+__host__ __device__ inline size_t grad_smem_bytes(int Lp) {
+    return (size_t)Lp * 4 + (size_t)(Lp + 1) * 8 + (size_t)4 * kGradFramesPerWarp * Lp * 4 + 8;
 }
 
-constexpr int kGradFrames = 4;         // k_grad: one frame per warp
-
-// XQ = VEC-wide loads per lane that hold the frame's logits row in registers (issued before the
-// history loads so that one memory round trip covers both); 0 = row loaded when it is needed.
+// XQ = VEC-wide loads per lane that hold the frame's logits row in registers (issued together
+// with the history loads so that one memory round trip covers both); 0 = row loaded when needed.
 template <int VEC, int CH, int XQ>
 __global__ void __launch_bounds__(128) k_grad(GradArgs a) {
     using V_t = typename VecT<VEC>::type;
+    constexpr int NCH = CH > 0 ? CH : 1, NXQ = XQ > 0 ? XQ : 1;
+    constexpr int F = (CH > 0 && CH <= 4) ? kGradFramesPerWarp : 1;      // frames in flight per warp
     const Problem& p = a.p; const Workspace& w = a.w;
-    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y, blk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int Tb = w.Tb[b], Lb = w.Lb[b];
     const bool infeasible = (w.flags[b] & UTT_INFEASIBLE) != 0;
     const float head = p.head ? p.head[b] : 1.0f;
-    extern __shared__ int gsm[];
-    int* s_lab = gsm; int* s_nxt = gsm + w.Lp; int* s_fst = gsm + 2 * w.Lp;
-    float* gbuf = reinterpret_cast<float*>(gsm + 3 * w.Lp) + (size_t)warp * w.Lp;
-    const int t = blockIdx.x * kGradFrames + warp;
-    const bool live = t < p.T && t < Tb && !infeasible;
-    const int nvec = p.V / VEC;
-    constexpr int NXQ = XQ > 0 ? XQ : 1;
-    // everything that does not depend on the history is requested first
-    const float* xrow = p.logits + b * p.st_b + (long long)(t < p.T ? t : 0) * p.st_t;
-    const V_t* xv = reinterpret_cast<const V_t*>(xrow);
-    V_t xr[NXQ]; float2 fr = make_float2(0.0f, 0.0f);
-    if (live) {
-        fr = w.fr[(size_t)b * p.T + t];
-        if (XQ > 0) {
-#pragma unroll
-            for (int q = 0; q < NXQ; ++q) { const int k = q * 32 + lane; xr[q] = k < nvec ? __ldg(xv + k) : vec_fill<VEC>(0.0f); }
-        }
-    }
-    {
-        const int* lab = w.lab + (size_t)b * w.Lp;
-        const int* nxt = w.nxt + (size_t)b * w.Lp;
-        const int* fst = w.first + (size_t)b * w.Lp;
-        for (int j = tid; j < Lb; j += 128) { s_lab[j] = lab[j]; s_nxt[j] = nxt[j]; s_fst[j] = fst[j]; }
+    const int t_first = blk * kG;
+    const bool cta_live = !infeasible && t_first < Tb;
+    extern __shared__ __align__(8) unsigned char gsm_raw[];
+    int2* s_dl = reinterpret_cast<int2*>(gsm_raw);                                   // Lp + 1
+    int* s_ord = reinterpret_cast<int*>(s_dl + (w.Lp + 1));                          // Lp
+    float* gbuf0 = reinterpret_cast<float*>(s_ord + w.Lp) + (size_t)warp * kGradFramesPerWarp * w.Lp;
+    int nd = 0;
+    if (cta_live) {
+        nd = w.nd[b];
+        const int* ord = w.ord + (size_t)b * w.Lp;
+        const int2* dl = w.dl + (size_t)b * (w.Lp + 1);
+        for (int j = tid; j < Lb; j += 128) s_ord[j] = ord[j];
+        for (int j = tid; j <= nd; j += 128) s_dl[j] = dl[j];
     }
     __syncthreads();
-    if (t >= p.T) return;
-    float* grow = p.grad + b * p.gst_b + (long long)t * p.gst_t;
-    if (!live) { zero_row<VEC>(grow, p.V, lane); return; }
 
     const int pairs = 32 * w.P * w.NW;
-    constexpr int NCH = CH > 0 ? CH : 1;
-    const size_t blk = (size_t)b * w.NB + t / kG;
-    const size_t hoff = (blk * kG + (t % kG)) * pairs, ooff = blk * pairs;
-    const FrameHist A{w.hA + hoff, w.oA + ooff};
-    const FrameHist Bh{w.hB + hoff, w.oB + ooff};
-    float zb = 0.0f, zl = 0.0f;
-    if (CH > 0) {
-        // single pass: products and exponents stay in registers
-        float wb[NCH], wl[NCH]; int eb[NCH], el[NCH];
-        int emax = INT_MIN;
+    const size_t blkoff = (size_t)b * w.NB + blk;
+    const int2* hA0 = w.hA + blkoff * kG * pairs;
+    const int2* hB0 = w.hB + blkoff * kG * pairs;
+    const int2* oA = w.oA + blkoff * pairs;
+    const int2* oB = w.oB + blkoff * pairs;
+    // alpha pair g <-> beta' pairs: blank of pair g = reversed-walker blank of slot L-g, label of
+    // pair g = reversed-walker label of slot L-1-g.  Offsets of the block, combined per state.
+    int ofb[NCH], ofl[NCH];
+    if (CH > 0 && cta_live) {
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const int g = c * 32 + lane;
-            if (g <= Lb) { load_pair(A, Bh, g, Lb, wb[c], eb[c], wl[c], el[c]); emax = max(emax, max(eb[c], el[c])); }
-            else { wb[c] = wl[c] = 0.0f; eb[c] = el[c] = INT_MIN / 2; }
-        }
-        emax = __reduce_max_sync(0xffffffffu, emax);
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            const int g = c * 32 + lane;
+            ofb[c] = ofl[c] = 0;
             if (g <= Lb) {
-                zb += xscale0(wb[c], eb[c] - emax);
-                if (g < Lb) { const float v = xscale0(wl[c], el[c] - emax); zl += v; gbuf[g] = v; }
+                const int2 oa = __ldg(oA + g);
+                ofb[c] = oa.x + __ldg(&oB[Lb - g].x);
+                if (g < Lb) ofl[c] = oa.y + __ldg(&oB[Lb - 1 - g].y);
             }
         }
-    } else {
-        int emax = INT_MIN;
-        for (int g = lane; g <= Lb; g += 32) {
-            float wb, wl; int eb, el;
-            load_pair(A, Bh, g, Lb, wb, eb, wl, el);
-            emax = max(emax, max(eb, el));
-        }
-        emax = __reduce_max_sync(0xffffffffu, emax);
-        for (int g = lane; g <= Lb; g += 32) {
-            float wb, wl; int eb, el;
-            load_pair(A, Bh, g, Lb, wb, eb, wl, el);
-            zb += xscale0(wb, eb - emax);
-            if (g < Lb) { const float v = xscale0(wl, el - emax); zl += v; gbuf[g] = v; }
-        }
     }
-    zb = warp_sum(zb); zl = warp_sum(zl);
-    const float rZ = 1.0f / (zb + zl);
-    const float gblank = zb * rZ;
-    __syncwarp();
-    // dense row: head * softmax, blank column corrected in place
-    V_t* gv = reinterpret_cast<V_t*>(grow);
-    if (XQ > 0) {
+    const int nvec = p.V / VEC;
+
 #pragma unroll
-        for (int q = 0; q < NXQ; ++q) {
-            const int k = q * 32 + lane;
-            if (k < nvec) {
-                float x[VEC]; vec_get<VEC>(xr[q], x);
-                float y[VEC];
+    for (int r = 0; r < kGradFramesPerWarp / F; ++r) {
+        int tt[F]; bool live[F];
+        int2 ha[F][NCH]; int hbb[F][NCH], hbl[F][NCH];
+        V_t xr[F][NXQ]; float2 fr[F];
+        // ---- every global load of the F frames ----
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) {
-                    y[j] = fast_ex2(fmaf(x[j] - fr.x, kLog2e, -fr.y));
-                    if (k * VEC + j == p.blank) y[j] -= gblank;
-                    y[j] *= head;
+        for (int f = 0; f < F; ++f) {
+            tt[f] = t_first + warp * kGradFramesPerWarp + r * F + f;
+            live[f] = cta_live && tt[f] < Tb;
+            fr[f] = make_float2(0.0f, 0.0f);
+            if (live[f]) {
+                fr[f] = w.fr[(size_t)b * p.T + tt[f]];
+                const float* xrow = p.logits + b * p.st_b + (long long)tt[f] * p.st_t;
+                if (XQ > 0) {
+                    const V_t* xv = reinterpret_cast<const V_t*>(xrow);
+#pragma unroll
+                    for (int q = 0; q < NXQ; ++q) { const int k = q * 32 + lane; xr[f][q] = k < nvec ? __ldg(xv + k) : vec_fill<VEC>(0.0f); }
                 }
-                V_t o; memcpy(&o, y, sizeof(o));
-                gv[k] = o;
-            }
-        }
-    } else {
-        for (int k = lane; k < nvec; k += 32) {
-            float x[VEC]; vec_get<VEC>(__ldg(xv + k), x);
-            float y[VEC];
+                if (CH > 0) {
+                    const int2* A = hA0 + (size_t)(tt[f] - t_first) * pairs;
+                    const int2* Bh = hB0 + (size_t)(tt[f] - t_first) * pairs;
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                y[j] = fast_ex2(fmaf(x[j] - fr.x, kLog2e, -fr.y));
-                if (k * VEC + j == p.blank) y[j] -= gblank;
-                y[j] *= head;
+                    for (int c = 0; c < NCH; ++c) {
+                        const int g = c * 32 + lane;
+                        ha[f][c] = make_int2(0, 0); hbb[f][c] = 0; hbl[f][c] = 0;
+                        if (g <= Lb) {
+                            ha[f][c] = __ldg(A + g);
+                            hbb[f][c] = __ldg(&Bh[Lb - g].x);
+                            if (g < Lb) hbl[f][c] = __ldg(&Bh[Lb - 1 - g].y);
+                        }
+                    }
+                }
             }
-            V_t o; memcpy(&o, y, sizeof(o));
-            gv[k] = o;
         }
-    }
-    for (int v = nvec * VEC + lane; v < p.V; v += 32) {
-        float y = fast_ex2(fmaf(__ldg(xrow + v) - fr.x, kLog2e, -fr.y));
-        if (v == p.blank) y -= gblank;
-        grow[v] = y * head;
-    }
-    __syncwarp();
-    // label columns: the first occurrence of each label value owns its column and sums
-    // the occupancy of every later occurrence (deterministic, no atomics)
-    for (int j = lane; j < Lb; j += 32) {
-        if (!s_fst[j]) continue;
-        float occ = 0.0f;
-        for (int k = j; k >= 0; k = s_nxt[k]) occ += gbuf[k];
-        const int v = s_lab[j];
-        const float y = fast_ex2(fmaf(__ldg(xrow + v) - fr.x, kLog2e, -fr.y));
-        grow[v] = head * (y - occ * rZ);
+        // ---- per frame: occupancy, softmax, gradient row ----
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+            const int t = tt[f];
+            if (t >= p.T) continue;
+            float* grow = p.grad + b * p.gst_b + (long long)t * p.gst_t;
+            if (!live[f]) { zero_row<VEC>(grow, p.V, lane); continue; }
+            const float* xrow = p.logits + b * p.st_b + (long long)t * p.st_t;
+            float* gbuf = gbuf0 + (size_t)(r * F + f) * w.Lp;
+            float zb = 0.0f, zl = 0.0f;
+            if (CH > 0) {
+                float wb[NCH], wl[NCH]; int eb[NCH], el[NCH];
+                int emax = INT_MIN;
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    hw_weight(ha[f][c].x, hbb[f][c], ofb[c], wb[c], eb[c]);
+                    hw_weight(ha[f][c].y, hbl[f][c], ofl[c], wl[c], el[c]);
+                    emax = max(emax, max(eb[c], el[c]));
+                }
+                emax = __reduce_max_sync(0xffffffffu, emax);
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    const int g = c * 32 + lane;
+                    zb += xscale0(wb[c], eb[c] - emax);
+                    const float v = xscale0(wl[c], el[c] - emax);
+                    zl += v;
+                    if (g < Lb) gbuf[g] = v;
+                }
+            } else {
+                const int2* A = hA0 + (size_t)(t - t_first) * pairs;
+                const int2* Bh = hB0 + (size_t)(t - t_first) * pairs;
+                int emax = INT_MIN;
+                for (int g = lane; g <= Lb; g += 32) {
+                    const int2 av = __ldg(A + g), oa = __ldg(oA + g);
+                    float wgt; int e;
+                    hw_weight(av.x, __ldg(&Bh[Lb - g].x), oa.x + __ldg(&oB[Lb - g].x), wgt, e);
+                    emax = max(emax, e);
+                    if (g < Lb) { hw_weight(av.y, __ldg(&Bh[Lb - 1 - g].y), oa.y + __ldg(&oB[Lb - 1 - g].y), wgt, e); emax = max(emax, e); }
+                }
+                emax = __reduce_max_sync(0xffffffffu, emax);
+                for (int g = lane; g <= Lb; g += 32) {
+                    const int2 av = __ldg(A + g), oa = __ldg(oA + g);
+                    float wgt; int e;
+                    hw_weight(av.x, __ldg(&Bh[Lb - g].x), oa.x + __ldg(&oB[Lb - g].x), wgt, e);
+                    zb += xscale0(wgt, e - emax);
+                    if (g < Lb) {
+                        hw_weight(av.y, __ldg(&Bh[Lb - 1 - g].y), oa.y + __ldg(&oB[Lb - 1 - g].y), wgt, e);
+                        const float v = xscale0(wgt, e - emax);
+                        zl += v; gbuf[g] = v;
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                zb += __shfl_xor_sync(0xffffffffu, zb, o);
+                zl += __shfl_xor_sync(0xffffffffu, zl, o);
+            }
+            const float rZ = 1.0f / (zb + zl);
+            const float gblank = zb * rZ;
+            __syncwarp();
+            // dense row: head * softmax, blank column corrected in place
+            const float fmx = fr[f].x, flz = fr[f].y;
+            V_t* gv = reinterpret_cast<V_t*>(grow);
+            if (XQ > 0) {
+#pragma unroll
+                for (int q = 0; q < NXQ; ++q) {
+                    const int k = q * 32 + lane;
+                    if (k < nvec) {
+                        float x[VEC]; vec_get<VEC>(xr[f][q], x);
+                        float y[VEC];
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j) {
+                            y[j] = fast_ex2(fmaf(x[j] - fmx, kLog2e, -flz));
+                            if (k * VEC + j == p.blank) y[j] -= gblank;
+                            y[j] *= head;
+                        }
+                        V_t o; memcpy(&o, y, sizeof(o));
+                        gv[k] = o;
+                    }
+                }
+            } else {
+                const V_t* xv = reinterpret_cast<const V_t*>(xrow);
+                for (int k = lane; k < nvec; k += 32) {
+                    float x[VEC]; vec_get<VEC>(__ldg(xv + k), x);
+                    float y[VEC];
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) {
+                        y[j] = fast_ex2(fmaf(x[j] - fmx, kLog2e, -flz));
+                        if (k * VEC + j == p.blank) y[j] -= gblank;
+                        y[j] *= head;
+                    }
+                    V_t o; memcpy(&o, y, sizeof(o));
+                    gv[k] = o;
+                }
+            }
+            for (int v = nvec * VEC + lane; v < p.V; v += 32) {
+                float y = fast_ex2(fmaf(__ldg(xrow + v) - fmx, kLog2e, -flz));
+                if (v == p.blank) y -= gblank;
+                grow[v] = y * head;
+            }
+            __syncwarp();
+            // label columns: one lane per distinct label value sums the occupancy of its occurrences in
+            // position order (deterministic, no atomics) and rewrites the column
+            for (int d = lane; d < nd; d += 32) {
+                const int2 e = s_dl[d];
+                const int end = s_dl[d + 1].y;
+                float occ = 0.0f;
+                for (int k = e.y; k < end; ++k) occ += gbuf[s_ord[k]];
+                if (e.x == p.blank) occ += zb;                       // invalid input (label == blank): keep both
+                const float y = fast_ex2(fmaf(__ldg(xrow + e.x) - fmx, kLog2e, -flz));
+                grow[e.x] = head * (y - occ * rZ);
+            }
+        }
     }
 }
 
