@@ -85,8 +85,15 @@ bool pick_stages(int W, int NW, int* stages) {
     return false;
 }
 
+// k_grad overlaps k_walk only while every walker CTA of the batch can be resident together
+bool overlap_allowed(int B) {
+    const char* e = getenv("CTCB_OVERLAP");
+    if (e) return atoi(e) != 0;
+    return B <= 296;
+}
+
 struct Layout {
-    size_t off_Tb, off_Lb, off_flags, off_lab, off_ord, off_dl, off_nd, off_fr, off_E, off_hA, off_hB, off_oA, off_oB, total;
+    size_t off_Tb, off_Lb, off_flags, off_lab, off_rank, off_dl, off_nd, off_fr, off_E, off_hA, off_hB, off_oA, off_oB, off_gprog, total;
     int Lp, W, NB, dense, P, NW;
     const WalkEntry* walk;
 };
@@ -110,9 +117,10 @@ Layout make_layout(int T, int B, int V, int Lmax, int need_grad) {
     l.off_Lb = take(sizeof(int) * B);
     l.off_flags = take(sizeof(int) * B);
     l.off_lab = take(sizeof(int) * (size_t)B * l.Lp);
-    l.off_ord = take(sizeof(int) * (size_t)B * l.Lp);
+    l.off_rank = take(sizeof(int) * (size_t)B * l.Lp);
     l.off_dl = take(sizeof(int2) * (size_t)B * (l.Lp + 1));
     l.off_nd = take(sizeof(int) * B);
+    l.off_gprog = take(sizeof(int) * 2 * (size_t)B);
     l.off_fr = take(sizeof(float2) * (size_t)B * T);
     l.off_E = take(sizeof(double) * (size_t)B * l.NB * l.W * ctcb::kEC);
     if (need_grad) {
@@ -132,7 +140,7 @@ ctcb::Workspace carve(const Layout& l, void* ws) {
     w.Lb = reinterpret_cast<int*>(base + l.off_Lb);
     w.flags = reinterpret_cast<int*>(base + l.off_flags);
     w.lab = reinterpret_cast<int*>(base + l.off_lab);
-    w.ord = reinterpret_cast<int*>(base + l.off_ord);
+    w.rank = reinterpret_cast<int*>(base + l.off_rank);
     w.dl = reinterpret_cast<int2*>(base + l.off_dl);
     w.nd = reinterpret_cast<int*>(base + l.off_nd);
     w.fr = reinterpret_cast<float2*>(base + l.off_fr);
@@ -141,6 +149,7 @@ ctcb::Workspace carve(const Layout& l, void* ws) {
     w.hB = reinterpret_cast<int2*>(base + l.off_hB);
     w.oA = reinterpret_cast<int2*>(base + l.off_oA);
     w.oB = reinterpret_cast<int2*>(base + l.off_oB);
+    w.gprog = reinterpret_cast<int*>(base + l.off_gprog);
     w.Lp = l.Lp; w.W = l.W; w.NB = l.NB; w.dense = l.dense; w.P = l.P; w.NW = l.NW;
     return w;
 }
@@ -244,7 +253,23 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
         int stages = 0;
         if (!pick_stages(lay.W, we->NW, &stages))
             return fail(CTCB_UNSUPPORTED, "Lmax=%d V=%d: the emission ring does not fit in shared memory", p->Lmax, p->V);
-        const size_t smem = ctcb::walk_smem_bytes(lay.W, we->NW, stages);
+        size_t smem = ctcb::walk_smem_bytes(lay.W, we->NW, stages);
+        if (need_grad && (phases & PH_BACKWARD) && overlap_allowed(p->B)) {
+            // SM partitioning by shared-memory reservation: the gradient kernel runs concurrently
+            // (programmatic dependent launch); its CTAs must not share an SM with a walker, whose
+            // T-step dependent chain is the critical path.  The walkers therefore ask for all the
+            // shared memory their share of an SM has, and the gradient CTAs land on the other SMs.
+            int dev = 0, nsm = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+            const char* eps = getenv("CTCB_WALK_PER_SM");
+            int per_sm = (2 * p->B + nsm - 1) / nsm;
+            if (eps && atoi(eps) > per_sm) per_sm = atoi(eps);
+            const size_t share = (size_t)233472 / per_sm;
+            size_t want = share > 2048 ? (share - 1024) / 128 * 128 : 0;
+            if (want > 232448) want = 232448;
+            if (want > smem) smem = want;
+        }
         const WalkFn wfn = we->fn[need_grad ? 1 : 0];
         const int vec = pick_vec(p->logits, p->logits_stride_t, p->logits_stride_b, p->V);
         const size_t esm = 2 * (size_t)lay.Lp * sizeof(int);
@@ -274,16 +299,17 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
     }
     if (phases & PH_BACKWARD) {
         ctcb::GradArgs ga{dp, w};
-        const size_t gsm = ctcb::grad_smem_bytes(lay.Lp);
+        const int gpairs = p->Lmax + 1;
+        const int gch = gpairs <= 32 ? 1 : gpairs <= 64 ? 2 : gpairs <= 128 ? 4 : gpairs <= 256 ? 8 : gpairs <= 512 ? 16 : 0;
+        const size_t gsm = ctcb::grad_smem_bytes(lay.Lp, 32 * gch);
         if (gsm > 200 * 1024) return fail(CTCB_UNSUPPORTED, "Lmax=%d too long for the gradient kernel", p->Lmax);
         int vec = pick_vec(p->logits, p->logits_stride_t, p->logits_stride_b, p->V);
         const int gvec = pick_vec(p->grad, p->grad_stride_t, p->grad_stride_b, p->V);
         if (gvec < vec) vec = gvec;
-        const int pairs = p->Lmax + 1;
-        const int ch = pairs <= 32 ? 1 : pairs <= 64 ? 2 : pairs <= 128 ? 4 : pairs <= 256 ? 8 : pairs <= 512 ? 16 : 0;
+        const int ch = gch;
         const int units = (p->V / vec + 31) / 32;
         const int xq = units <= 1 ? 1 : units <= 2 ? 2 : units <= 4 ? 4 : 0;
-        const dim3 ggrid(lay.NB, p->B);                  // one frame block per CTA
+        const dim3 ggrid(p->B, lay.NB);                  // one frame block per CTA, utterance-fastest
         using GradFn = void (*)(ctcb::GradArgs);
         GradFn gfn = nullptr;
 #define GRAD_X(V_, C_) (xq == 1 ? ctcb::k_grad<V_, C_, 1> : xq == 2 ? ctcb::k_grad<V_, C_, 2> : xq == 4 ? ctcb::k_grad<V_, C_, 4> : ctcb::k_grad<V_, C_, 0>)
@@ -296,7 +322,18 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
             std::lock_guard<std::mutex> lk(mu);
             CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(gfn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
         }
-        gfn<<<ggrid, 128, gsm, stream>>>(ga);
+        // programmatic dependent of k_walk when both are enqueued by this call: the gradient CTAs
+        // start while the walkers run and wait per frame block on Workspace::gprog.  Not when
+        // per-kernel events sit between the launches (ctcb_loss_grad_timed) or for batches whose
+        // walkers do not fit the GPU at once (the waiting CTAs would hold slots the walkers need).
+        const bool overlap = (phases & PH_FORWARD) && !g_prof_events && overlap_allowed(p->B);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = ggrid; cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = gsm; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = overlap ? 1 : 0;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, gfn, ga));
         mark(stream);
     }
     CUDA_TRY(cudaGetLastError());

@@ -59,9 +59,9 @@ struct Problem {          // device view of ctcb_problem_t
 struct Workspace {        // carved out of the caller's workspace by the host (ctcb.cu)
     int* Tb; int* Lb; int* flags;     // (B,)
     int* lab;                         // (B, Lp) int32 labels
-    int* ord;                         // (B, Lp) label positions sorted by (label value, position)
-    int2* dl;                         // (B, Lp+1) distinct labels in increasing order: {value, first index into ord};
-                                      //   entry nd is the sentinel {-1, L}
+    int* rank;                        // (B, Lp) rank of each label position in the order (label value, position)
+    int2* dl;                         // (B, Lp+1) distinct labels in increasing order: {value, start
+                                      //   of its run in rank order}; entry nd is the sentinel {-1, L}
     int* nd;                          // (B,) number of distinct labels
     float2* fr;                       // (B, T) {row max, log2 sum exp2((x-max)*log2e)}
     double* E;                        // (B, NB, W, kEC) emissions exp(x - rowmax) of frame block n = t / 8, frame-minor:
@@ -71,6 +71,8 @@ struct Workspace {        // carved out of the caller's workspace by the host (c
     int2* hB;                         // same for beta'_t in the reversed walker's pair coordinates, relative to oB
     int2* oA;                         // (B, NB, NW*PW) exponent offsets {blank, label} valid for frame block n
     int2* oB;
+    int* gprog;                       // (B, 2) frame blocks whose history is complete {alpha walker, beta walker}:
+                                      //   published with release/gpu scope, polled by the gradient CTAs
     int Lp, W, NB, dense, P, NW;      // PW = 32*P pairs per walker warp
 };
 
@@ -292,10 +294,11 @@ __global__ void __launch_bounds__(128) k_emit(Problem p, Workspace w) {
     if (!meta_cta) return;
     // ---- per-utterance metadata ----
     // The gradient kernel sums the occupancy of every occurrence of a label value into that
-    // value's column in a FIXED order (no atomics): positions sorted by (value, position), and
-    // the list of distinct values with the start of each run.  Ranks by counting (L <= 2047).
+    // value's column in a FIXED order (no atomics): it writes the occupancies at their rank in
+    // the order (value, position), so that each distinct value is one contiguous run, and walks the
+    // list of distinct values {value, start of its run}.  Ranks by counting (L <= 2047).
     int* lab = w.lab + (size_t)b * w.Lp;
-    int* ord = w.ord + (size_t)b * w.Lp;
+    int* rank = w.rank + (size_t)b * w.Lp;
     int2* dl = w.dl + (size_t)b * (w.Lp + 1);
     int* s_run = slab + w.Lp;                      // start of the run a position opens, or -1
     __shared__ int s_nd;
@@ -307,7 +310,7 @@ __global__ void __launch_bounds__(128) k_emit(Problem p, Workspace w) {
         if (j > 0 && slab[j - 1] == v) ++rep;
         int lt = 0, eqb = 0;
         for (int k = 0; k < L; ++k) { const int u = slab[k]; lt += u < v; eqb += (u == v) & (k < j); }
-        ord[lt + eqb] = j;
+        rank[j] = lt + eqb;
         s_run[j] = eqb == 0 ? lt : -1;
     }
     if (rep) atomicAdd(&s_rep, rep);
@@ -328,6 +331,7 @@ __global__ void __launch_bounds__(128) k_emit(Problem p, Workspace w) {
         if (Tb <= 0 || L + s_rep > Tb) flags |= UTT_INFEASIBLE;
         w.Tb[b] = Tb; w.Lb[b] = L; w.flags[b] = flags;
         w.nd[b] = s_nd; dl[s_nd] = make_int2(-1, L);
+        w.gprog[2 * b] = 0; w.gprog[2 * b + 1] = 0;
         if (p.status) p.status[b] = flags;
         if (flags & UTT_INFEASIBLE) p.loss[b] = 0.0f;   // defined behaviour, SURVEY 7.3-6
     }
@@ -356,6 +360,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "@p bra D_%=;\n\t"
         "bra W_%=;\n\t"
         "D_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
 }
 __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -493,11 +511,18 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
             if (lane == 0) { sts_f64(lsum, s); sts_release(lsum + 8, 1); }
         }
         if (lane == 0) {
-            int st = 0, ph = 1;                 // first re-use of stage 0 waits for its first release
-            for (int n = npro; n < NQ; ++n) {
-                mbar_wait(&empty[st], ph ^ 1);
-                issue(n, st);
-                if (++st == NS) { st = 0; ph ^= 1; }
+            // Group n is complete (every walker warp handed its ring stage back, after storing its
+            // history) -> refill the stage with block n + NS and publish the progress for the
+            // gradient CTAs, which run concurrently (k_grad is a programmatic dependent of this
+            // kernel).  A completion that is immediately followed by the next one is not published
+            // on its own: the fence of a release at gpu scope costs about one group.
+            int* gp = HIST ? w.gprog + 2 * b + DIR : nullptr;
+            int st = 0; uint32_t par = 0;
+            for (int n = 0; n < NQ; ++n) {
+                mbar_wait(&empty[st], par);
+                if (n + NS < NQ) issue(n + NS, st);
+                if (++st == NS) { st = 0; par ^= 1; }
+                if (HIST && (n + 1 == NQ || !mbar_test(&empty[st], par))) st_release_gpu(gp, n + 1);
             }
         }
         return;
@@ -781,6 +806,9 @@ template <int P, int NW, bool HIST>
 __global__ void __launch_bounds__((NW + 1) * 32) k_walk(WalkArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int b = blockIdx.x;
+    // the gradient kernel may start as soon as every walker CTA is resident: its CTAs wait per
+    // frame block on the progress this kernel publishes (Workspace::gprog)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int flags = a.w.flags[b], Tb = a.w.Tb[b], Lb = a.w.Lb[b];
     if (flags & UTT_INFEASIBLE) return;
     if (blockIdx.y == 0) walk_dir<P, NW, 0, HIST>(a, smem_raw, Tb, Lb);
@@ -817,17 +845,19 @@ constexpr int kNoState = INT_MIN / 2;
 
 // high word of a positive fp64 -> its 20 mantissa bits as a float in [1,2)
 __device__ __forceinline__ float hw_mant(int h) { return __int_as_float(((h & 0x000fffff) << 3) | 0x3f800000); }
-// weight (mantissa product in [1,4), total exponent) of alpha*beta' for one state
+// weight (mantissa product in [1,4), total exponent) of alpha*beta' for one state; an exactly-zero
+// factor (high word 0) gives the exponent kNoState, which xscale0 turns into weight 0
 __device__ __forceinline__ void hw_weight(int ha, int hb, int off, float& wgt, int& e) {
-    const bool zero = (ha == 0) | (hb == 0);
-    wgt = zero ? 0.0f : hw_mant(ha) * hw_mant(hb);
-    e = zero ? kNoState : (ha >> 20) + (hb >> 20) + off;
+    wgt = hw_mant(ha) * hw_mant(hb);
+    e = min((unsigned)ha, (unsigned)hb) == 0u ? kNoState : (ha >> 20) + (hb >> 20) + off;
 }
 
 constexpr int kGradFramesPerWarp = 2;  // 4 warps x 2 frames = one frame block per CTA
 
-__host__ __device__ inline size_t grad_smem_bytes(int Lp) {
-    return (size_t)Lp * 4 + (size_t)(Lp + 1) * 8 + (size_t)4 * kGradFramesPerWarp * Lp * 4 + 8;
+// occupancy row of one frame in rank order: Lp label slots, or a slot per register-resident pair
+__host__ __device__ inline int grad_row_floats(int Lp, int pairs_cap) { return ((Lp > pairs_cap ? Lp : pairs_cap) + 3) & ~3; }
+__host__ __device__ inline size_t grad_smem_bytes(int Lp, int pairs_cap) {
+    return (size_t)(Lp + 1) * 8 + (size_t)4 * kGradFramesPerWarp * grad_row_floats(Lp, pairs_cap) * 4 + 16;
 }
 
 // XQ = VEC-wide loads per lane that hold the frame's logits row in registers (issued together
@@ -838,23 +868,33 @@ __global__ void __launch_bounds__(128) k_grad(GradArgs a) {
     constexpr int NCH = CH > 0 ? CH : 1, NXQ = XQ > 0 ? XQ : 1;
     constexpr int F = (CH > 0 && CH <= 4) ? kGradFramesPerWarp : 1;      // frames in flight per warp
     const Problem& p = a.p; const Workspace& w = a.w;
-    const int b = blockIdx.y, blk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int Tb = w.Tb[b], Lb = w.Lb[b];
     const bool infeasible = (w.flags[b] & UTT_INFEASIBLE) != 0;
+    // CTAs are dispatched utterance-fastest, and per utterance in the order the walkers complete
+    // the frame blocks: the two walkers meet in the middle, so from the middle outwards
+    const int NQ = infeasible ? 0 : (Tb + kG - 1) / kG;
+    int blk = blockIdx.y;
+    if (blk < NQ) blk = (blk & 1) ? NQ / 2 - (blk + 1) / 2 : NQ / 2 + blk / 2;
     const float head = p.head ? p.head[b] : 1.0f;
     const int t_first = blk * kG;
-    const bool cta_live = !infeasible && t_first < Tb;
-    extern __shared__ __align__(8) unsigned char gsm_raw[];
-    int2* s_dl = reinterpret_cast<int2*>(gsm_raw);                                   // Lp + 1
-    int* s_ord = reinterpret_cast<int*>(s_dl + (w.Lp + 1));                          // Lp
-    float* gbuf0 = reinterpret_cast<float*>(s_ord + w.Lp) + (size_t)warp * kGradFramesPerWarp * w.Lp;
+    const bool cta_live = blk < NQ;
+    const int GW = grad_row_floats(w.Lp, 32 * CH);
+    extern __shared__ __align__(16) unsigned char gsm_raw[];
+    float* gbuf0 = reinterpret_cast<float*>(gsm_raw) + (size_t)warp * kGradFramesPerWarp * GW;
+    int2* s_dl = reinterpret_cast<int2*>(reinterpret_cast<float*>(gsm_raw) + (size_t)4 * kGradFramesPerWarp * GW);   // Lp + 1
+    const int* rank = w.rank + (size_t)b * w.Lp;
     int nd = 0;
     if (cta_live) {
         nd = w.nd[b];
-        const int* ord = w.ord + (size_t)b * w.Lp;
         const int2* dl = w.dl + (size_t)b * (w.Lp + 1);
-        for (int j = tid; j < Lb; j += 128) s_ord[j] = ord[j];
         for (int j = tid; j <= nd; j += 128) s_dl[j] = dl[j];
+        if (tid == 0) {
+            // block n is frame block n of the alpha walker and block NQ-1-n of the beta walker
+            const int* gp = w.gprog + 2 * b;
+            while (ld_acquire_gpu(gp) < blk + 1) __nanosleep(256);
+            while (ld_acquire_gpu(gp + 1) < NQ - blk) __nanosleep(256);
+        }
     }
     __syncthreads();
 
@@ -865,18 +905,20 @@ __global__ void __launch_bounds__(128) k_grad(GradArgs a) {
     const int2* oA = w.oA + blkoff * pairs;
     const int2* oB = w.oB + blkoff * pairs;
     // alpha pair g <-> beta' pairs: blank of pair g = reversed-walker blank of slot L-g, label of
-    // pair g = reversed-walker label of slot L-1-g.  Offsets of the block, combined per state.
-    int ofb[NCH], ofl[NCH];
+    // pair g = reversed-walker label of slot L-1-g.  Per lane and chunk, once per frame block: the
+    // (clamped) history indices, the combined offsets -- kNoState for pairs beyond the lattice,
+    // whose history is never masked by the walkers -- and the slot of the label state in rank order.
+    int ibb[NCH], ibl[NCH], ofb[NCH], ofl[NCH], rk[NCH];
     if (CH > 0 && cta_live) {
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const int g = c * 32 + lane;
-            ofb[c] = ofl[c] = 0;
-            if (g <= Lb) {
-                const int2 oa = __ldg(oA + g);
-                ofb[c] = oa.x + __ldg(&oB[Lb - g].x);
-                if (g < Lb) ofl[c] = oa.y + __ldg(&oB[Lb - 1 - g].y);
-            }
+            ibb[c] = max(Lb - g, 0); ibl[c] = max(Lb - 1 - g, 0);
+            const int2 oa = __ldcg(oA + g);
+            const int ob = __ldcg(&oB[ibb[c]].x), ol = __ldcg(&oB[ibl[c]].y);
+            ofb[c] = g <= Lb ? oa.x + ob : kNoState;
+            ofl[c] = g < Lb ? oa.y + ol : kNoState;
+            rk[c] = g < Lb ? rank[g] : g;
         }
     }
     const int nvec = p.V / VEC;
@@ -901,17 +943,13 @@ __global__ void __launch_bounds__(128) k_grad(GradArgs a) {
                     for (int q = 0; q < NXQ; ++q) { const int k = q * 32 + lane; xr[f][q] = k < nvec ? __ldg(xv + k) : vec_fill<VEC>(0.0f); }
                 }
                 if (CH > 0) {
-                    const int2* A = hA0 + (size_t)(tt[f] - t_first) * pairs;
+                    const int2* A = hA0 + (size_t)(tt[f] - t_first) * pairs + lane;
                     const int2* Bh = hB0 + (size_t)(tt[f] - t_first) * pairs;
 #pragma unroll
                     for (int c = 0; c < NCH; ++c) {
-                        const int g = c * 32 + lane;
-                        ha[f][c] = make_int2(0, 0); hbb[f][c] = 0; hbl[f][c] = 0;
-                        if (g <= Lb) {
-                            ha[f][c] = __ldg(A + g);
-                            hbb[f][c] = __ldg(&Bh[Lb - g].x);
-                            if (g < Lb) hbl[f][c] = __ldg(&Bh[Lb - 1 - g].y);
-                        }
+                        ha[f][c] = __ldcg(A + c * 32);
+                        hbb[f][c] = __ldcg(&Bh[ibb[c]].x);
+                        hbl[f][c] = __ldcg(&Bh[ibl[c]].y);
                     }
                 }
             }
@@ -924,7 +962,7 @@ __global__ void __launch_bounds__(128) k_grad(GradArgs a) {
             float* grow = p.grad + b * p.gst_b + (long long)t * p.gst_t;
             if (!live[f]) { zero_row<VEC>(grow, p.V, lane); continue; }
             const float* xrow = p.logits + b * p.st_b + (long long)t * p.st_t;
-            float* gbuf = gbuf0 + (size_t)(r * F + f) * w.Lp;
+            float* gbuf = gbuf0 + (size_t)(r * F + f) * GW;
             float zb = 0.0f, zl = 0.0f;
             if (CH > 0) {
                 float wb[NCH], wl[NCH]; int eb[NCH], el[NCH];
@@ -938,33 +976,32 @@ __global__ void __launch_bounds__(128) k_grad(GradArgs a) {
                 emax = __reduce_max_sync(0xffffffffu, emax);
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
-                    const int g = c * 32 + lane;
                     zb += xscale0(wb[c], eb[c] - emax);
                     const float v = xscale0(wl[c], el[c] - emax);
                     zl += v;
-                    if (g < Lb) gbuf[g] = v;
+                    gbuf[rk[c]] = v;
                 }
             } else {
                 const int2* A = hA0 + (size_t)(t - t_first) * pairs;
                 const int2* Bh = hB0 + (size_t)(t - t_first) * pairs;
                 int emax = INT_MIN;
                 for (int g = lane; g <= Lb; g += 32) {
-                    const int2 av = __ldg(A + g), oa = __ldg(oA + g);
+                    const int2 av = __ldcg(A + g), oa = __ldcg(oA + g);
                     float wgt; int e;
-                    hw_weight(av.x, __ldg(&Bh[Lb - g].x), oa.x + __ldg(&oB[Lb - g].x), wgt, e);
+                    hw_weight(av.x, __ldcg(&Bh[Lb - g].x), oa.x + __ldcg(&oB[Lb - g].x), wgt, e);
                     emax = max(emax, e);
-                    if (g < Lb) { hw_weight(av.y, __ldg(&Bh[Lb - 1 - g].y), oa.y + __ldg(&oB[Lb - 1 - g].y), wgt, e); emax = max(emax, e); }
+                    if (g < Lb) { hw_weight(av.y, __ldcg(&Bh[Lb - 1 - g].y), oa.y + __ldcg(&oB[Lb - 1 - g].y), wgt, e); emax = max(emax, e); }
                 }
                 emax = __reduce_max_sync(0xffffffffu, emax);
                 for (int g = lane; g <= Lb; g += 32) {
-                    const int2 av = __ldg(A + g), oa = __ldg(oA + g);
+                    const int2 av = __ldcg(A + g), oa = __ldcg(oA + g);
                     float wgt; int e;
-                    hw_weight(av.x, __ldg(&Bh[Lb - g].x), oa.x + __ldg(&oB[Lb - g].x), wgt, e);
+                    hw_weight(av.x, __ldcg(&Bh[Lb - g].x), oa.x + __ldcg(&oB[Lb - g].x), wgt, e);
                     zb += xscale0(wgt, e - emax);
                     if (g < Lb) {
-                        hw_weight(av.y, __ldg(&Bh[Lb - 1 - g].y), oa.y + __ldg(&oB[Lb - 1 - g].y), wgt, e);
+                        hw_weight(av.y, __ldcg(&Bh[Lb - 1 - g].y), oa.y + __ldcg(&oB[Lb - 1 - g].y), wgt, e);
                         const float v = xscale0(wgt, e - emax);
-                        zl += v; gbuf[g] = v;
+                        zl += v; gbuf[rank[g]] = v;
                     }
                 }
             }
@@ -1017,19 +1054,22 @@ __global__ void __launch_bounds__(128) k_grad(GradArgs a) {
                 grow[v] = y * head;
             }
             __syncwarp();
-            // label columns: one lane per distinct label value sums the occupancy of its occurrences in
-            // position order (deterministic, no atomics) and rewrites the column
+            // label columns: one lane per distinct label value sums its run of the rank-ordered
+            // occupancies in position order (deterministic, no atomics) and rewrites the column
             for (int d = lane; d < nd; d += 32) {
                 const int2 e = s_dl[d];
                 const int end = s_dl[d + 1].y;
                 float occ = 0.0f;
-                for (int k = e.y; k < end; ++k) occ += gbuf[s_ord[k]];
+                for (int k = e.y; k < end; ++k) occ += gbuf[k];
                 if (e.x == p.blank) occ += zb;                       // invalid input (label == blank): keep both
                 const float y = fast_ex2(fmaf(__ldg(xrow + e.x) - fmx, kLog2e, -flz));
                 grow[e.x] = head * (y - occ * rZ);
             }
         }
     }
+    // the stream's next kernel must also see what the walkers write last (loss, loss_sum): one CTA
+    // holds this grid open until the walker grid has completed and flushed
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------
