@@ -44,8 +44,9 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 struct WalkCfg { int P, NW; };
 
 using WalkFn = void (*)(ctcb::WalkArgs);
-struct WalkEntry { int P, NW; WalkFn fn[2]; };   // [HIST]
-#define WALK(P_, NW_) {P_, NW_, {ctcb::k_walk<P_, NW_, false>, ctcb::k_walk<P_, NW_, true>}}
+struct WalkEntry { int P, NW; WalkFn fn[2][2]; };   // [FUSED][HIST]
+#define WALK(P_, NW_) {P_, NW_, {{ctcb::k_walk<P_, NW_, false, false>, ctcb::k_walk<P_, NW_, true, false>}, \
+                                 {ctcb::k_walk<P_, NW_, false, true>, ctcb::k_walk<P_, NW_, true, true>}}}
 const WalkEntry kWalkTable[] = {
     WALK(1, 1), WALK(2, 1), WALK(4, 1), WALK(1, 2), WALK(2, 2), WALK(4, 2), WALK(1, 3), WALK(2, 3),
     WALK(1, 4), WALK(2, 4), WALK(4, 4), WALK(2, 5), WALK(2, 6), WALK(1, 8), WALK(2, 8), WALK(4, 8),
@@ -74,12 +75,12 @@ const WalkEntry* choose_walk(int pairs) {
 }
 
 // emission ring depth: as deep as fits a modest budget (several walker CTAs share an SM)
-bool pick_stages(int W, int NW, int* stages) {
+bool pick_stages(int W, int NW, int fused_Lp, int* stages) {
     const char* es = getenv("CTCB_WALK_STAGES");
     const size_t budget = 40 * 1024, hard = 200 * 1024;
     for (int s = es ? atoi(es) : ctcb::kMaxStages; s >= 2; --s) {
         if (s > ctcb::kMaxStages) continue;
-        const size_t need = ctcb::walk_smem_bytes(W, NW, s);
+        const size_t need = ctcb::walk_smem_bytes(W, NW, s, fused_Lp);
         if (need <= budget || (s <= 3 && need <= hard)) { *stages = s; return true; }
     }
     return false;
@@ -94,9 +95,17 @@ bool overlap_allowed(int B) {
 
 struct Layout {
     size_t off_Tb, off_Lb, off_flags, off_lab, off_rank, off_dl, off_nd, off_fr, off_E, off_hA, off_hB, off_oA, off_oB, off_gprog, total;
-    int Lp, W, NB, dense, P, NW;
+    int Lp, W, NB, dense, fused, P, NW;
     const WalkEntry* walk;
 };
+
+// small dense vocabularies: the walkers' own producer warps turn logits rows into emission
+// blocks (no k_emit launch, no emission table in HBM)
+inline bool fused_emit(int V, int Lmax) {
+    const char* e = getenv("CTCB_FUSED");
+    if (e && atoi(e) == 0) return false;
+    return V <= 64;
+}
 
 // dense emission table (the whole softmax row, label-indexed by the walkers) when the
 // vocabulary is not wider than the label row; gathered columns otherwise
@@ -106,6 +115,7 @@ Layout make_layout(int T, int B, int V, int Lmax, int need_grad) {
     Layout l{};
     l.Lp = (int)align_up((size_t)(Lmax > 0 ? Lmax : 1), 4);
     l.dense = dense_table(V, Lmax) ? 1 : 0;
+    l.fused = (l.dense && fused_emit(V, Lmax)) ? 1 : 0;
     l.W = l.dense ? V : Lmax + 1;                 // columns per frame block (64 bytes each)
     l.NB = (T + ctcb::kG - 1) / ctcb::kG;
     l.walk = choose_walk(Lmax + 1);
@@ -120,9 +130,9 @@ Layout make_layout(int T, int B, int V, int Lmax, int need_grad) {
     l.off_rank = take(sizeof(int) * (size_t)B * l.Lp);
     l.off_dl = take(sizeof(int2) * (size_t)B * (l.Lp + 1));
     l.off_nd = take(sizeof(int) * B);
-    l.off_gprog = take(sizeof(int) * 2 * (size_t)B);
+    l.off_gprog = take(sizeof(int) * 4 * (size_t)B);
     l.off_fr = take(sizeof(float2) * (size_t)B * T);
-    l.off_E = take(sizeof(double) * (size_t)B * l.NB * l.W * ctcb::kEC);
+    l.off_E = take(l.fused ? 0 : sizeof(double) * (size_t)B * l.NB * l.W * ctcb::kEC);
     if (need_grad) {
         l.off_hA = take(sizeof(int2) * (size_t)B * l.NB * ctcb::kG * pairs);
         l.off_hB = take(sizeof(int2) * (size_t)B * l.NB * ctcb::kG * pairs);
@@ -151,6 +161,7 @@ ctcb::Workspace carve(const Layout& l, void* ws) {
     w.oB = reinterpret_cast<int2*>(base + l.off_oB);
     w.gprog = reinterpret_cast<int*>(base + l.off_gprog);
     w.Lp = l.Lp; w.W = l.W; w.NB = l.NB; w.dense = l.dense; w.P = l.P; w.NW = l.NW;
+    w.fused = l.fused;
     return w;
 }
 
@@ -251,9 +262,10 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
         if (!we) return fail(CTCB_UNSUPPORTED, "no walker configuration for Lmax=%d", p->Lmax);
         g_walk_p = we->P; g_walk_nw = we->NW;
         int stages = 0;
-        if (!pick_stages(lay.W, we->NW, &stages))
+        if (!pick_stages(lay.W, we->NW, lay.fused ? lay.Lp : 0, &stages))
             return fail(CTCB_UNSUPPORTED, "Lmax=%d V=%d: the emission ring does not fit in shared memory", p->Lmax, p->V);
-        size_t smem = ctcb::walk_smem_bytes(lay.W, we->NW, stages);
+        const WalkFn wfn = we->fn[lay.fused][need_grad ? 1 : 0];
+        size_t smem = ctcb::walk_smem_bytes(lay.W, we->NW, stages, lay.fused ? lay.Lp : 0);
         if (need_grad && (phases & PH_BACKWARD) && overlap_allowed(p->B)) {
             // SM partitioning by shared-memory reservation: the gradient kernel runs concurrently
             // (programmatic dependent launch); its CTAs must not share an SM with a walker, whose
@@ -267,16 +279,19 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
             if (eps && atoi(eps) > per_sm) per_sm = atoi(eps);
             const size_t share = (size_t)233472 / per_sm;
             size_t want = share > 2048 ? (share - 1024) / 128 * 128 : 0;
-            if (want > 232448) want = 232448;
+            cudaFuncAttributes fa{};
+            CUDA_TRY(cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(wfn)));
+            const size_t cap = 232448 - (fa.sharedSizeBytes + 127) / 128 * 128;   // opt-in maximum minus the kernel's static part
+            if (want > cap) want = cap;
             if (want > smem) smem = want;
         }
-        const WalkFn wfn = we->fn[need_grad ? 1 : 0];
         const int vec = pick_vec(p->logits, p->logits_stride_t, p->logits_stride_b, p->V);
         const size_t esm = 2 * (size_t)lay.Lp * sizeof(int);
         {
             std::lock_guard<std::mutex> lk(mu);
             CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(wfn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
+        if (!lay.fused) {
         const dim3 egrid((lay.NB + 3) / 4 + 1, p->B);   // + the metadata CTA of each utterance
         // NQ: vector loads per lane that hold one logits row in registers (0 = two-pass)
         const int units = (p->V / vec + 31) / 32;
@@ -293,8 +308,10 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
 #undef EMIT_NQ
 #undef EMIT_LAUNCH
         mark(stream);
-        ctcb::WalkArgs wa{w, p->T, stages, p->blank, p->loss, p->loss_sum, nullptr};
-        wfn<<<dim3(p->B, need_grad ? 2 : 1), (we->NW + 1) * 32, smem, stream>>>(wa);
+        }
+        ctcb::WalkArgs wa{dp, w, p->T, stages, p->blank, p->loss, p->loss_sum, nullptr};
+        const int wthreads = (we->NW + (lay.fused ? ctcb::kFusedProducers + 1 : 1)) * 32;
+        wfn<<<dim3(p->B, need_grad ? 2 : 1), wthreads, smem, stream>>>(wa);
         mark(stream);
     }
     if (phases & PH_BACKWARD) {

@@ -71,9 +71,11 @@ struct Workspace {        // carved out of the caller's workspace by the host (c
     int2* hB;                         // same for beta'_t in the reversed walker's pair coordinates, relative to oB
     int2* oA;                         // (B, NB, NW*PW) exponent offsets {blank, label} valid for frame block n
     int2* oB;
-    int* gprog;                       // (B, 2) frame blocks whose history is complete {alpha walker, beta walker}:
-                                      //   published with release/gpu scope, polled by the gradient CTAs
+    int* gprog;                       // (B, 4) {frame blocks whose history is complete: alpha walker, beta walker;
+                                      //   metadata ready (Tb, Lb, flags, rank, dl, nd); unused}: published with
+                                      //   release/gpu scope, polled by the gradient CTAs
     int Lp, W, NB, dense, P, NW;      // PW = 32*P pairs per walker warp
+    int fused;                        // emissions made by the walkers' producer warps (no k_emit, no E)
 };
 
 __device__ __forceinline__ long long load_as_int(const void* p, int dtype, long long i) {
@@ -331,7 +333,7 @@ __global__ void __launch_bounds__(128) k_emit(Problem p, Workspace w) {
         if (Tb <= 0 || L + s_rep > Tb) flags |= UTT_INFEASIBLE;
         w.Tb[b] = Tb; w.Lb[b] = L; w.flags[b] = flags;
         w.nd[b] = s_nd; dl[s_nd] = make_int2(-1, L);
-        w.gprog[2 * b] = 0; w.gprog[2 * b + 1] = 0;
+        w.gprog[4 * b] = 0; w.gprog[4 * b + 1] = 0; w.gprog[4 * b + 2] = 1;
         if (p.status) p.status[b] = flags;
         if (flags & UTT_INFEASIBLE) p.loss[b] = 0.0f;   // defined behaviour, SURVEY 7.3-6
     }
@@ -368,6 +370,11 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
         "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
+}
+// wait of a warp that has slack (producers run many blocks ahead): it shares an SM sub-partition
+// with a walker warp whose dependent chain is the critical path, so it must not spin on the issue port
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    while (!mbar_test(bar, parity)) __nanosleep(128);
 }
 __device__ __forceinline__ void st_release_gpu(int* p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -444,6 +451,7 @@ __device__ __forceinline__ double2 lds_v2f64(uint32_t addr) {
 // partial one), so both histories and both offset tables are indexed by t / 8.
 // ---------------------------------------------------------------------------------------
 struct WalkArgs {
+    Problem p;             // read by the fused variant only (parameter layer + logits)
     Workspace w; int T; int stages; int blank; float* loss; double* loss_sum;
     long long* trace;      // debug only (scripts/ubench/walk_trace.cu); nullptr in the product
 };
@@ -458,14 +466,17 @@ struct WalkArgs {
 struct HaloMeta { double lm; int el; int R; int F; int pad; };   // 24 bytes, 8-byte aligned
 constexpr int kHaloDepth = 4;                                    // groups a warp may lead its right neighbour by
 
-__host__ __device__ inline size_t walk_smem_bytes(int W, int NW, int stages) {
+constexpr int kFusedProducers = 2;      // fused variant: warps that turn logits rows into emission blocks
+
+// fused_Lp > 0: the fused variant also keeps the utterance's int labels (fused_Lp ints)
+__host__ __device__ inline size_t walk_smem_bytes(int W, int NW, int stages, int fused_Lp = 0) {
     return (size_t)stages * kEC * W * sizeof(double) + 2 * kMaxStages * sizeof(uint64_t) +
            (size_t)NW * kHaloDepth * kG * sizeof(double) + (size_t)NW * kHaloDepth * sizeof(HaloMeta) +
-           (size_t)NW * sizeof(int) + 32;
+           (size_t)NW * sizeof(int) + 64 + (fused_Lp ? 16 + kFusedProducers * 64 + (size_t)fused_Lp * sizeof(int) : 0);
 }
 
-template <int P, int NW, int DIR, bool HIST>
-__device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_raw, int Tb, int Lb) {
+template <int P, int NW, int DIR, bool HIST, bool FUSED>
+__device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_raw, int Tb, int Lb, int uflags) {
     constexpr int PW = 32 * P;
     constexpr unsigned FULL = 0xffffffffu;
     const Workspace& w = a.w;
@@ -482,17 +493,133 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
     const uint32_t halo = smem_u32(empty + kMaxStages);                          // [NW][4][kG] double
     const uint32_t meta = halo + NW * kHaloDepth * kG * 8;                       // [NW][4] HaloMeta
     const uint32_t prog = meta + NW * kHaloDepth * (uint32_t)sizeof(HaloMeta);   // [NW] int: groups completed
-    const uint32_t lsum = (prog + NW * 4 + 7u) & ~7u;                            // double, then an int flag
+    const uint32_t lsum = (prog + NW * 4 + 7u) & ~7u;      // double + int flag; fused: 8 doubles per producer warp at +16
+    int* slab = reinterpret_cast<int*>(smem_raw + (lsum - ring) + 32 + kFusedProducers * 64);           // fused: Lp int labels (filled by k_walk)
 
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         sts_s32(lsum + 8, 0);
+        if (FUSED) for (int q = 0; q < kFusedProducers * 8; ++q) sts_f64(lsum + 16 + q * 8, 0.0);
     }
     if (tid < NW) sts_s32(prog + tid * 4, 0);
     __syncthreads();
 
-    if (warp == NW) {                           // ---- producer warp ----
+    if (FUSED && warp >= NW && warp < NW + kFusedProducers) {
+        // ---- fused producer warps: logits rows -> emission blocks, straight into the ring ----
+        // Producer q owns the walker groups n = q, q + 2, ...  Four lanes share one frame of the
+        // block (lane = 4*frame + quarter), each holding a contiguous quarter of the row (<= 16
+        // columns, V <= 64, any stride or alignment): row max and sum need two shuffle steps per
+        // block instead of a full warp reduction per frame -- the walkers' own shuffles, which sit
+        // on the critical path, go through the same SM-wide pipe.  Every load of the NEXT block is
+        // in flight while this one is reduced.  The alpha CTA also keeps {row max, log2 sum} per
+        // frame for the gradient's softmax and sums log2(sum) for the loss.
+        const Problem& p = a.p;
+        constexpr int CPL = 16;                                        // columns per lane, at most
+        const int q = warp - NW, V = p.V;
+        const int fj = lane >> 2, qk = lane & 3;                       // frame of the block, quarter of the row
+        const int cpl = (V + 3) >> 2, col0 = qk * cpl;                 // this lane's columns [col0, col0 + cpl) below V
+        const float* base = p.logits + b * p.st_b;
+        const float kMinProb = 7.888609052210118e-31f;                 // 2^kMinLog2
+        auto load_blk = [&](int n, float (&x)[CPL]) {
+            const int t = (DIR ? NQ - 1 - n : n) * kG + fj;
+            const float* row = base + (long long)t * p.st_t + col0;
+            const bool valid = t < Tb;
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) x[i] = (valid && i < cpl && col0 + i < V) ? __ldg(row + i) : -INFINITY;
+        };
+        float cur[CPL], nxt[CPL];
+        double ls = 0.0;
+        int n = q;
+        if (n < NQ) load_blk(n, cur);
+#pragma unroll 1
+        for (; n < NQ; n += kFusedProducers) {
+            if (n + kFusedProducers < NQ) load_blk(n + kFusedProducers, nxt);
+            const int t = (DIR ? NQ - 1 - n : n) * kG + fj;
+            const bool valid = t < Tb;
+            float mx = cur[0];
+#pragma unroll
+            for (int i = 1; i < CPL; ++i) mx = fmaxf(mx, cur[i]);
+            mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, 2));
+            float e[CPL], sm = 0.0f;
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {                            // rows past T_b are all -inf: keep NaN out
+                e[i] = valid ? fast_ex2((cur[i] - mx) * kLog2e) : 0.0f;
+                sm += e[i];
+            }
+            sm += __shfl_xor_sync(FULL, sm, 1);
+            sm += __shfl_xor_sync(FULL, sm, 2);
+            if (DIR == 0 && valid && qk == 0) {
+                const float l2 = log2f(sm);
+                ls += (double)l2;
+                w.fr[(size_t)b * a.T + t] = make_float2(mx, l2);
+            }
+            const int st = n % NS, use = n / NS;
+            if (use > 0) mbar_wait_relaxed(&empty[st], (uint32_t)((use - 1) & 1));
+            const uint32_t dst = ring + (uint32_t)st * stage_bytes + (uint32_t)col0 * (kEC * 8u) + (uint32_t)fj * 8u;
+#pragma unroll
+            for (int i = 0; i < CPL; ++i)
+                if (i < cpl && col0 + i < V) sts_f64(dst + (uint32_t)i * (kEC * 8u), valid ? (double)fmaxf(e[i], kMinProb) : 0.0);
+            if (DIR == 0 && qk == 0) sts_f64(lsum + 16 + (q * 8 + fj) * 8, ls);   // before the arrive: the walkers' acquire covers it
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[st]);
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) cur[i] = nxt[i];
+        }
+        return;
+    }
+    if (FUSED && warp == NW + kFusedProducers) {
+        // ---- fused publisher warp ----
+        const Problem& p = a.p;
+        if (DIR == 0 && HIST) {
+            // metadata of the gradient kernel (what k_emit's extra CTA writes in the unfused path); the
+            // vocabulary has at most 64 symbols, so ranks come from two counting passes over the labels
+            int* rank = w.rank + (size_t)b * w.Lp;
+            int2* dl = w.dl + (size_t)b * (w.Lp + 1);
+            int c0 = 0, c1 = 0;
+            for (int j = 0; j < Lb; ++j) { const int v = slab[j]; c0 += v == lane; c1 += v == lane + 32; }
+            int i0 = c0, i1 = c1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y0 = __shfl_up_sync(FULL, i0, o), y1 = __shfl_up_sync(FULL, i1, o);
+                if (lane >= o) { i0 += y0; i1 += y1; }
+            }
+            const int tot0 = __shfl_sync(FULL, i0, 31);
+            int r0 = i0 - c0, r1 = tot0 + i1 - c1;
+            const unsigned m0 = __ballot_sync(FULL, c0 > 0), m1 = __ballot_sync(FULL, c1 > 0);
+            const unsigned below = (1u << lane) - 1u;
+            const int nd = __popc(m0) + __popc(m1);
+            if (c0 > 0) dl[__popc(m0 & below)] = make_int2(lane, r0);
+            if (c1 > 0) dl[__popc(m0) + __popc(m1 & below)] = make_int2(lane + 32, r1);
+            for (int j = 0; j < Lb; ++j) {
+                const int v = slab[j];
+                if (v == lane) rank[j] = r0++;
+                else if (v == lane + 32) rank[j] = r1++;
+            }
+            if (lane == 0) {
+                dl[nd] = make_int2(-1, Lb);
+                w.nd[b] = nd; w.Tb[b] = Tb; w.Lb[b] = Lb; w.flags[b] = uflags;
+            }
+            __syncwarp();
+            if (lane == 0) st_release_gpu(w.gprog + 4 * b + 2, 1);
+        }
+        if (HIST && lane == 0) {
+            // the last walker warp's group count (shared memory) -> global progress for the gradient CTAs
+            int* gp = w.gprog + 4 * b + DIR;
+            const uint32_t last_prog = prog + (NW - 1) * 4;
+            int seen = 0;
+            while (seen < NQ) {
+                const int v = lds_acquire(last_prog);
+                if (v > seen) { st_release_gpu(gp, v); seen = v; }
+                else __nanosleep(128);
+            }
+        }
+        (void)p;
+        return;
+    }
+
+    if (!FUSED && warp == NW) {                 // ---- producer warp (emission table from k_emit, by TMA) ----
         const double* Eb = w.E + (size_t)b * w.NB * W * kEC;
         auto issue = [&](int n, int st) {       // block of walker group n into ring stage st
             const int blk = DIR ? NQ - 1 - n : n;
@@ -516,10 +643,10 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
             // gradient CTAs, which run concurrently (k_grad is a programmatic dependent of this
             // kernel).  A completion that is immediately followed by the next one is not published
             // on its own: the fence of a release at gpu scope costs about one group.
-            int* gp = HIST ? w.gprog + 2 * b + DIR : nullptr;
+            int* gp = HIST ? w.gprog + 4 * b + DIR : nullptr;
             int st = 0; uint32_t par = 0;
             for (int n = 0; n < NQ; ++n) {
-                mbar_wait(&empty[st], par);
+                mbar_wait_relaxed(&empty[st], par);
                 if (n + NS < NQ) issue(n + NS, st);
                 if (++st == NS) { st = 0; par ^= 1; }
                 if (HIST && (n + 1 == NQ || !mbar_test(&empty[st], par))) st_release_gpu(gp, n + 1);
@@ -529,7 +656,7 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
     }
 
     // ---- walker warps ----
-    const int* lab = w.lab + (size_t)b * w.Lp;
+    const int* lab = FUSED ? slab : w.lab + (size_t)b * w.Lp;
     const int g0 = tid * P;
     const uint32_t bcol = (w.dense ? (uint32_t)a.blank : 0u) * (kEC * 8u);
     bool skip[P]; uint32_t ccol[P];
@@ -773,7 +900,7 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
             }
         }
         CTCB_TP(4);
-        if (NW > 1) {                                           // publish: halo slots, then the count
+        if (NW > 1 || (FUSED && HIST)) {                        // publish: halo slots (and history), then the count
             __syncwarp();
             if (lane == 31) sts_release(prog + warp * 4, n + 1);
         }
@@ -793,8 +920,15 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
             if (g0 + p == Lb) {
                 const double prev = p == 0 ? pm : lm[p - 1];
                 const double sb = fma(prev, fb[p], bm[p]);
-                while (lds_acquire(lsum + 8) == 0) { }
-                const double nll = -kLn2 * ((double)eb[p] + log2(sb) - lds_f64(lsum));
+                double lz = 0.0;
+                if (FUSED) {
+#pragma unroll
+                    for (int q = 0; q < kFusedProducers * 8; ++q) lz += lds_f64(lsum + 16 + q * 8);
+                } else {
+                    while (lds_acquire(lsum + 8) == 0) { }
+                    lz = lds_f64(lsum);
+                }
+                const double nll = -kLn2 * ((double)eb[p] + log2(sb) - lz);
                 a.loss[b] = (float)nll;
                 if (a.loss_sum) atomicAdd(a.loss_sum, nll);
             }
@@ -802,17 +936,94 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
     }
 }
 
-template <int P, int NW, bool HIST>
-__global__ void __launch_bounds__((NW + 1) * 32) k_walk(WalkArgs a) {
+template <int P, int NW, bool HIST, bool FUSED>
+__global__ void __launch_bounds__((NW + (FUSED ? kFusedProducers + 1 : 1)) * 32) k_walk(WalkArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int b = blockIdx.x;
-    // the gradient kernel may start as soon as every walker CTA is resident: its CTAs wait per
-    // frame block on the progress this kernel publishes (Workspace::gprog)
+    if (!FUSED) {
+        // the gradient kernel may start as soon as every walker CTA is resident: its CTAs wait per
+        // frame block on the progress this kernel publishes (Workspace::gprog)
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        const int flags = a.w.flags[b], Tb = a.w.Tb[b], Lb = a.w.Lb[b];
+        if (flags & UTT_INFEASIBLE) return;
+        if (blockIdx.y == 0) walk_dir<P, NW, 0, HIST, false>(a, smem_raw, Tb, Lb, flags);
+        else                 walk_dir<P, NW, 1, HIST, false>(a, smem_raw, Tb, Lb, flags);
+        return;
+    }
+    // ---- fused variant: no k_emit ran.  Rows a3/a5 (operator parameter layer, lattice metadata)
+    // are derived here by every walker CTA for itself. ----
+    const Problem& p = a.p;
+    const Workspace& w = a.w;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    __shared__ int s_L, s_rep, s_flags;
+    if (tid == 0) {
+        // the progress words of this call start at 0 BEFORE any gradient CTA can exist
+        w.gprog[4 * b + blockIdx.y] = 0;
+        if (blockIdx.y == 0) w.gprog[4 * b + 2] = 0;
+        __threadfence();
+        s_L = p.Lmax; s_rep = 0; s_flags = 0;
+    }
+    __syncthreads();
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    const int flags = a.w.flags[b], Tb = a.w.Tb[b], Lb = a.w.Lb[b];
+    int Tb = p.T, lenflags = 0;
+    if (p.data_len) {
+        long long t64 = load_as_int(p.data_len, p.data_len_dtype, b);
+        if (t64 < 0) { t64 = 0; lenflags = UTT_LEN_CLAMPED; }
+        if (t64 > p.T) { t64 = p.T; lenflags = UTT_LEN_CLAMPED; }
+        Tb = (int)t64;
+    }
+    int L;
+    if (p.label_len) {
+        long long l64 = load_as_int(p.label_len, p.label_len_dtype, b);
+        if (l64 < 0) { l64 = 0; lenflags = UTT_LEN_CLAMPED; }
+        if (l64 > p.Lmax) { l64 = p.Lmax; lenflags = UTT_LEN_CLAMPED; }
+        L = (int)l64;
+    } else {
+        for (int j = tid; j < p.Lmax; j += nthr)
+            if (load_as_int(p.labels, p.label_dtype, b * p.lst_b + j * p.lst_l) == p.label_pad) atomicMin(&s_L, j);
+        __syncthreads();
+        L = s_L;
+    }
+    // the labels live behind the walker's other shared-memory regions (same carve as walk_dir)
+    int* slab;
+    {
+        const size_t stage_bytes = (size_t)w.W * kEC * 8;
+        size_t off = (size_t)a.stages * stage_bytes + 2 * kMaxStages * sizeof(uint64_t) +
+                     (size_t)NW * kHaloDepth * kG * 8 + (size_t)NW * kHaloDepth * sizeof(HaloMeta) + (size_t)NW * 4;
+        off = (off + 7) & ~(size_t)7;
+        slab = reinterpret_cast<int*>(smem_raw + off + 32 + kFusedProducers * 64);
+    }
+    {
+        int bad = 0;
+        for (int j = tid; j < L; j += nthr) {
+            long long v = load_as_int(p.labels, p.label_dtype, b * p.lst_b + j * p.lst_l);
+            if (v < 0 || v >= p.V || v == p.blank) bad = 1;
+            slab[j] = (int)(v < 0 ? 0 : (v >= p.V ? p.V - 1 : v));
+        }
+        if (bad) atomicOr(&s_flags, UTT_BAD_LABEL);
+    }
+    __syncthreads();
+    {
+        int rep = 0;
+        for (int j = tid + 1; j < L; j += nthr) rep += slab[j] == slab[j - 1];
+        if (rep) atomicAdd(&s_rep, rep);
+    }
+    __syncthreads();
+    int flags = s_flags | lenflags;
+    if (Tb <= 0 || L + s_rep > Tb) flags |= UTT_INFEASIBLE;
+    if (blockIdx.y == 0 && tid == 0) {
+        if (p.status) p.status[b] = flags;
+        if (flags & UTT_INFEASIBLE) {
+            p.loss[b] = 0.0f;                        // defined behaviour, SURVEY 7.3-6
+            w.Tb[b] = Tb; w.Lb[b] = L; w.flags[b] = flags; w.nd[b] = 0;
+            st_release_gpu(w.gprog + 4 * b + 2, 1);
+        } else if (!HIST) {
+            w.Tb[b] = Tb; w.Lb[b] = L; w.flags[b] = flags;
+        }
+    }
     if (flags & UTT_INFEASIBLE) return;
-    if (blockIdx.y == 0) walk_dir<P, NW, 0, HIST>(a, smem_raw, Tb, Lb);
-    else                 walk_dir<P, NW, 1, HIST>(a, smem_raw, Tb, Lb);
+    if (blockIdx.y == 0) walk_dir<P, NW, 0, HIST, true>(a, smem_raw, Tb, L, flags);
+    else                 walk_dir<P, NW, 1, HIST, true>(a, smem_raw, Tb, L, flags);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -869,8 +1080,12 @@ __global__ void __launch_bounds__(128) k_grad(GradArgs a) {
     constexpr int F = (CH > 0 && CH <= 4) ? kGradFramesPerWarp : 1;      // frames in flight per warp
     const Problem& p = a.p; const Workspace& w = a.w;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int Tb = w.Tb[b], Lb = w.Lb[b];
-    const bool infeasible = (w.flags[b] & UTT_INFEASIBLE) != 0;
+    // the utterance's metadata is written by k_emit (complete before this grid exists) or, in the
+    // fused path, by the concurrently running alpha walker CTA
+    if (tid == 0) { while (ld_acquire_gpu(w.gprog + 4 * b + 2) == 0) __nanosleep(256); }
+    __syncthreads();
+    const int Tb = __ldcg(w.Tb + b), Lb = __ldcg(w.Lb + b);
+    const bool infeasible = (__ldcg(w.flags + b) & UTT_INFEASIBLE) != 0;
     // CTAs are dispatched utterance-fastest, and per utterance in the order the walkers complete
     // the frame blocks: the two walkers meet in the middle, so from the middle outwards
     const int NQ = infeasible ? 0 : (Tb + kG - 1) / kG;
@@ -886,12 +1101,12 @@ __global__ void __launch_bounds__(128) k_grad(GradArgs a) {
     const int* rank = w.rank + (size_t)b * w.Lp;
     int nd = 0;
     if (cta_live) {
-        nd = w.nd[b];
+        nd = __ldcg(w.nd + b);
         const int2* dl = w.dl + (size_t)b * (w.Lp + 1);
-        for (int j = tid; j <= nd; j += 128) s_dl[j] = dl[j];
+        for (int j = tid; j <= nd; j += 128) s_dl[j] = __ldcg(dl + j);
         if (tid == 0) {
             // block n is frame block n of the alpha walker and block NQ-1-n of the beta walker
-            const int* gp = w.gprog + 2 * b;
+            const int* gp = w.gprog + 4 * b;
             while (ld_acquire_gpu(gp) < blk + 1) __nanosleep(256);
             while (ld_acquire_gpu(gp + 1) < NQ - blk) __nanosleep(256);
         }
@@ -918,7 +1133,7 @@ __global__ void __launch_bounds__(128) k_grad(GradArgs a) {
             const int ob = __ldcg(&oB[ibb[c]].x), ol = __ldcg(&oB[ibl[c]].y);
             ofb[c] = g <= Lb ? oa.x + ob : kNoState;
             ofl[c] = g < Lb ? oa.y + ol : kNoState;
-            rk[c] = g < Lb ? rank[g] : g;
+            rk[c] = g < Lb ? __ldcg(rank + g) : g;
         }
     }
     const int nvec = p.V / VEC;
@@ -935,7 +1150,7 @@ __global__ void __launch_bounds__(128) k_grad(GradArgs a) {
             live[f] = cta_live && tt[f] < Tb;
             fr[f] = make_float2(0.0f, 0.0f);
             if (live[f]) {
-                fr[f] = w.fr[(size_t)b * p.T + tt[f]];
+                fr[f] = __ldcg(w.fr + (size_t)b * p.T + tt[f]);
                 const float* xrow = p.logits + b * p.st_b + (long long)tt[f] * p.st_t;
                 if (XQ > 0) {
                     const V_t* xv = reinterpret_cast<const V_t*>(xrow);
@@ -1001,7 +1216,7 @@ __global__ void __launch_bounds__(128) k_grad(GradArgs a) {
                     if (g < Lb) {
                         hw_weight(av.y, __ldcg(&Bh[Lb - 1 - g].y), oa.y + __ldcg(&oB[Lb - 1 - g].y), wgt, e);
                         const float v = xscale0(wgt, e - emax);
-                        zl += v; gbuf[rank[g]] = v;
+                        zl += v; gbuf[__ldcg(rank + g)] = v;
                     }
                 }
             }

@@ -39,9 +39,9 @@ int main(int argc, char** argv) {
     std::vector<long long> ht(tn);
     int stages = 13;
     size_t smem = walk_smem_bytes(W, TNW, stages);
-    auto fn = k_walk<TP, TNW, THIST>;
+    auto fn = k_walk<TP, TNW, THIST, false>;
     cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    WalkArgs a{w, T, stages, 0, loss, nullptr, trace};
+    WalkArgs a{Problem{}, w, T, stages, 0, loss, nullptr, trace};
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int rep = 0; rep < 3; ++rep) {
         cudaMemset(trace, 0, tn * 8);
