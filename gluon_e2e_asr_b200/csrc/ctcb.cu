@@ -47,11 +47,15 @@ using WalkFn = void (*)(ctcb::WalkArgs);
 struct WalkEntry { int P, NW; WalkFn fn[2][2]; };   // [FUSED][HIST]
 #define WALK(P_, NW_) {P_, NW_, {{ctcb::k_walk<P_, NW_, false, false>, ctcb::k_walk<P_, NW_, true, false>}, \
                                  {ctcb::k_walk<P_, NW_, false, true>, ctcb::k_walk<P_, NW_, true, true>}}}
+#ifdef CTCB_SMALL_TABLE   // experiment builds: the configurations the BASELINE shapes use
+const WalkEntry kWalkTable[] = { WALK(1, 1), WALK(2, 1), WALK(1, 4), WALK(2, 2), WALK(4, 1), WALK(2, 3), WALK(2, 5) };
+#else
 const WalkEntry kWalkTable[] = {
-    WALK(1, 1), WALK(2, 1), WALK(4, 1), WALK(1, 2), WALK(2, 2), WALK(4, 2), WALK(1, 3), WALK(2, 3),
+    WALK(1, 1), WALK(2, 1), WALK(4, 1), WALK(1, 2), WALK(2, 2), WALK(4, 2), WALK(1, 3), WALK(2, 3), WALK(4, 3),
     WALK(1, 4), WALK(2, 4), WALK(4, 4), WALK(2, 5), WALK(2, 6), WALK(1, 8), WALK(2, 8), WALK(4, 8),
     WALK(2, 12), WALK(2, 16), WALK(4, 16),
 };
+#endif
 #undef WALK
 
 const WalkEntry* find_walk(int P, int NW) {

@@ -464,7 +464,8 @@ struct WalkArgs {
 #endif
 
 struct HaloMeta { double lm; int el; int R; int F; int pad; };   // 24 bytes, 8-byte aligned
-constexpr int kHaloDepth = 4;                                    // groups a warp may lead its right neighbour by
+constexpr int kHaloDepth = 16;   // halo ring depth in groups (= kMaxStages): a warp cannot lead its right neighbour by more
+                                 // than the emission ring holds, because a ring stage is recycled only when every warp is done with it
 
 constexpr int kFusedProducers = 2;      // fused variant: warps that turn logits rows into emission blocks
 
@@ -677,10 +678,13 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
     }
     if (tid == 0) bm[0] = 1.0;                  // virtual alpha_{-1} = delta(s = 0)
 
-    int2* hist = nullptr; int2* offs = nullptr;
+    // history / offset rows of the current frame block: running pointers (dir 1 walks the blocks downwards)
+    int2* hch = nullptr; int2* och = nullptr;
+    constexpr long long kHistStep = (long long)kG * NW * PW, kOffStep = (long long)NW * PW;
     if (HIST) {
-        hist = (DIR ? w.hB : w.hA) + (size_t)b * w.NB * kG * NW * PW + g0;
-        offs = (DIR ? w.oB : w.oA) + (size_t)b * w.NB * NW * PW + g0;
+        const size_t blk0 = DIR ? (size_t)(NQ - 1) : 0;
+        hch = (DIR ? w.hB : w.hA) + ((size_t)b * w.NB + blk0) * kG * NW * PW + g0;
+        och = (DIR ? w.oB : w.oA) + ((size_t)b * w.NB + blk0) * NW * PW + g0;
     }
 
     const bool has_left = NW > 1 && warp > 0, has_right = NW > 1 && warp < NW - 1;
@@ -689,7 +693,7 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
     const uint32_t nb_halo = halo + (warp > 0 ? warp - 1 : 0) * kHaloDepth * kG * 8;
     const uint32_t my_meta = meta + warp * kHaloDepth * (uint32_t)sizeof(HaloMeta);
     const uint32_t nb_meta = meta + (warp > 0 ? warp - 1 : 0) * kHaloDepth * (uint32_t)sizeof(HaloMeta);
-    const uint32_t nb_prog = prog + (warp > 0 ? warp - 1 : 0) * 4, rt_prog = prog + (warp + 1 < NW ? warp + 1 : warp) * 4;
+    const uint32_t nb_prog = prog + (warp > 0 ? warp - 1 : 0) * 4;
     double pm = 0.0;                            // left neighbour's label state for the coming step (lane 0: left warp's)
     int c_el = 0, c_R = 0, c_F = 0;             // left warp's meta as of my last renormalisation
     int Rout = 0, Fout = 0;                     // my scan carry / front offset for the right warp
@@ -711,20 +715,9 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
 #pragma unroll
         for (int p = 0; p < P; ++p) yl[p] = lds_f64(stage_base + ccol[p] + (uint32_t)j0 * 8u);
         // ---- between groups: everything that needs a branch ----
-        if (has_left) { while (lds_acquire(nb_prog) < n + 1) { } }                    // left neighbour finished this group
-        if (has_right) { while (lds_relaxed(rt_prog) < n + 1 - kHaloDepth) { } }      // do not lap the halo ring
-        CTCB_TP(1);
-        // left neighbour's state for this group (written at ITS group-n boundary)
-        int m_el = 0, m_R = kZeroE, m_F = 0;
-        if (has_left) {
-            const uint32_t ma = nb_meta + par * (uint32_t)sizeof(HaloMeta);
-            const double hal = lds_f64(ma);
-            if (lane == 0) pm = hal;
-            m_el = lds_relaxed(ma + 8); m_R = lds_relaxed(ma + 12); m_F = lds_relaxed(ma + 16);
-        }
         // renormalise?  (some state drifted past 2^+-kDrift, or the left neighbour's offsets moved).
         // Positive doubles order like their high words; an exact zero (high word 0) never triggers.
-        int bad = has_left ? ((m_el ^ c_el) | (m_R ^ c_R) | (m_F ^ c_F)) : 0;
+        int bad = 0;
         {
             constexpr unsigned LO = (1023u - kDrift) << 20, SPAN = (2u * kDrift + 1u) << 20;
 #pragma unroll
@@ -734,8 +727,19 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
                 bad |= (int)(hl != 0u) & (int)(hl - LO >= SPAN);
             }
         }
+        if (has_left) { while (lds_acquire(nb_prog) < n + 1) { } }                    // left neighbour finished this group
+        CTCB_TP(1);
+        // left neighbour's state for this group (written at ITS group-n boundary)
+        int m_el = 0, m_R = kZeroE, m_F = 0;
+        if (has_left) {
+            const uint32_t ma = nb_meta + par * (uint32_t)sizeof(HaloMeta);
+            const double hal = lds_f64(ma);
+            if (lane == 0) pm = hal;
+            m_el = lds_relaxed(ma + 8); m_R = lds_relaxed(ma + 12); m_F = lds_relaxed(ma + 16);
+            bad |= (m_el ^ c_el) | (m_R ^ c_R) | (m_F ^ c_F);
+        }
         const bool trig = bad != 0;
-        if (__any_sync(FULL, trig)) {
+        if (__builtin_expect(__any_sync(FULL, trig), 0)) {
             CTCB_TP(7);
             c_el = m_el; c_R = m_R; c_F = m_F;
             int natb[P], natl[P], am[P];
@@ -813,12 +817,9 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
             sts_f64(ma, lm[P - 1]);
             sts_s32(ma + 8, el[P - 1]); sts_s32(ma + 12, Rout); sts_s32(ma + 16, Fout);
         }
-        int2* hch = nullptr;
         if (HIST) {
-            int2* o = offs + (size_t)blk * NW * PW;
 #pragma unroll
-            for (int p = 0; p < P; ++p) o[p] = make_int2(eb[p], el[p]);
-            hch = hist + (size_t)blk * kG * NW * PW;
+            for (int p = 0; p < P; ++p) och[p] = make_int2(eb[p], el[p]);
         }
         CTCB_TP(2);
         // halo slot of walking-order step s: dir 0 s = j, dir 1 s = ns-1-j
@@ -900,16 +901,18 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
             }
         }
         CTCB_TP(4);
-        if (NW > 1 || (FUSED && HIST)) {                        // publish: halo slots (and history), then the count
-            __syncwarp();
-            if (lane == 31) sts_release(prog + warp * 4, n + 1);
+        // publish: halo slots (and history), then the count; hand the ring stage back to the producer
+        // (one warp barrier orders every lane's stage reads and history stores before both)
+        __syncwarp();
+        if (lane == 31) {
+            if (NW > 1 || (FUSED && HIST)) sts_release(prog + warp * 4, n + 1);
+            mbar_arrive(&empty[st]);
         }
         CTCB_TP(5);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[st]);                  // hand the ring stage back to the producer
         CTCB_TP(6);
         stage_base += stage_bytes;
         if (++st == NS) { st = 0; ph ^= 1; stage_base = ring; }
+        if (HIST) { hch += DIR ? -kHistStep : kHistStep; och += DIR ? -kOffStep : kOffStep; }
     }
 
     if (DIR == 0) {
