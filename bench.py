@@ -9,7 +9,7 @@ V=46, L<=120, variable lengths).  N>1 (torchrun) gives every rank its own cfg2-s
 utterances -- the path has no data-path collective; the per-step float64 loss-sum all-reduce
 (NCCL) runs on a side stream -- and reports the aggregate ("scaling": "weak").
 
-`value`  : device-resident inputs, the 3-kernel step replayed from CUDA graphs, CUDA events
+`value`  : device-resident inputs, the step's kernels replayed from CUDA graphs, CUDA events
            around exactly K steps, max over ranks.
 `e2e`    : same metric through the public API (CtcLoss(...)(pred, ...).mean().backward()) with
            pinned HOST inputs: H2D of logits/labels/lengths and D2H of the loss vector are
@@ -205,25 +205,47 @@ def run_cuda(args, rank, world, local_rank):
             "loss": torch.empty((B,), device=dev), "grad": torch.empty((B, T, V), device=dev),
             "frames": float(d["pred_lengths"].sum()),
         })
-    loss_sum = torch.zeros((), dtype=torch.float64, device=dev)
+    # Per-step loss sum (float64, accumulated by the walkers) and its all-reduce.  Two slots: step i
+    # accumulates into slot i % 2 while the side branch of the same graph reduces slot (i-1) % 2 --
+    # the previous step's sum -- over NCCL, so the collective never sits on the kernels' critical path
+    # and costs no host call per step (it is part of the captured graph).
+    loss_sums = torch.zeros((2,), dtype=torch.float64, device=dev)
+    red_buf = torch.zeros((2, 3), dtype=torch.float64, device=dev)      # {loss sum, frames, utterances} per slot
+    if nset % 2:
+        nset -= 1
+        sets = sets[:nset]
+    graph_allreduce = world > 1 and not args.no_graph_allreduce
 
-    def step_eager(s):
-        ops.ctc_loss_and_grad(s["pred"], s["label"], s["pl"], s["ll"], head_grad=head, loss_sum=loss_sum,
+    def step_eager(s, slot=0):
+        ops.ctc_loss_and_grad(s["pred"], s["label"], s["pl"], s["ll"], head_grad=head, loss_sum=loss_sums[slot],
                               out_loss=s["loss"], out_grad=s["grad"], handoff="pointer")
+
+    def reduce_slot(slot):
+        red_buf[slot, 0].copy_(loss_sums[slot], non_blocking=True)
+        loss_sums[slot].zero_()
+        dist.all_reduce(red_buf[slot])
 
     stream = torch.cuda.Stream(dev)
     comm_stream = torch.cuda.Stream(dev)
     graphs = []
     with torch.cuda.stream(stream):
-        for s in sets[:2]:
-            step_eager(s)
+        for i, s in enumerate(sets[:2]):
+            step_eager(s, i % 2)
+        if world > 1:
+            reduce_slot(0); reduce_slot(1)              # NCCL warm-up outside any capture
         torch.cuda.synchronize()
         launches_per_step = _lib.last_launch_count()
         walk_cfg = _lib.last_walk_config()
-        for s in sets:
+        for i, s in enumerate(sets):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=stream):
-                step_eager(s)
+                if graph_allreduce:
+                    comm_stream.wait_stream(stream)
+                    with torch.cuda.stream(comm_stream):
+                        reduce_slot((i + 1) % 2)        # the previous step's slot
+                step_eager(s, i % 2)
+                if graph_allreduce:
+                    stream.wait_stream(comm_stream)
             graphs.append(g)
     torch.cuda.synchronize()
 
@@ -231,8 +253,6 @@ def run_cuda(args, rank, world, local_rank):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-
-    red_buf = torch.zeros((3,), dtype=torch.float64, device=dev)
 
     def run_steps(k, graph=True, allreduce=True):
         frames = 0.0
@@ -242,16 +262,15 @@ def run_cuda(args, rank, world, local_rank):
                 if graph:
                     graphs[i % nset].replay()
                 else:
-                    step_eager(s)
+                    step_eager(s, i % 2)
                 frames += s["frames"]
-                if world > 1 and allreduce:
+                if world > 1 and allreduce and not (graph and graph_allreduce):
                     # scalar loss-sum all-reduce on a side stream: never blocks the next step
                     ev = torch.cuda.Event()
                     ev.record(stream)
                     comm_stream.wait_event(ev)
                     with torch.cuda.stream(comm_stream):
-                        red_buf[0].copy_(loss_sum, non_blocking=True)
-                        dist.all_reduce(red_buf)
+                        reduce_slot(i % 2)
             stream.wait_stream(comm_stream)
         return frames
 
@@ -292,20 +311,24 @@ def run_cuda(args, rank, world, local_rank):
     eager_ms = ee0.elapsed_time(ee1) / n_eager
 
     # ---- e2e: public API, pinned host inputs, H2D + D2H inside the timed region ----------
+    # Each host batch is collated in ONE pinned arena (gluon_e2e_asr_b200.batch.PinnedBatch: what the
+    # reference's batchify + split_and_load do with four arrays), so the step's H2D is a single copy.
+    from gluon_e2e_asr_b200.batch import PinnedBatch
     hsets = []
     for s in sets[:min(nset, 8)]:
         d = s["np"]
-        hsets.append({k: torch.from_numpy(d[k]).pin_memory() for k in ("pred", "label", "pred_lengths", "label_lengths")})
-    h2d = sum(int(v.numel() * v.element_size()) for v in hsets[0].values())
+        hsets.append(PinnedBatch.from_arrays(d["pred"], d["label"], d["pred_lengths"], d["label_lengths"]))
+    h2d = hsets[0].h2d_bytes
     loss_host = torch.empty((B,), dtype=torch.float32).pin_memory()
     d2h = int(loss_host.numel() * 4)
+    for h in hsets:
+        h.load(dev)["pred"].requires_grad_(True)
 
     def e2e_step(h):
-        pred = h["pred"].to(dev, non_blocking=True).requires_grad_(True)
-        lab = h["label"].to(dev, non_blocking=True)
-        pl = h["pred_lengths"].to(dev, non_blocking=True)
-        ll = h["label_lengths"].to(dev, non_blocking=True)
-        loss = blk(pred, lab, pl, ll)
+        x = h.load(dev)                                 # one cudaMemcpyAsync: logits, labels, both length vectors
+        pred = x["pred"]
+        pred.grad = None
+        loss = blk(pred, x["label"], x["pred_lengths"], x["label_lengths"])
         loss.mean().backward()
         loss_host.copy_(loss.detach(), non_blocking=True)
         torch.cuda.current_stream().synchronize()       # the step's result is on the host
@@ -371,7 +394,8 @@ def run_cuda(args, rank, world, local_rank):
         "kernel_ms": {k: float(v) for k, v in zip(knames, kms)},
         "step_achieved": alg / (ms_per_step * 1e-3) / 1e9, "step_frac": alg / (ms_per_step * 1e-3) / 1e9 / peak,
         "note": "fp32 logits/gradient in HBM, fp64 linear-domain lattice recursion; the V=46 path is recursion-latency "
-                "bound (T dependent steps per utterance, 2B CTAs), not HBM bound: SURVEY.md 8d / DESIGN.md sections 5-6",
+                "bound (T dependent steps per utterance, 2B CTAs), not HBM bound: SURVEY.md 8d / DESIGN.md sections 5-6; "
+                "kernel_ms are the kernels timed one after the other, in the step k_grad runs concurrently with k_walk",
     }
 
     # ---- other workloads, same run (N=1 only): context numbers, not the headline ----------
@@ -403,13 +427,18 @@ def run_cuda(args, rank, world, local_rank):
                        "valid_frames_per_step": frames_all / args.steps,
                        "utterances_per_sec": B * world / (ms_per_step * 1e-3),
                        "l2": "inputs rotate over %d buffer sets (%.0f MB logits+grad > 126 MB L2)" % (nset, nset * per_set / 1e6),
-                       "launch": "%d kernels per step replayed from a CUDA graph; eager_ms_per_step=%.4f" % (launches_per_step, eager_ms),
+                       "launch": "%d kernels per step (k_grad a programmatic dependent of k_walk) replayed from a CUDA graph; "
+                                 "eager_ms_per_step=%.4f" % (launches_per_step, eager_ms),
                        "walker": {"pairs_per_lane": walk_cfg[0], "warps": walk_cfg[1]},
-                       "collective": "none on the data path; float64 loss-sum all-reduce per step on a side stream" if world > 1 else "none"},
+                       "collective": ("none on the data path; float64 loss-sum all-reduce (NCCL) of the previous step's sum on a side "
+                                      "branch of each step's CUDA graph" if graph_allreduce else
+                                      "none on the data path; float64 loss-sum all-reduce per step on a side stream")
+                       if world > 1 else "none"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
-                    "api": "CtcLoss(layout='NTC',label_layout='NT')(pred,label,pred_lengths,label_lengths).mean().backward()"},
+                    "api": "PinnedBatch.load(dev) -> CtcLoss(layout='NTC',label_layout='NT')(pred,label,pred_lengths,label_lengths)"
+                           ".mean().backward() -> loss to pinned host"},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline,
         }
@@ -419,8 +448,14 @@ def run_cuda(args, rank, world, local_rank):
             line["other_workloads"] = others
         print(json.dumps(line), flush=True)
     if world > 1:
+        # The captured graphs hold NCCL work: tearing the communicator down under them can block, and a
+        # rank that lingers would stall the launcher.  Everything is measured and printed; leave together.
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def measure_other(torch, ops, dev, oname, peak, steps=20, warmup=3):
@@ -467,6 +502,8 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--no-others", action="store_true", help="skip the context measurements of the other configs")
+    ap.add_argument("--no-graph-allreduce", action="store_true",
+                    help="N>1: issue the loss-sum all-reduce from the host every step instead of from the captured graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

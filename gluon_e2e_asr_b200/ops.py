@@ -32,6 +32,35 @@ def workspace_bytes(T, B, V, Lmax, need_grad=True):
     return _lib.workspace_bytes(T, B, V, Lmax, need_grad)
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_cur_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
+def _stream_ptr(device):
+    """cudaStream_t of torch's current stream on ``device`` (host-side plumbing, kept cheap)."""
+    if _raw_stream is not None:
+        return _raw_stream(device.index)
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class _on_device:
+    """``with torch.cuda.device(d)`` only when ``d`` is not already current."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, device):
+        same = _cur_device is not None and _cur_device() == device.index
+        self.ctx = None if same else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
 def _as_index_tensor(x, device, name):
     """labels / lengths: any float or int dtype (the reference delivers float32,
     reader_kaldi_io.py:33-35, batchify.py:78-82); other dtypes are cast to float32/int64."""
@@ -119,9 +148,9 @@ class _Call:
 
     def run(self, phase, ws, loss, grad=None, head=None, loss_sum=None, status=None, keep=False, handoff=None):
         lib = _lib.load()
-        stream = torch.cuda.current_stream(self.data.device).cuda_stream
+        stream = _stream_ptr(self.data.device)
         handoff = handoff or _HANDOFF
-        with torch.cuda.device(self.data.device):
+        with _on_device(self.data.device):
             if handoff == "dlpack" and status is None:
                 caps = []
 
@@ -165,14 +194,14 @@ class _CtcLossFn(torch.autograd.Function):
     def forward(ctx, data, label, data_lengths, label_lengths, blank_last, ntc, tn):
         call = _Call(data, label, data_lengths, label_lengths, blank_last, ntc, tn)
         need = ctx.needs_input_grad[0]
-        ws = _alloc_ws(call, need)
         loss = torch.empty((call.B,), dtype=torch.float32, device=data.device)
         ctx.call = call
         if need and data.numel() <= _FUSE_IN_FORWARD_MAX_ELEMS:
             grad = torch.empty_like(data)           # same layout as the logits: no swapaxes backward
-            call.run(_lib.PHASE_FUSED, ws, loss, grad=grad)
+            call.run(_lib.PHASE_FUSED, _cached_ws(call, data.device), loss, grad=grad)
             ctx.grad, ctx.ws = grad, None
         else:
+            ws = _alloc_ws(call, need)              # holds the history until backward: not shared
             call.run(_lib.PHASE_FORWARD, ws, loss, keep=need)
             ctx.grad, ctx.ws = None, ws
         return loss
@@ -185,10 +214,9 @@ class _CtcLossFn(torch.autograd.Function):
         if ctx.grad is not None:
             grad, ctx.grad = ctx.grad, None
             ta, ba = call._axes[0], call._axes[1]
-            with torch.cuda.device(grad.device):
+            with _on_device(grad.device):
                 _lib.check(_lib.load().ctcb_scale_rows(grad.data_ptr(), grad.stride(ta), grad.stride(ba), call.T, call.B,
-                                                       call.V, head.data_ptr(),
-                                                       torch.cuda.current_stream(grad.device).cuda_stream))
+                                                       call.V, head.data_ptr(), _stream_ptr(grad.device)))
             return grad, None, None, None, None, None, None
         ws = ctx.ws
         if ws is None:
@@ -237,6 +265,16 @@ def _ctc_loss_layout(pred, label, pred_lengths, label_lengths, blank_label, layo
 _ws_cache = {}
 
 
+def _cached_ws(call, dev):
+    """Scratch workspace per (device, stream, shape): calls on one stream are ordered, so the fused
+    forward+gradient may reuse it from call to call."""
+    key = (dev.index, _stream_ptr(dev), call.T, call.B, call.V, call.Lmax)
+    ws = _ws_cache.get(key)
+    if ws is None:
+        ws = _ws_cache[key] = _alloc_ws(call, True)
+    return ws
+
+
 def ctc_loss_and_grad(pred, label, pred_lengths=None, label_lengths=None, head_grad=None,
                       blank_label="first", layout="NTC", label_layout="NT", loss_sum=None,
                       status=None, out_loss=None, out_grad=None, handoff=None):
@@ -250,10 +288,7 @@ def ctc_loss_and_grad(pred, label, pred_lengths=None, label_lengths=None, head_g
     call = _Call(pred, label, pred_lengths, label_lengths, _blank_last(blank_label),
                  layout == "NTC", label_layout == "TN")
     dev = pred.device
-    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream, call.T, call.B, call.V, call.Lmax)
-    ws = _ws_cache.get(key)
-    if ws is None:
-        ws = _ws_cache[key] = _alloc_ws(call, True)
+    ws = _cached_ws(call, dev)
     loss = out_loss if out_loss is not None else torch.empty((call.B,), dtype=torch.float32, device=dev)
     grad = out_grad if out_grad is not None else torch.empty_like(pred)
     if head_grad is not None:
@@ -275,11 +310,11 @@ def greedy_decode(pred, pred_lengths=None, blank=0, layout="NTC"):
     toks = torch.zeros((B, T), dtype=torch.int32, device=pred.device)
     lens = torch.empty((B,), dtype=torch.int32, device=pred.device)
     lib = _lib.load()
-    with torch.cuda.device(pred.device):
+    with _on_device(pred.device):
         rc = lib.ctcb_greedy_decode(pred.data_ptr(), pred.stride(ta), pred.stride(ba),
                                     pl.data_ptr() if pl is not None else None,
                                     _DT[pl.dtype] if pl is not None else 0, T, B, V, blank,
                                     toks.data_ptr(), lens.data_ptr(),
-                                    torch.cuda.current_stream(pred.device).cuda_stream)
+                                    _stream_ptr(pred.device))
     _lib.check(rc)
     return toks, lens
