@@ -92,7 +92,8 @@ _ws_bytes = {}
 
 
 def workspace_bytes(T, B, V, Lmax, need_grad=True):
-    key = (T, B, V, Lmax, bool(need_grad), os.environ.get("CTCB_WALK_P"), os.environ.get("CTCB_WALK_NW"))
+    key = (T, B, V, Lmax, bool(need_grad), os.environ.get("CTCB_WALK_P"), os.environ.get("CTCB_WALK_NW"),
+           os.environ.get("CTCB_FUSED"))
     n = _ws_bytes.get(key)
     if n is None:
         out = ctypes.c_size_t(0)

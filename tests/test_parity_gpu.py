@@ -289,3 +289,115 @@ def test_greedy_decode(dev):
     toks, lens = toks.cpu().numpy(), lens.cpu().numpy()
     for b in range(6):
         assert list(toks[b, :lens[b]]) == ref[b]
+
+
+def _env(**kw):
+    """Context manager: set libctcb's debugging switches (read with getenv at every call)."""
+    import contextlib
+
+    @contextlib.contextmanager
+    def cm():
+        old = {k: os.environ.get(k) for k in kw}
+        try:
+            for k, v in kw.items():
+                os.environ[k] = str(v)
+            yield
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+    return cm()
+
+
+def test_overlapped_and_serial_schedules_give_the_same_bits(dev):
+    """k_grad as a programmatic dependent of k_walk (progress flags, SM partitioning) against the
+    same kernels launched one after the other: identical bits, repeatedly (a race would show)."""
+    from gluon_e2e_asr_b200 import ctc_loss_and_grad, ops
+    B, T, V, L = CONFIGS["cfg2"]
+    d = make_batch(B, T, V, L, seed=21)
+    t = _to(dev, d)
+    args = (t["pred"], t["label"], t["pred_lengths"], t["label_lengths"])
+    with _env(CTCB_OVERLAP=0):
+        ops._ws_cache.clear()
+        l0, g0 = ctc_loss_and_grad(*args)
+        l0, g0 = l0.clone(), g0.clone()
+    for rep in range(5):
+        with _env(CTCB_OVERLAP=1):
+            l1, g1 = ctc_loss_and_grad(*args, out_grad=torch.full_like(g0, float("nan")))
+        assert torch.equal(l0, l1) and torch.equal(g0, g1), "overlap run %d differs" % rep
+    with _env(CTCB_OVERLAP=1, CTCB_WALK_PER_SM=2):
+        l2, g2 = ctc_loss_and_grad(*args)
+    assert torch.equal(l0, l2) and torch.equal(g0, g2)
+
+
+def test_fused_and_unfused_emissions_agree(dev):
+    """Emission blocks made by the walkers' producer warps (V <= 64) against k_emit + TMA: the same
+    numerators; only the summation order of the loss normaliser differs."""
+    from gluon_e2e_asr_b200 import ctc_loss_and_grad, ops
+    d = make_batch(8, 200, 46, 50, seed=22)
+    t = _to(dev, d)
+    args = (t["pred"], t["label"], t["pred_lengths"], t["label_lengths"])
+    lf, gf = ctc_loss_and_grad(*args)
+    lf, gf = lf.clone(), gf.clone()
+    with _env(CTCB_FUSED=0):
+        ops._ws_cache.clear()                      # the workspace layout differs (emission table)
+        lu, gu = ctc_loss_and_grad(*args)
+    ops._ws_cache.clear()
+    torch.testing.assert_close(lf, lu, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(gf, gu, rtol=1e-5, atol=1e-7)
+    # odd vocabulary / TNC strides / blank last go through the fused producers too
+    d = make_batch(5, 61, 63, 9, seed=23, blank=62)
+    loss, grad = _run_block(dev, d, layout="TNC", blank_label="last")
+    lo, go, _ = _oracle(d, blank_label="last")
+    _check(loss, grad, lo, go, "fused V=63 TNC blank last")
+
+
+def test_step_replays_from_a_cuda_graph(dev):
+    """The two-kernel step (programmatic dependency included) captured once and replayed."""
+    from gluon_e2e_asr_b200 import ctc_loss_and_grad
+    d = make_batch(16, 120, 46, 30, seed=24)
+    t = _to(dev, d)
+    args = (t["pred"], t["label"], t["pred_lengths"], t["label_lengths"])
+    l0, g0 = ctc_loss_and_grad(*args)
+    l0, g0 = l0.clone(), g0.clone()
+    loss = torch.empty_like(l0); grad = torch.empty_like(g0)
+    s = torch.cuda.Stream(dev)
+    with torch.cuda.stream(s):
+        ctc_loss_and_grad(*args, out_loss=loss, out_grad=grad, handoff="pointer")      # warm the workspace cache
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            ctc_loss_and_grad(*args, out_loss=loss, out_grad=grad, handoff="pointer")
+        for _ in range(3):
+            loss.fill_(float("nan")); grad.fill_(float("nan"))
+            g.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(loss, l0) and torch.equal(grad, g0)
+
+
+def test_batch_larger_than_the_resident_walkers(dev):
+    """B > 296: the walkers do not fit the GPU at once, k_grad is a plain launch after them."""
+    from gluon_e2e_asr_b200 import ctc_loss_and_grad
+    d = make_batch(320, 24, 11, 6, seed=25)
+    t = _to(dev, d)
+    loss, grad = ctc_loss_and_grad(t["pred"], t["label"], t["pred_lengths"], t["label_lengths"])
+    lo, go, _ = _oracle(d)
+    _check(loss.cpu().numpy(), grad.cpu().numpy(), lo, go, "B=320")
+
+
+def test_pinned_batch_single_copy(dev):
+    from gluon_e2e_asr_b200 import CtcLoss
+    from gluon_e2e_asr_b200.batch import PinnedBatch
+    d = make_batch(4, 60, 46, 12, seed=26)
+    pb = PinnedBatch.from_arrays(d["pred"], d["label"], d["pred_lengths"], d["label_lengths"])
+    assert pb.arena.is_pinned()
+    x = pb.load(dev)
+    assert x["pred"].data_ptr() % 256 == 0 and x["label"].data_ptr() % 256 == 0
+    pred = x["pred"].requires_grad_(True)
+    loss = CtcLoss()(pred, x["label"], x["pred_lengths"], x["label_lengths"])
+    loss.sum().backward()
+    lo, go, _ = _oracle(d)
+    _check(loss.detach().cpu().numpy(), pred.grad.cpu().numpy(), lo, go, "pinned batch")
+    assert pb.load(dev)["pred"] is x["pred"]                    # persistent device arena, same views
