@@ -505,6 +505,26 @@ int ctcb_greedy_decode(const float* logits, int64_t stride_t, int64_t stride_b, 
     return CTCB_OK;
 }
 
+int ctcb_edit_distance(const int32_t* ref, int64_t ref_stride, const int32_t* ref_len, const int32_t* hyp,
+                       int64_t hyp_stride, const int32_t* hyp_len, int32_t B, int32_t max_ref, int32_t max_hyp,
+                       int32_t* out_dist, long long* totals, void* stream) {
+    if (!ref_len || !hyp_len || !out_dist || (max_ref > 0 && !ref) || (max_hyp > 0 && !hyp))
+        return fail(CTCB_INVALID_VALUE, "NULL argument");
+    if (B <= 0 || max_ref < 0 || max_hyp < 0) return fail(CTCB_INVALID_VALUE, "bad shape");
+    if (!is_device_ptr(ref_len) || !is_device_ptr(hyp_len) || !is_device_ptr(out_dist) || !is_device_ptr(ref) ||
+        !is_device_ptr(hyp) || !is_device_ptr(totals))
+        return fail(CTCB_INVALID_VALUE, "buffers must be CUDA device memory");
+    const size_t smem = sizeof(int) * ((size_t)max_hyp + 2 * ((size_t)max_hyp + 1));
+    if (smem > 200 * 1024) return fail(CTCB_UNSUPPORTED, "max_hyp=%d too long for the edit-distance kernel", max_hyp);
+    if (smem > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(ctcb::k_edit_distance), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ctcb::k_edit_distance<<<B, 128, smem, static_cast<cudaStream_t>(stream)>>>(ref, ref_stride, ref_len, hyp, hyp_stride,
+                                                                             hyp_len, max_ref, max_hyp, out_dist, totals);
+    CUDA_TRY(cudaGetLastError());
+    g_launches = 1;
+    return CTCB_OK;
+}
+
 // ---- NCCL loss-sum allreduce (dlopen, no link-time dependency) ----------------------------
 int ctcb_loss_sum_allreduce(void* nccl_comm, double* dev_values, int32_t count, void* stream) {
     typedef int (*allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);

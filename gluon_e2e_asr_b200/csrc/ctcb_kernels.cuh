@@ -1357,4 +1357,59 @@ __global__ void __launch_bounds__(256) k_greedy_decode(const float* logits, long
     if (tid == 255) out_len[b] = base + incl;
 }
 
+// ---------------------------------------------------------------------------------------
+// k_edit_distance: grid B, block 128.  scripts/swbd/wer.py:45-68 (next-row scope): Levenshtein
+// distance of one (reference, hypothesis) pair per CTA.  Row i of the DP table from row i-1:
+//     t[j] = min(d[i-1][j] + 1, d[i-1][j-1] + (ref[i-1] != hyp[j-1]))          (parallel over j)
+//     d[i][j] = min(t[j], d[i][j-1] + 1) = j + min_{k<=j}(t[k] - k)            (prefix-min scan)
+// each thread owns a contiguous chunk of columns; the scan is a warp shuffle scan of the chunk
+// minima plus one hop through shared memory.  (The reference takes d[i-1][j-1] alone on a match;
+// neighbouring cells differ by at most one, so the three-way minimum gives the same number.)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_edit_distance(const int* ref, long long ref_stride, const int* ref_len,
+                                                       const int* hyp, long long hyp_stride, const int* hyp_len,
+                                                       int max_ref, int max_hyp, int* out_dist, long long* totals) {
+    extern __shared__ int esm[];                  // hyp[M], then two rows of M + 1 cells
+    __shared__ int s_wmin[4];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = min(max(ref_len[b], 0), max_ref), M = min(max(hyp_len[b], 0), max_hyp);
+    int* s_hyp = esm; int* row0 = esm + max_hyp; int* row1 = row0 + max_hyp + 1;
+    const int* r = ref + b * ref_stride;
+    const int* h = hyp + b * hyp_stride;
+    for (int j = tid; j < M; j += 128) s_hyp[j] = h[j];
+    for (int j = tid; j <= M; j += 128) row0[j] = j;
+    __syncthreads();
+    const int chunk = (M + 1 + 127) / 128, lo = min(tid * chunk, M + 1), hi = min(lo + chunk, M + 1);
+    int* prev = row0; int* cur = row1;
+    for (int i = 1; i <= N; ++i) {
+        const int ri = r[i - 1];
+        int run = INT_MAX;                        // running min of t[k] - k over this thread's chunk
+        for (int j = lo; j < hi; ++j) {
+            const int t = j == 0 ? i : min(prev[j] + 1, prev[j - 1] + (ri != s_hyp[j - 1]));
+            run = min(run, t - j);
+            cur[j] = run;                         // chunk-local prefix minimum, completed below
+        }
+        // exclusive prefix-min of the chunk minima over the block
+        int incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl = min(incl, y); }
+        if (lane == 31) s_wmin[warp] = incl;
+        int excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = INT_MAX;
+        __syncthreads();
+        for (int k = 0; k < warp; ++k) excl = min(excl, s_wmin[k]);
+        for (int j = lo; j < hi; ++j) cur[j] = min(cur[j], excl) + j;
+        __syncthreads();
+        int* sw = prev; prev = cur; cur = sw;
+    }
+    if (tid == 0) {
+        const int d = prev[M];
+        out_dist[b] = d;
+        if (totals) {
+            atomicAdd(reinterpret_cast<unsigned long long*>(totals), (unsigned long long)d);
+            atomicAdd(reinterpret_cast<unsigned long long*>(totals + 1), (unsigned long long)N);
+        }
+    }
+}
+
 }  // namespace ctcb

@@ -318,3 +318,35 @@ def greedy_decode(pred, pred_lengths=None, blank=0, layout="NTC"):
                                     _stream_ptr(pred.device))
     _lib.check(rc)
     return toks, lens
+
+
+def edit_distance(ref, ref_lengths, hyp, hyp_lengths, totals=None):
+    """Levenshtein distance of each (reference, hypothesis) row pair -- scripts/swbd/wer.py:45-68
+    for a batch, on the device.  ref (B, Nmax) / hyp (B, Mmax) int32 CUDA tensors (unit stride
+    along the row) with int32 lengths; ``greedy_decode``'s outputs can be passed as hyp/hyp_lengths.
+    ``totals``: optional int64 CUDA tensor of 2, += {sum of distances, sum of reference lengths}.
+    Returns (B,) int32."""
+    for name, t in (("ref", ref), ("hyp", hyp), ("ref_lengths", ref_lengths), ("hyp_lengths", hyp_lengths)):
+        if not isinstance(t, torch.Tensor) or not t.is_cuda:
+            raise RuntimeError("edit_distance has no CPU path: %s must be a CUDA tensor" % name)
+        if t.dtype != torch.int32:
+            raise TypeError("%s must be int32, got %s" % (name, t.dtype))
+    if ref.dim() != 2 or hyp.dim() != 2 or ref.shape[0] != hyp.shape[0]:
+        raise ValueError("ref and hyp must be (B, N) and (B, M)")
+    if ref.shape[1] > 1 and ref.stride(1) != 1:
+        ref = ref.contiguous()
+    if hyp.shape[1] > 1 and hyp.stride(1) != 1:
+        hyp = hyp.contiguous()
+    B = ref.shape[0]
+    ref_lengths, hyp_lengths = ref_lengths.contiguous(), hyp_lengths.contiguous()
+    if totals is not None and (totals.dtype != torch.int64 or totals.numel() < 2 or not totals.is_cuda):
+        raise TypeError("totals must be an int64 CUDA tensor with two elements")
+    out = torch.empty((B,), dtype=torch.int32, device=ref.device)
+    with _on_device(ref.device):
+        rc = _lib.load().ctcb_edit_distance(ref.data_ptr(), ref.stride(0), ref_lengths.data_ptr(),
+                                            hyp.data_ptr(), hyp.stride(0), hyp_lengths.data_ptr(),
+                                            B, ref.shape[1], hyp.shape[1], out.data_ptr(),
+                                            totals.data_ptr() if totals is not None else None,
+                                            _stream_ptr(ref.device))
+    _lib.check(rc)
+    return out

@@ -134,6 +134,18 @@ int ctcb_greedy_decode(const float* logits, int64_t stride_t, int64_t stride_b,
                        int32_t T, int32_t B, int32_t V, int32_t blank,
                        int32_t* out_tokens, int32_t* out_lengths, void* stream);
 
+/* Edit distance of each (reference, hypothesis) token pair of a batch: scripts/swbd/wer.py:45-68
+ * (`_edit_distance`; next-row scope).  ref (B, max_ref) / hyp (B, max_hyp)
+ * int32 rows with the given row strides (elements) and lengths; `ctcb_greedy_decode`'s
+ * out_tokens / out_lengths can be passed as hyp / hyp_len directly, so validation WER
+ * (train_ctc_ce.py:149-168) needs no per-token host work.  out_dist (B,) int32.  When `totals` is
+ * not NULL, totals[0] += sum of distances and totals[1] += sum of reference lengths: the two
+ * numbers `compute_wer` (wer.py:9-43) divides.  Device buffers. */
+int ctcb_edit_distance(const int32_t* ref, int64_t ref_stride, const int32_t* ref_len,
+                       const int32_t* hyp, int64_t hyp_stride, const int32_t* hyp_len,
+                       int32_t B, int32_t max_ref, int32_t max_hyp,
+                       int32_t* out_dist, long long* totals, void* stream);
+
 /* Sum of `count` doubles across the ranks of an NCCL communicator, in place, on `stream`
  * (ncclAllReduce, ncclSum).  NCCL is resolved with dlopen at first use, so libctcb.so has
  * no link-time NCCL dependency.  Replaces the host-side `+=` of `.asscalar()` values

@@ -251,3 +251,32 @@ def split_and_load_slices(n, k):
         return [slice(0, n)]
     m = n // k
     return [slice(i * m, (i + 1) * m) for i in range(k - 1)] + [slice((k - 1) * m, n)]
+
+
+def edit_distance(ref, hyp):
+    """scripts/swbd/wer.py:45-68 (`_edit_distance`): full (N+1) x (M+1) table; a match copies the
+    diagonal, otherwise 1 + the smallest of the three neighbours."""
+    n, m = len(ref), len(hyp)
+    tab = [[0] * (m + 1) for _ in range(n + 1)]
+    for i in range(n + 1):
+        tab[i][0] = i
+    for j in range(m + 1):
+        tab[0][j] = j
+    for i in range(1, n + 1):
+        for j in range(1, m + 1):
+            if ref[i - 1] == hyp[j - 1]:
+                tab[i][j] = tab[i - 1][j - 1]
+            else:
+                tab[i][j] = 1 + min(tab[i - 1][j], tab[i][j - 1], tab[i - 1][j - 1])
+    return tab[n][m]
+
+
+def compute_wer(reference_corpus, translation_corpus, lower_case=False):
+    """scripts/swbd/wer.py:9-43: total edit distance over total reference length."""
+    dist = words = 0
+    for ref, hyp in zip(reference_corpus, translation_corpus):
+        if lower_case:
+            ref, hyp = [w.lower() for w in ref], [w.lower() for w in hyp]
+        dist += edit_distance(ref, hyp)
+        words += len(ref)
+    return dist / words
