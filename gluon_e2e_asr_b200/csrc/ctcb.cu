@@ -91,10 +91,12 @@ bool pick_stages(int W, int NW, int fused_Lp, int* stages) {
 }
 
 // k_grad overlaps k_walk only while every walker CTA of the batch can be resident together
-bool overlap_allowed(int B) {
+// ... and only for the fused (small-vocabulary) path: with a wide vocabulary the gradient kernel is
+// HBM-bound and wants the whole GPU; sharing it with the walkers measured no better than running after them
+bool overlap_allowed(int B, bool fused) {
     const char* e = getenv("CTCB_OVERLAP");
     if (e) return atoi(e) != 0;
-    return B <= 296;
+    return fused && B <= 296;
 }
 
 struct Layout {
@@ -270,7 +272,7 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
             return fail(CTCB_UNSUPPORTED, "Lmax=%d V=%d: the emission ring does not fit in shared memory", p->Lmax, p->V);
         const WalkFn wfn = we->fn[lay.fused][need_grad ? 1 : 0];
         size_t smem = ctcb::walk_smem_bytes(lay.W, we->NW, stages, lay.fused ? lay.Lp : 0);
-        if (need_grad && (phases & PH_BACKWARD) && overlap_allowed(p->B)) {
+        if (need_grad && (phases & PH_BACKWARD) && overlap_allowed(p->B, lay.fused != 0)) {
             // SM partitioning by shared-memory reservation: the gradient kernel runs concurrently
             // (programmatic dependent launch); its CTAs must not share an SM with a walker, whose
             // T-step dependent chain is the critical path.  The walkers therefore ask for all the
@@ -296,10 +298,11 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
             CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(wfn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
         if (!lay.fused) {
-        const dim3 egrid((lay.NB + 3) / 4 + 1, p->B);   // + the metadata CTA of each utterance
         // NQ: vector loads per lane that hold one logits row in registers (0 = two-pass)
         const int units = (p->V / vec + 31) / 32;
         const int nq = units <= 1 ? 1 : units <= 2 ? 2 : units <= 4 ? 4 : units <= 8 ? 8 : units <= 16 ? 16 : 0;
+        const int bpc = ctcb::emit_blocks_per_cta(nq);
+        const dim3 egrid((lay.NB + bpc - 1) / bpc + 1, p->B);   // + the metadata CTA of each utterance
 #define EMIT_LAUNCH(V_, Q_) ctcb::k_emit<V_, Q_><<<egrid, 128, esm, stream>>>(dp, w)
 #define EMIT_NQ(V_) switch (nq) { case 1: EMIT_LAUNCH(V_, 1); break; case 2: EMIT_LAUNCH(V_, 2); break; \
                                   case 4: EMIT_LAUNCH(V_, 4); break; case 8: EMIT_LAUNCH(V_, 8); break;  \
@@ -347,7 +350,7 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
         // start while the walkers run and wait per frame block on Workspace::gprog.  Not when
         // per-kernel events sit between the launches (ctcb_loss_grad_timed) or for batches whose
         // walkers do not fit the GPU at once (the waiting CTAs would hold slots the walkers need).
-        const bool overlap = (phases & PH_FORWARD) && !g_prof_events && overlap_allowed(p->B);
+        const bool overlap = (phases & PH_FORWARD) && !g_prof_events && overlap_allowed(p->B, lay.fused != 0);
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = ggrid; cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = gsm; cfg.stream = stream;
         cudaLaunchAttribute attr[1];

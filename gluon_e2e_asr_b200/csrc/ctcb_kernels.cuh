@@ -152,6 +152,8 @@ template <> __device__ __forceinline__ float4 vec_fill<4>(float v) { return make
 // NQ = VEC-wide loads per lane that cover one logits row (power of two, <= 16): the rows of
 // F = 16/NQ frames (at most 8) are held in registers, so every global load of those frames is
 // in flight before the first reduction.  NQ = 0: rows too wide for registers, two passes.
+__host__ __device__ constexpr int emit_blocks_per_cta(int nq) { return nq >= 8 ? 1 : 4; }
+
 template <int VEC, int NQ>
 __global__ void __launch_bounds__(128) k_emit(Problem p, Workspace w) {
     using V_t = typename VecT<VEC>::type;
@@ -193,7 +195,12 @@ __global__ void __launch_bounds__(128) k_emit(Problem p, Workspace w) {
     }
 
     const int nvec = p.V / VEC;
-    const int blk = blockIdx.x * 4 + warp, t0 = blk * kG;
+    // frame blocks per CTA: one warp per block, or -- for wide rows (8 or 16 vector loads per lane) --
+    // one block per CTA with two frames per warp: four times as many CTAs, so the grid is several
+    // waves deep and every SM keeps more row loads in flight
+    constexpr int BPC = emit_blocks_per_cta(NQ), FPW = kG * BPC / 4;
+    const int blk = BPC == 4 ? blockIdx.x * 4 + warp : blockIdx.x, t0 = blk * kG;
+    const int jbeg = BPC == 4 ? 0 : warp * FPW;
     if (!meta_cta && t0 < Tb) {
         float mxs[kG];
         const float* rows = p.logits + b * p.st_b + (long long)t0 * p.st_t;
@@ -201,7 +208,8 @@ __global__ void __launch_bounds__(128) k_emit(Problem p, Workspace w) {
             constexpr int NQ1 = NQ > 0 ? NQ : 1;
             constexpr int F = NQ1 >= 16 ? 1 : (NQ1 >= 8 ? 2 : (NQ1 >= 4 ? 4 : 8));
 #pragma unroll
-            for (int jf = 0; jf < kG; jf += F) {
+            for (int jk = 0; jk < FPW; jk += F) {
+                const int jf = jbeg + jk;
                 V_t x[F][NQ1]; float xt[F];
 #pragma unroll
                 for (int f = 0; f < F; ++f) {                   // every load of F frames in flight
@@ -247,6 +255,21 @@ __global__ void __launch_bounds__(128) k_emit(Problem p, Workspace w) {
                     mxs[jf + f] = mx[f];
                     if (lane == f && t0 + jf + f < Tb) w.fr[(size_t)b * p.T + t0 + jf + f] = make_float2(mx[f], log2f(sum[f]));
                 }
+                // the emission columns of these frames NOW, while their rows are still in L1: gathering
+                // after the whole block re-read evicted rows from L2/HBM (ncu: 1.26x the compulsory bytes)
+                {
+                    const int ncol = w.dense ? p.V : L + 1;
+                    double* eblk = w.E + ((size_t)b * w.NB + blk) * w.W * kEC;
+                    for (int col = lane; col < ncol; col += 32) {
+                        const int v = w.dense ? col : (col == 0 ? p.blank : slab[col - 1]);
+#pragma unroll
+                        for (int f = 0; f < F; ++f) {
+                            const bool valid = t0 + jf + f < Tb;
+                            const float xv = valid ? __ldg(rows + (jf + f) * p.st_t + v) : 0.0f;
+                            eblk[(size_t)col * kEC + jf + f] = valid ? (double)fast_ex2(fmaxf((xv - mx[f]) * kLog2e, kMinLog2)) : 0.0;
+                        }
+                    }
+                }
             }
         } else {
 #pragma unroll
@@ -276,7 +299,7 @@ __global__ void __launch_bounds__(128) k_emit(Problem p, Workspace w) {
                 mxs[j] = mx;
             }
         }
-        const int ncol = w.dense ? p.V : L + 1;
+        const int ncol = NQ > 0 ? 0 : (w.dense ? p.V : L + 1);      // NQ > 0: already written frame by frame
         double* eblk = w.E + ((size_t)b * w.NB + blk) * w.W * kEC;
         for (int col = lane; col < ncol; col += 32) {
             const int v = w.dense ? col : (col == 0 ? p.blank : slab[col - 1]);
@@ -1077,7 +1100,7 @@ __host__ __device__ inline size_t grad_smem_bytes(int Lp, int pairs_cap) {
 // XQ = VEC-wide loads per lane that hold the frame's logits row in registers (issued together
 // with the history loads so that one memory round trip covers both); 0 = row loaded when needed.
 template <int VEC, int CH, int XQ>
-__global__ void __launch_bounds__(128) k_grad(GradArgs a) {
+__global__ void __launch_bounds__(128, (CH == 0 || CH == 8) ? 5 : 1) k_grad(GradArgs a) {
     using V_t = typename VecT<VEC>::type;
     constexpr int NCH = CH > 0 ? CH : 1, NXQ = XQ > 0 ? XQ : 1;
     constexpr int F = (CH > 0 && CH <= 4) ? kGradFramesPerWarp : 1;      // frames in flight per warp
@@ -1231,7 +1254,7 @@ __global__ void __launch_bounds__(128) k_grad(GradArgs a) {
             const float rZ = 1.0f / (zb + zl);
             const float gblank = zb * rZ;
             __syncwarp();
-            // dense row: head * softmax, blank column corrected in place
+            // dense row: head * softmax, blank column corrected
             const float fmx = fr[f].x, flz = fr[f].y;
             V_t* gv = reinterpret_cast<V_t*>(grow);
             if (XQ > 0) {
@@ -1252,18 +1275,24 @@ __global__ void __launch_bounds__(128) k_grad(GradArgs a) {
                     }
                 }
             } else {
+                // wide rows: four vector loads in flight per lane; the blank column is fixed afterwards
                 const V_t* xv = reinterpret_cast<const V_t*>(xrow);
-                for (int k = lane; k < nvec; k += 32) {
-                    float x[VEC]; vec_get<VEC>(__ldg(xv + k), x);
-                    float y[VEC];
+                for (int k0 = lane; k0 < nvec; k0 += 128) {
+                    V_t xq[4];
 #pragma unroll
-                    for (int j = 0; j < VEC; ++j) {
-                        y[j] = fast_ex2(fmaf(x[j] - fmx, kLog2e, -flz));
-                        if (k * VEC + j == p.blank) y[j] -= gblank;
-                        y[j] *= head;
+                    for (int u = 0; u < 4; ++u) { const int k = k0 + 32 * u; xq[u] = k < nvec ? __ldg(xv + k) : vec_fill<VEC>(0.0f); }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int k = k0 + 32 * u;
+                        if (k < nvec) {
+                            float x[VEC]; vec_get<VEC>(xq[u], x);
+                            float y[VEC];
+#pragma unroll
+                            for (int j = 0; j < VEC; ++j) y[j] = head * fast_ex2(fmaf(x[j] - fmx, kLog2e, -flz));
+                            V_t o; memcpy(&o, y, sizeof(o));
+                            gv[k] = o;
+                        }
                     }
-                    V_t o; memcpy(&o, y, sizeof(o));
-                    gv[k] = o;
                 }
             }
             for (int v = nvec * VEC + lane; v < p.V; v += 32) {
@@ -1272,6 +1301,13 @@ __global__ void __launch_bounds__(128) k_grad(GradArgs a) {
                 grow[v] = y * head;
             }
             __syncwarp();
+            if (XQ == 0) {
+                if (lane == 0 && p.blank < nvec * VEC) {
+                    const float y = fast_ex2(fmaf(__ldg(xrow + p.blank) - fmx, kLog2e, -flz));
+                    grow[p.blank] = head * (y - gblank);
+                }
+                __syncwarp();
+            }
             // label columns: one lane per distinct label value sums its run of the rank-ordered
             // occupancies in position order (deterministic, no atomics) and rewrites the column
             for (int d = lane; d < nd; d += 32) {

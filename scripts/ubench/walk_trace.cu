@@ -13,6 +13,9 @@ using namespace ctcb;
 #ifndef TNW
 #define TNW 2
 #endif
+#ifndef THIST
+#define THIST true
+#endif
 int main(int argc, char** argv) {
     const int B = argc > 1 ? atoi(argv[1]) : 32, T = argc > 2 ? atoi(argv[2]) : 500, L = argc > 3 ? atoi(argv[3]) : 120;
     const int V = 46, W = 46, Lp = (L + 3) / 4 * 4, NB = (T + kG - 1) / kG, PAIRS = TNW * TP * 32;
@@ -41,14 +44,14 @@ int main(int argc, char** argv) {
     std::vector<long long> ht(tn);
     int stages = argc > 4 ? atoi(argv[4]) : 8;
     size_t smem = walk_smem_bytes(W, TNW, stages, Lp);
-    auto fn = k_walk<TP, TNW, true, true>;
+    auto fn = k_walk<TP, TNW, THIST, true>;
     cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     WalkArgs a{p, w, T, stages, 0, loss, nullptr, trace};
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int rep = 0; rep < 3; ++rep) {
         cudaMemset(trace, 0, tn * 8);
         cudaEventRecord(e0);
-        fn<<<dim3(B, 2), (TNW + kFusedProducers + 1) * 32, smem>>>(a);
+        fn<<<dim3(B, THIST ? 2 : 1), (TNW + kFusedProducers + 1) * 32, smem>>>(a);
         cudaEventRecord(e1);
         cudaError_t err = cudaDeviceSynchronize();
         float ms; cudaEventElapsedTime(&ms, e0, e1);
@@ -58,7 +61,7 @@ int main(int argc, char** argv) {
     std::vector<float> hl(B); cudaMemcpy(hl.data(), loss, B * 4, cudaMemcpyDeviceToHost);
     printf("loss[0] = %f\n", hl[0]);
     const int NQ = (T + kG - 1) / kG;
-    for (int dir = 0; dir < 2; ++dir)
+    for (int dir = 0; dir < (THIST ? 2 : 1); ++dir)
         for (int wp = 0; wp < TNW; ++wp) {
             long long* t = ht.data() + (size_t)(dir * 32 + wp) * 4096;
             double acc[7] = {0};
