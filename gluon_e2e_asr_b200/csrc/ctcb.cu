@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <utility>
 #include <vector>
 
 #include "ctcb.h"
@@ -97,6 +98,26 @@ bool overlap_allowed(int B, bool fused) {
     const char* e = getenv("CTCB_OVERLAP");
     if (e) return atoi(e) != 0;
     return fused && B <= 296;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) only when a launch needs more than any before it
+// (per device and kernel): it is a driver call, and this sits on the per-step host path
+cudaError_t ensure_dynamic_smem(const void* fn, size_t bytes) {
+    static std::mutex mu;
+    static std::vector<std::pair<std::pair<int, const void*>, size_t>> seen;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& e : seen)
+        if (e.first.first == dev && e.first.second == fn) {
+            if (e.second >= bytes) return cudaSuccess;
+            const cudaError_t rc = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+            if (rc == cudaSuccess) e.second = bytes;
+            return rc;
+        }
+    const cudaError_t rc = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (rc == cudaSuccess) seen.push_back({{dev, fn}, bytes});
+    return rc;
 }
 
 struct Layout {
@@ -261,7 +282,6 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const ctcb::Problem dp = to_device_problem(p);
     const ctcb::Workspace w = carve(lay, workspace);
-    static std::mutex mu;
 
     if (phases & PH_FORWARD) {
         const WalkEntry* we = lay.walk;
@@ -293,10 +313,7 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
         }
         const int vec = pick_vec(p->logits, p->logits_stride_t, p->logits_stride_b, p->V);
         const size_t esm = 2 * (size_t)lay.Lp * sizeof(int);
-        {
-            std::lock_guard<std::mutex> lk(mu);
-            CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(wfn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        }
+        CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(wfn), smem));
         if (!lay.fused) {
         // NQ: vector loads per lane that hold one logits row in registers (0 = two-pass)
         const int units = (p->V / vec + 31) / 32;
@@ -342,10 +359,7 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
         gfn = vec == 4 ? GRAD_CH(4) : vec == 2 ? GRAD_CH(2) : GRAD_CH(1);
 #undef GRAD_CH
 #undef GRAD_X
-        if (gsm > 48 * 1024) {
-            std::lock_guard<std::mutex> lk(mu);
-            CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(gfn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
-        }
+        if (gsm > 48 * 1024) CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(gfn), gsm));
         // programmatic dependent of k_walk when both are enqueued by this call: the gradient CTAs
         // start while the walkers run and wait per frame block on Workspace::gprog.  Not when
         // per-kernel events sit between the launches (ctcb_loss_grad_timed) or for batches whose
