@@ -401,3 +401,37 @@ def test_pinned_batch_single_copy(dev):
     lo, go, _ = _oracle(d)
     _check(loss.detach().cpu().numpy(), pred.grad.cpu().numpy(), lo, go, "pinned batch")
     assert pb.load(dev)["pred"] is x["pred"]                    # persistent device arena, same views
+
+
+@pytest.mark.parametrize("B,T,V,L,seed", [
+    (2, 2300, 30, 2047, 40),      # the longest label row the library takes: 16 walker warps x 4 pairs per lane
+    (2, 1500, 30, 700, 41),       # 12 walker warps
+    (3, 900, 64, 200, 42),        # widest fused vocabulary
+    (3, 300, 65, 40, 43),         # narrowest unfused vocabulary (k_emit + TMA, dense table)
+    (4, 64, 2, 20, 44),           # V = 2: blank and one symbol, every neighbour a repeat
+    (1, 1, 5, 1, 45),             # one frame, one label
+])
+def test_extreme_shapes_vs_oracle(dev, B, T, V, L, seed):
+    d = make_batch(B, T, V, L, seed=seed)
+    loss, grad = _run_block(dev, d)
+    lo, go, ok = _oracle(d)
+    _check(loss, grad, lo, go, "B%d T%d V%d L%d" % (B, T, V, L))
+
+
+def test_strided_views_and_wide_logit_range(dev):
+    """Logits that are a slice of a larger tensor (T and B strides not compact, V stride 1), and a
+    logit spread of +-30 (per-frame probabilities down to e^-60)."""
+    from gluon_e2e_asr_b200 import ctc_loss_and_grad
+    d = make_batch(5, 90, 46, 20, seed=46, scale=12.0)
+    big = torch.zeros((7, 100, 46 + 18), device=dev)
+    big[1:6, 4:94, 9:55] = torch.tensor(d["pred"], device=dev)
+    view = big[1:6, 4:94, 9:55]
+    assert not view.is_contiguous() and view.stride(2) == 1
+    t = _to(dev, d)
+    out = torch.zeros_like(big)
+    gview = out[1:6, 4:94, 9:55]
+    loss, grad = ctc_loss_and_grad(view, t["label"], t["pred_lengths"], t["label_lengths"], out_grad=gview)
+    lo, go, ok = _oracle(d)
+    assert ok.all()
+    _check(loss.cpu().numpy(), gview.cpu().numpy(), lo, go, "strided")
+    assert out[0].abs().max().item() == 0 and out[:, :4].abs().max().item() == 0      # nothing written outside the view
