@@ -424,7 +424,21 @@ HostScratch g_hs[64];
 size_t dt_size(int d) { return (d == CTCB_I32 || d == CTCB_F32) ? 4 : 8; }
 }  // namespace
 
-int ctcb_loss_grad_host(const ctcb_problem_t* hp, int device) {
+namespace {
+int loss_grad_host_impl(const ctcb_problem_t* hp, int device, float** dev_grad);
+}
+
+int ctcb_loss_grad_host(const ctcb_problem_t* hp, int device) { return loss_grad_host_impl(hp, device, nullptr); }
+
+int ctcb_loss_grad_host_resident(const ctcb_problem_t* hp, int device, float** dev_grad) {
+    if (!dev_grad) return fail(CTCB_INVALID_VALUE, "dev_grad is NULL");
+    return loss_grad_host_impl(hp, device, dev_grad);
+}
+
+namespace {
+// dev_grad != nullptr: the gradient is computed but stays in the device scratch (its address is
+// returned); hp->grad is ignored
+int loss_grad_host_impl(const ctcb_problem_t* hp, int device, float** dev_grad) {
     if (int rc = validate(hp)) return rc;
     if (device < 0 || device >= 64) return fail(CTCB_INVALID_VALUE, "device %d out of range", device);
     int ndev = 0;
@@ -432,12 +446,12 @@ int ctcb_loss_grad_host(const ctcb_problem_t* hp, int device) {
         return fail(CTCB_UNSUPPORTED, "CUDA device %d not available (there is no CPU path)", device);
     CUDA_TRY(cudaSetDevice(device));
     const int T = hp->T, B = hp->B, V = hp->V, Lmax = hp->Lmax;
-    const bool need_grad = hp->grad != nullptr;
+    const bool need_grad = hp->grad != nullptr || dev_grad != nullptr;
     // the host entry takes compact buffers only: strides must describe TNC or NTC exactly
     const bool tnc = hp->logits_stride_t == (long long)B * V && hp->logits_stride_b == V;
     const bool ntc = hp->logits_stride_t == V && hp->logits_stride_b == (long long)T * V;
     if (!tnc && !ntc) return fail(CTCB_INVALID_VALUE, "host entry needs compact TNC or NTC logits");
-    if (need_grad && (hp->grad_stride_t != hp->logits_stride_t || hp->grad_stride_b != hp->logits_stride_b))
+    if (need_grad && !dev_grad && (hp->grad_stride_t != hp->logits_stride_t || hp->grad_stride_b != hp->logits_stride_b))
         return fail(CTCB_INVALID_VALUE, "host entry needs grad in the logits' layout");
     if (Lmax > 0 && !((hp->label_stride_b == Lmax && hp->label_stride_l == 1) || (hp->label_stride_b == 1 && hp->label_stride_l == B)))
         return fail(CTCB_INVALID_VALUE, "host entry needs compact NT or TN labels");
@@ -469,6 +483,7 @@ int ctcb_loss_grad_host(const ctcb_problem_t* hp, int device) {
     ctcb_problem_t d = *hp;
     d.logits = reinterpret_cast<float*>(base + o_log);
     d.grad = need_grad ? reinterpret_cast<float*>(base + o_grad) : nullptr;
+    if (dev_grad) { d.grad_stride_t = hp->logits_stride_t; d.grad_stride_b = hp->logits_stride_b; *dev_grad = d.grad; }
     d.labels = base + o_lab;
     d.data_lengths = hp->data_lengths ? base + o_dl : nullptr;
     d.label_lengths = hp->label_lengths ? base + o_ll : nullptr;
@@ -485,13 +500,14 @@ int ctcb_loss_grad_host(const ctcb_problem_t* hp, int device) {
     if (hp->loss_sum) COPY_TRY(cudaMemcpyAsync(base + o_sum, hp->loss_sum, sizeof(double), cudaMemcpyHostToDevice, s));
     if (int rc = ctcb_loss_grad(&d, base + o_ws, ws_bytes, s)) return rc;
     COPY_TRY(cudaMemcpyAsync(hp->loss, base + o_loss, sizeof(float) * B, cudaMemcpyDeviceToHost, s));
-    if (need_grad) COPY_TRY(cudaMemcpyAsync(hp->grad, base + o_grad, n_log, cudaMemcpyDeviceToHost, s));
+    if (need_grad && !dev_grad) COPY_TRY(cudaMemcpyAsync(hp->grad, base + o_grad, n_log, cudaMemcpyDeviceToHost, s));
     if (hp->loss_sum) COPY_TRY(cudaMemcpyAsync(hp->loss_sum, base + o_sum, sizeof(double), cudaMemcpyDeviceToHost, s));
     if (hp->status) COPY_TRY(cudaMemcpyAsync(hp->status, base + o_stat, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
 #undef COPY_TRY
     CUDA_TRY(cudaStreamSynchronize(s));
     return CTCB_OK;
 }
+}  // namespace
 
 int ctcb_scale_rows(float* grad, int64_t stride_t, int64_t stride_b, int32_t T, int32_t B, int32_t V,
                     const float* head_grad, void* stream) {

@@ -120,6 +120,13 @@ int ctcb_loss_grad_timed(const ctcb_problem_t* p, void* workspace, size_t worksp
  * bench.py's end-to-end leg. */
 int ctcb_loss_grad_host(const ctcb_problem_t* p, int device);
 
+/* The training-step form of the host entry: inputs come from host buffers, the loss goes back to
+ * the host, and the gradient STAYS on the device, where the model's backward pass consumes it
+ * (train_ctc_ce.py:363-366: only `loss.asscalar()` crosses back).  *dev_grad receives the device
+ * address of the gradient (same layout as the logits; library scratch, valid until the next
+ * host-entry call on this device); p->grad is ignored. */
+int ctcb_loss_grad_host_resident(const ctcb_problem_t* p, int device, float** dev_grad);
+
 /* The operator's Backward for a caller that ran ctcb_loss_grad with head_grad = NULL in its
  * Forward (what MXNet's operator does: Forward stores the gradient, Backward multiplies it by
  * the head gradient -- SURVEY 8a row a8): grad[b, t, :] *= head_grad[b], in place. */

@@ -435,3 +435,29 @@ def test_strided_views_and_wide_logit_range(dev):
     assert ok.all()
     _check(loss.cpu().numpy(), gview.cpu().numpy(), lo, go, "strided")
     assert out[0].abs().max().item() == 0 and out[:, :4].abs().max().item() == 0      # nothing written outside the view
+
+
+def test_host_entry_with_resident_gradient(dev):
+    """ctcb_loss_grad_host_resident: host buffers in, loss back, gradient left on the device."""
+    import ctypes
+    from gluon_e2e_asr_b200 import _lib, ctc_loss_and_grad
+    d = make_batch(4, 50, 46, 9, seed=27)
+    t = _to(dev, d)
+    loss, grad = ctc_loss_and_grad(t["pred"], t["label"], t["pred_lengths"], t["label_lengths"])
+    x = np.ascontiguousarray(d["pred"]); l = np.empty((4,), np.float32)
+    lab = np.ascontiguousarray(d["label"])
+    p = _lib.Problem()
+    p.T, p.B, p.V, p.Lmax, p.blank, p.label_pad = 50, 4, 46, 9, 0, 0
+    p.logits, p.logits_stride_t, p.logits_stride_b = x.ctypes.data, 46, 50 * 46
+    p.labels, p.label_dtype, p.label_stride_b, p.label_stride_l = lab.ctypes.data, _lib.DT_F32, 9, 1
+    p.data_lengths, p.data_lengths_dtype = d["pred_lengths"].ctypes.data, _lib.DT_F32
+    p.label_lengths, p.label_lengths_dtype = d["label_lengths"].ctypes.data, _lib.DT_F32
+    p.loss = l.ctypes.data
+    dg = ctypes.c_void_p()
+    _lib.check(_lib.load().ctcb_loss_grad_host_resident(ctypes.byref(p), 0, ctypes.byref(dg)))
+    np.testing.assert_array_equal(l, loss.cpu().numpy())
+    got = torch.empty_like(grad)
+    assert dg.value
+    ctypes.CDLL("libcudart.so.12").cudaMemcpy(ctypes.c_void_p(got.data_ptr()), dg, ctypes.c_size_t(got.numel() * 4), 3)
+    assert torch.equal(got, grad)
+    assert _lib.load().ctcb_loss_grad_host_resident(ctypes.byref(p), 0, None) == _lib.CTCB_INVALID_VALUE
