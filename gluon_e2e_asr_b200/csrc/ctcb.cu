@@ -418,7 +418,11 @@ int ctcb_backward(const ctcb_problem_t* p, void* workspace, size_t workspace_byt
 
 // ---- host-buffer entry ------------------------------------------------------------------
 namespace {
-struct HostScratch { void* ptr = nullptr; size_t bytes = 0; cudaStream_t stream = nullptr; };
+struct HostScratch {
+    void* ptr = nullptr; size_t bytes = 0;
+    cudaStream_t stream = nullptr, stream2 = nullptr;          // second stream: the other half of a pipelined batch
+    cudaEvent_t ev_small = nullptr, ev_copy0 = nullptr, ev_done1 = nullptr;
+};
 std::mutex g_hs_mu;
 HostScratch g_hs[64];
 size_t dt_size(int d) { return (d == CTCB_I32 || d == CTCB_F32) ? 4 : 8; }
@@ -456,8 +460,17 @@ int loss_grad_host_impl(const ctcb_problem_t* hp, int device, float** dev_grad) 
     if (Lmax > 0 && !((hp->label_stride_b == Lmax && hp->label_stride_l == 1) || (hp->label_stride_b == 1 && hp->label_stride_l == B)))
         return fail(CTCB_INVALID_VALUE, "host entry needs compact NT or TN labels");
 
-    size_t ws_bytes = 0;
-    ctcb_workspace_bytes(T, B, V, Lmax, need_grad, &ws_bytes);
+    // Two halves of the batch on two streams: the second half's logits cross PCIe while the first
+    // half's kernels run (the kernels are bound by the T-step recursion, not by the batch size).
+    // Needs utterance-major buffers (NTC logits, NT labels) so that a half is one contiguous copy.
+    const bool nt = Lmax == 0 || (hp->label_stride_b == Lmax && hp->label_stride_l == 1);
+    // (measured at cfg2: no faster than one copy + one launch -- two launches of latency-bound kernels cost
+    // what the overlap gains -- so it is opt-in: CTCB_HOST_CHUNKS=2)
+    int nchunk = 1;
+    if (const char* ec = getenv("CTCB_HOST_CHUNKS")) { if (atoi(ec) >= 2 && ntc && nt && B >= 16) nchunk = 2; }
+    const int Bc[2] = {nchunk == 2 ? (B + 1) / 2 : B, nchunk == 2 ? B - (B + 1) / 2 : 0};
+    size_t ws_bytes[2] = {0, 0};
+    for (int c = 0; c < nchunk; ++c) ctcb_workspace_bytes(T, Bc[c], V, Lmax, need_grad, &ws_bytes[c]);
     const size_t n_log = sizeof(float) * (size_t)T * B * V;
     const size_t n_lab = dt_size(hp->label_dtype) * (size_t)B * (Lmax > 0 ? Lmax : 1);
     const size_t n_dl = hp->data_lengths ? dt_size(hp->data_lengths_dtype) * (size_t)B : 0;
@@ -465,13 +478,20 @@ int loss_grad_host_impl(const ctcb_problem_t* hp, int device, float** dev_grad) 
     const size_t n_head = hp->head_grad ? sizeof(float) * (size_t)B : 0;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
-    const size_t o_ws = take(ws_bytes), o_log = take(n_log), o_grad = take(need_grad ? n_log : 0), o_lab = take(n_lab),
+    const size_t o_ws[2] = {take(ws_bytes[0]), take(ws_bytes[1])};
+    const size_t o_log = take(n_log), o_grad = take(need_grad ? n_log : 0), o_lab = take(n_lab),
                  o_dl = take(n_dl), o_ll = take(n_ll), o_head = take(n_head), o_loss = take(sizeof(float) * B),
                  o_sum = take(sizeof(double)), o_stat = take(sizeof(int) * B);
     std::lock_guard<std::mutex> lk(g_hs_mu);
     HostScratch& hs = g_hs[device];
-    if (!hs.stream && cudaStreamCreateWithFlags(&hs.stream, cudaStreamNonBlocking) != cudaSuccess)
-        return fail(CTCB_MEMOPS_FAILED, "cudaStreamCreate failed");
+    if (!hs.stream) {
+        if (cudaStreamCreateWithFlags(&hs.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&hs.stream2, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&hs.ev_small, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&hs.ev_copy0, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&hs.ev_done1, cudaEventDisableTiming) != cudaSuccess)
+            return fail(CTCB_MEMOPS_FAILED, "stream / event creation failed");
+    }
     if (hs.bytes < o) {
         if (hs.ptr) cudaFree(hs.ptr);
         hs.ptr = nullptr; hs.bytes = 0;
@@ -480,25 +500,40 @@ int loss_grad_host_impl(const ctcb_problem_t* hp, int device, float** dev_grad) 
     }
     char* base = static_cast<char*>(hs.ptr);
     cudaStream_t s = hs.stream;
-    ctcb_problem_t d = *hp;
-    d.logits = reinterpret_cast<float*>(base + o_log);
-    d.grad = need_grad ? reinterpret_cast<float*>(base + o_grad) : nullptr;
-    if (dev_grad) { d.grad_stride_t = hp->logits_stride_t; d.grad_stride_b = hp->logits_stride_b; *dev_grad = d.grad; }
-    d.labels = base + o_lab;
-    d.data_lengths = hp->data_lengths ? base + o_dl : nullptr;
-    d.label_lengths = hp->label_lengths ? base + o_ll : nullptr;
-    d.head_grad = hp->head_grad ? reinterpret_cast<float*>(base + o_head) : nullptr;
-    d.loss = reinterpret_cast<float*>(base + o_loss);
-    d.loss_sum = hp->loss_sum ? reinterpret_cast<double*>(base + o_sum) : nullptr;
-    d.status = hp->status ? reinterpret_cast<int32_t*>(base + o_stat) : nullptr;
+    if (dev_grad) *dev_grad = reinterpret_cast<float*>(base + o_grad);
 #define COPY_TRY(expr) do { if ((expr) != cudaSuccess) return fail(CTCB_MEMOPS_FAILED, "%s: %s", #expr, cudaGetErrorString(cudaGetLastError())); } while (0)
-    COPY_TRY(cudaMemcpyAsync(base + o_log, hp->logits, n_log, cudaMemcpyHostToDevice, s));
+    // small inputs of the whole batch first, then the logits half by half
     if (Lmax > 0) COPY_TRY(cudaMemcpyAsync(base + o_lab, hp->labels, n_lab, cudaMemcpyHostToDevice, s));
     if (n_dl) COPY_TRY(cudaMemcpyAsync(base + o_dl, hp->data_lengths, n_dl, cudaMemcpyHostToDevice, s));
     if (n_ll) COPY_TRY(cudaMemcpyAsync(base + o_ll, hp->label_lengths, n_ll, cudaMemcpyHostToDevice, s));
     if (n_head) COPY_TRY(cudaMemcpyAsync(base + o_head, hp->head_grad, n_head, cudaMemcpyHostToDevice, s));
     if (hp->loss_sum) COPY_TRY(cudaMemcpyAsync(base + o_sum, hp->loss_sum, sizeof(double), cudaMemcpyHostToDevice, s));
-    if (int rc = ctcb_loss_grad(&d, base + o_ws, ws_bytes, s)) return rc;
+    if (nchunk == 2) COPY_TRY(cudaEventRecord(hs.ev_small, s));
+    int b0 = 0;
+    for (int c = 0; c < nchunk; ++c) {
+        cudaStream_t sc = c == 0 ? s : hs.stream2;
+        const size_t row = (size_t)T * V;                                    // floats per utterance (NTC halves)
+        const size_t log_off = nchunk == 2 ? sizeof(float) * row * b0 : 0, log_n = nchunk == 2 ? sizeof(float) * row * Bc[c] : n_log;
+        if (c == 1) { COPY_TRY(cudaStreamWaitEvent(sc, hs.ev_small, 0)); COPY_TRY(cudaStreamWaitEvent(sc, hs.ev_copy0, 0)); }
+        COPY_TRY(cudaMemcpyAsync(base + o_log + log_off, reinterpret_cast<const char*>(hp->logits) + log_off, log_n, cudaMemcpyHostToDevice, sc));
+        if (nchunk == 2 && c == 0) COPY_TRY(cudaEventRecord(hs.ev_copy0, sc));
+        ctcb_problem_t d = *hp;
+        d.B = Bc[c];
+        d.logits = reinterpret_cast<float*>(base + o_log + log_off);
+        d.grad = need_grad ? reinterpret_cast<float*>(base + o_grad + log_off) : nullptr;
+        if (dev_grad) { d.grad_stride_t = hp->logits_stride_t; d.grad_stride_b = hp->logits_stride_b; }
+        if (nchunk == 2) { d.logits_stride_b = (long long)row; if (need_grad) d.grad_stride_b = (long long)row; }
+        d.labels = base + o_lab + dt_size(hp->label_dtype) * (size_t)b0 * (nchunk == 2 ? Lmax : 0);
+        d.data_lengths = hp->data_lengths ? base + o_dl + dt_size(hp->data_lengths_dtype) * (size_t)b0 : nullptr;
+        d.label_lengths = hp->label_lengths ? base + o_ll + dt_size(hp->label_lengths_dtype) * (size_t)b0 : nullptr;
+        d.head_grad = hp->head_grad ? reinterpret_cast<float*>(base + o_head) + b0 : nullptr;
+        d.loss = reinterpret_cast<float*>(base + o_loss) + b0;
+        d.loss_sum = hp->loss_sum ? reinterpret_cast<double*>(base + o_sum) : nullptr;
+        d.status = hp->status ? reinterpret_cast<int32_t*>(base + o_stat) + b0 : nullptr;
+        if (int rc = ctcb_loss_grad(&d, base + o_ws[c], ws_bytes[c], sc)) return rc;
+        if (c == 1) { COPY_TRY(cudaEventRecord(hs.ev_done1, sc)); COPY_TRY(cudaStreamWaitEvent(s, hs.ev_done1, 0)); }
+        b0 += Bc[c];
+    }
     COPY_TRY(cudaMemcpyAsync(hp->loss, base + o_loss, sizeof(float) * B, cudaMemcpyDeviceToHost, s));
     if (need_grad && !dev_grad) COPY_TRY(cudaMemcpyAsync(hp->grad, base + o_grad, n_log, cudaMemcpyDeviceToHost, s));
     if (hp->loss_sum) COPY_TRY(cudaMemcpyAsync(hp->loss_sum, base + o_sum, sizeof(double), cudaMemcpyDeviceToHost, s));

@@ -461,3 +461,38 @@ def test_host_entry_with_resident_gradient(dev):
     ctypes.CDLL("libcudart.so.12").cudaMemcpy(ctypes.c_void_p(got.data_ptr()), dg, ctypes.c_size_t(got.numel() * 4), 3)
     assert torch.equal(got, grad)
     assert _lib.load().ctcb_loss_grad_host_resident(ctypes.byref(p), 0, None) == _lib.CTCB_INVALID_VALUE
+
+
+def test_host_entry_pipelines_two_halves(dev):
+    """CTCB_HOST_CHUNKS=2, B >= 16, utterance-major buffers: the host entry copies and computes the
+    batch in two halves on two streams; per-utterance results are the same bits as one device call."""
+    import ctypes
+    from gluon_e2e_asr_b200 import _lib, ctc_loss_and_grad
+    B, T, V, L = 19, 70, 46, 14
+    d = make_batch(B, T, V, L, seed=28)
+    d["pred_lengths"][3] = 5.0; d["label_lengths"][3] = 9.0           # one infeasible utterance
+    t = _to(dev, d)
+    head = np.linspace(0.5, 1.5, B).astype(np.float32)
+    s_dev = torch.zeros((), dtype=torch.float64, device=dev)
+    st_dev = torch.zeros((B,), dtype=torch.int32, device=dev)
+    loss, grad = ctc_loss_and_grad(t["pred"], t["label"], t["pred_lengths"], t["label_lengths"],
+                                   head_grad=torch.tensor(head, device=dev), loss_sum=s_dev, status=st_dev)
+    x = np.ascontiguousarray(d["pred"]); g = np.empty_like(x); l = np.empty((B,), np.float32)
+    lab = np.ascontiguousarray(d["label"]); st = np.zeros((B,), np.int32); ssum = np.zeros((1,), np.float64)
+    p = _lib.Problem()
+    p.T, p.B, p.V, p.Lmax, p.blank, p.label_pad = T, B, V, L, 0, 0
+    p.logits, p.logits_stride_t, p.logits_stride_b = x.ctypes.data, V, T * V
+    p.grad, p.grad_stride_t, p.grad_stride_b = g.ctypes.data, V, T * V
+    p.labels, p.label_dtype, p.label_stride_b, p.label_stride_l = lab.ctypes.data, _lib.DT_F32, L, 1
+    p.data_lengths, p.data_lengths_dtype = d["pred_lengths"].ctypes.data, _lib.DT_F32
+    p.label_lengths, p.label_lengths_dtype = d["label_lengths"].ctypes.data, _lib.DT_F32
+    p.head_grad, p.loss, p.status, p.loss_sum = head.ctypes.data, l.ctypes.data, st.ctypes.data, ssum.ctypes.data
+    for chunks in (2, 1):
+        g[:] = np.nan; l[:] = np.nan; st[:] = 0; ssum[0] = 0.0
+        with _env(CTCB_HOST_CHUNKS=chunks):
+            _lib.check(_lib.load().ctcb_loss_grad_host(ctypes.byref(p), 0))
+        np.testing.assert_array_equal(l, loss.cpu().numpy())
+        np.testing.assert_array_equal(g, grad.cpu().numpy())
+        np.testing.assert_array_equal(st, st_dev.cpu().numpy())
+        assert st[3] & 1 and l[3] == 0
+        assert abs(ssum[0] - s_dev.item()) < 1e-9 * max(1.0, abs(s_dev.item()))
