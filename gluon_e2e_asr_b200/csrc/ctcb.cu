@@ -359,6 +359,14 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
         gfn = vec == 4 ? GRAD_CH(4) : vec == 2 ? GRAD_CH(2) : GRAD_CH(1);
 #undef GRAD_CH
 #undef GRAD_X
+        // batches that run after the walkers (no overlap): the high-occupancy variant of the register-resident kernels
+        if (ch >= 1 && ch <= 4 && !((phases & PH_FORWARD) && !g_prof_events && overlap_allowed(p->B, lay.fused != 0))) {
+#define GRADO_X(V_, C_) (xq == 1 ? ctcb::k_grad<V_, C_, 1, 1> : xq == 2 ? ctcb::k_grad<V_, C_, 2, 1> : xq == 4 ? ctcb::k_grad<V_, C_, 4, 1> : ctcb::k_grad<V_, C_, 0, 1>)
+#define GRADO_CH(V_) (ch == 1 ? GRADO_X(V_, 1) : ch == 2 ? GRADO_X(V_, 2) : GRADO_X(V_, 4))
+            gfn = vec == 4 ? GRADO_CH(4) : vec == 2 ? GRADO_CH(2) : GRADO_CH(1);
+#undef GRADO_CH
+#undef GRADO_X
+        }
         if (gsm > 48 * 1024) CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(gfn), gsm));
         // programmatic dependent of k_walk when both are enqueued by this call: the gradient CTAs
         // start while the walkers run and wait per frame block on Workspace::gprog.  Not when

@@ -1099,8 +1099,11 @@ __host__ __device__ inline size_t grad_smem_bytes(int Lp, int pairs_cap) {
 
 // XQ = VEC-wide loads per lane that hold the frame's logits row in registers (issued together
 // with the history loads so that one memory round trip covers both); 0 = row loaded when needed.
-template <int VEC, int CH, int XQ>
-__global__ void __launch_bounds__(128, (CH == 0 || CH == 8) ? 5 : (CH <= 4 ? 8 : 1)) k_grad(GradArgs a) {
+// OCC = 1: registers capped at 64 (8 CTAs per SM instead of 7, a few spilled words) for batches
+// that run after the walkers: measured -14 % at cfg5, but +5 % on the overlapped cfg2 step, where
+// the kernel shares the GPU with the walkers and its tail is what counts -- hence a variant.
+template <int VEC, int CH, int XQ, int OCC = 0>
+__global__ void __launch_bounds__(128, (CH == 0 || CH == 8) ? 5 : (CH <= 4 ? (OCC ? 8 : 1) : 3)) k_grad(GradArgs a) {
     using V_t = typename VecT<VEC>::type;
     constexpr int NCH = CH > 0 ? CH : 1, NXQ = XQ > 0 ? XQ : 1;
     constexpr int F = (CH > 0 && CH <= 4) ? kGradFramesPerWarp : 1;      // frames in flight per warp

@@ -311,9 +311,12 @@ def _env(**kw):
     return cm()
 
 
-def test_overlapped_and_serial_schedules_give_the_same_bits(dev):
+def test_overlapped_and_serial_schedules_agree(dev):
     """k_grad as a programmatic dependent of k_walk (progress flags, SM partitioning) against the
-    same kernels launched one after the other: identical bits, repeatedly (a race would show)."""
+    kernels launched one after the other.  The overlapped schedule gives the same BITS run after
+    run (a race between the walkers and the gradient CTAs would show) and under a different SM
+    partition; the serial schedule launches the high-occupancy build of the same gradient kernel,
+    whose floating-point contractions may differ in the last bit, so it is compared to 1e-6."""
     from gluon_e2e_asr_b200 import ctc_loss_and_grad, ops
     B, T, V, L = CONFIGS["cfg2"]
     d = make_batch(B, T, V, L, seed=21)
@@ -323,13 +326,18 @@ def test_overlapped_and_serial_schedules_give_the_same_bits(dev):
         ops._ws_cache.clear()
         l0, g0 = ctc_loss_and_grad(*args)
         l0, g0 = l0.clone(), g0.clone()
+    ref = None
     for rep in range(5):
         with _env(CTCB_OVERLAP=1):
             l1, g1 = ctc_loss_and_grad(*args, out_grad=torch.full_like(g0, float("nan")))
-        assert torch.equal(l0, l1) and torch.equal(g0, g1), "overlap run %d differs" % rep
+        if ref is None:
+            ref = (l1.clone(), g1.clone())
+        assert torch.equal(ref[0], l1) and torch.equal(ref[1], g1), "overlap run %d differs" % rep
+    assert torch.equal(l0, ref[0])
+    torch.testing.assert_close(ref[1], g0, rtol=1e-6, atol=1e-7)
     with _env(CTCB_OVERLAP=1, CTCB_WALK_PER_SM=2):
         l2, g2 = ctc_loss_and_grad(*args)
-    assert torch.equal(l0, l2) and torch.equal(g0, g2)
+    assert torch.equal(ref[0], l2) and torch.equal(ref[1], g2)
 
 
 def test_fused_and_unfused_emissions_agree(dev):
