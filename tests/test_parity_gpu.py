@@ -504,3 +504,46 @@ def test_host_entry_pipelines_two_halves(dev):
         np.testing.assert_array_equal(st, st_dev.cpu().numpy())
         assert st[3] & 1 and l[3] == 0
         assert abs(ssum[0] - s_dev.item()) < 1e-9 * max(1.0, abs(s_dev.item()))
+
+
+def test_random_small_problems_vs_oracle(dev):
+    """Property test (hypothesis): random shapes, vocabularies on both sides of the fused limit, ragged
+    and infeasible lengths, both blank conventions, both layouts, int or float labels -- loss, gradient
+    and status bits against the fp64 oracle."""
+    hyp = pytest.importorskip("hypothesis")
+    st = hyp.strategies
+    from gluon_e2e_asr_b200 import ctc_loss_and_grad
+
+    @hyp.settings(max_examples=60, deadline=None, derandomize=True,
+                  suppress_health_check=list(hyp.HealthCheck))
+    @hyp.given(B=st.integers(1, 5), T=st.integers(1, 40), V=st.sampled_from([2, 3, 7, 46, 63, 64, 65, 90]),
+               L=st.integers(0, 12), seed=st.integers(0, 10 ** 6), blank_last=st.booleans(), tnc=st.booleans(),
+               int_labels=st.booleans(), scale=st.sampled_from([0.3, 1.0, 6.0]))
+    def run(B, T, V, L, seed, blank_last, tnc, int_labels, scale):
+        rng = np.random.default_rng(seed)
+        blank = V - 1 if blank_last else 0
+        lo, hi = (0, V - 1) if blank_last else (1, V)
+        lab = rng.integers(lo, hi, (B, max(L, 1))).astype(np.float32)
+        Lb = rng.integers(0, L + 1, B).astype(np.float32)
+        Tb = rng.integers(1, T + 1, B).astype(np.float32)           # some utterances end up infeasible
+        x = (rng.standard_normal((B, T, V)) * scale).astype(np.float32)
+        head = rng.uniform(0.5, 1.5, B)
+        d = dict(pred=x, label=lab, pred_lengths=Tb, label_lengths=Lb)
+        o = O.CtcLossOracle("NTC", "NT", "last" if blank_last else "first")
+        lo_, go_, ok = o(x, lab, Tb, Lb, head_grad=head)
+        xt = torch.tensor(x, device=dev)
+        if tnc:
+            xt = xt.transpose(0, 1).contiguous()
+        labt = torch.tensor(lab, device=dev)
+        if int_labels:
+            labt = labt.to(torch.int64)
+        status = torch.zeros((B,), dtype=torch.int32, device=dev)
+        loss, grad = ctc_loss_and_grad(xt, labt, torch.tensor(Tb, device=dev), torch.tensor(Lb, device=dev),
+                                       head_grad=torch.tensor(head, device=dev, dtype=torch.float32),
+                                       blank_label="last" if blank_last else "first",
+                                       layout="TNC" if tnc else "NTC", status=status)
+        g = grad.transpose(0, 1) if tnc else grad
+        _check(loss.cpu().numpy(), g.cpu().numpy(), lo_, go_, "B%d T%d V%d L%d seed%d" % (B, T, V, L, seed))
+        np.testing.assert_array_equal((status.cpu().numpy() & 1) == 0, ok)
+
+    run()
