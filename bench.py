@@ -11,10 +11,13 @@ utterances -- the path has no data-path collective; the per-step float64 loss-su
 
 `value`  : device-resident inputs, the step's kernels replayed from CUDA graphs, CUDA events
            around exactly K steps, max over ranks.
-`e2e`    : same metric through the drop-in boundary with HOST buffers: the C ABI's host entry
-           (ctcb_loss_grad_host_resident) with pinned host pointers -- H2D of logits/labels/lengths,
-           the kernels, D2H of the loss vector and the synchronisation are inside every timed call;
-           the gradient stays on the device, where the model's backward consumes it.
+`e2e`    : same metric through the drop-in boundary with HOST buffers: the C ABI's prefetching host
+           entry (ctcb_pipe_submit / ctcb_pipe_wait) with pinned host batches -- every step's H2D of
+           logits/labels/lengths, its kernels and the D2H of its loss vector are inside the timed loop
+           and every loss is read on the host; batch i+1's copy overlaps batch i's kernels (2 in
+           flight); the gradient stays on the device, where the model's backward consumes it.
+`e2e_sync`: the same through the synchronous host entry (ctcb_loss_grad_host_resident): copy, kernels,
+           loss back and a synchronisation inside every call, nothing overlapped.
 `e2e_plugin`: the same step through the Python mirror of the reference's block,
            CtcLoss(...)(pred, ...).mean().backward() (torch autograd on the path), pinned host
            inputs in one arena (PinnedBatch), loss read back.
@@ -397,6 +400,68 @@ def run_cuda(args, rank, world, local_rank):
     except Exception as exc:  # noqa: BLE001
         e2e_cabi = {"error": str(exc)[:200]}
 
+    # ---- e2e through the C ABI's prefetching host entry (ctcb_pipe_*): the same pinned host batches, batch i+1's
+    # H2D copy in flight while batch i's kernels run; every step's loss is read on the host before the step counts ----
+    e2e_pipe = None
+    try:
+        depth = args.pipe_depth
+        ph = ctypes.c_void_p()
+        _lib.check(lib.ctcb_pipe_create(local_rank, depth, ctypes.byref(ph)))
+        loss_bufs = [torch.zeros((B,), dtype=torch.float32).pin_memory() for _ in hsets]
+        loss_np = [b.numpy() for b in loss_bufs]
+        pprobs = []
+        for q0, lb in zip(probs, loss_bufs):
+            q = _lib.Problem()
+            ctypes.memmove(ctypes.byref(q), ctypes.byref(q0), ctypes.sizeof(q))
+            q.loss = lb.data_ptr()
+            pprobs.append(q)
+        npb = len(pprobs)
+        tk = ctypes.c_int64(-1)
+
+        def pipe_run(k):
+            """k batches through the pipe, `depth` in flight; returns the sum of all losses read on the host."""
+            acc, pending = 0.0, []
+            for i in range(k):
+                _lib.check(lib.ctcb_pipe_submit(ph, ctypes.byref(pprobs[i % npb]), ctypes.byref(tk)))
+                pending.append((tk.value, i % npb))
+                if len(pending) >= depth:
+                    t_, j = pending.pop(0)
+                    _lib.check(lib.ctcb_pipe_wait(ph, t_, None))
+                    acc += float(loss_np[j].sum())
+            for t_, j in pending:
+                _lib.check(lib.ctcb_pipe_wait(ph, t_, None))
+                acc += float(loss_np[j].sum())
+            return acc
+
+        pipe_run(max(2 * depth, 6))
+        # same bits as the synchronous host entry
+        _lib.check(lib.ctcb_loss_grad_host_resident(ctypes.byref(probs[0]), local_rank, ctypes.byref(dgrad)))
+        ref_loss = loss_host.clone()
+        pipe_run(1)
+        if not torch.equal(ref_loss, loss_bufs[0]):
+            raise RuntimeError("pipelined host entry disagrees with the synchronous one")
+        pipe_steps = max(e2e_steps, min(args.steps, 1000))
+        barrier()
+        t0 = time.perf_counter()
+        acc = pipe_run(pipe_steps)
+        pipe_ms = (time.perf_counter() - t0) * 1e3
+        pipe_frames = sum(sets[i % npb]["frames"] for i in range(pipe_steps))
+        tp_ = torch.tensor([pipe_ms, pipe_frames], dtype=torch.float64, device=dev)
+        if world > 1:
+            a = tp_.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
+            b = tp_.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
+            pipe_ms, pipe_frames = a[0].item(), b[1].item()
+        e2e_pipe = {"value": pipe_frames / (pipe_ms * 1e-3), "unit": UNIT, "ms_per_step": pipe_ms / pipe_steps,
+                    "h2d_bytes_per_step": hsets[0].h2d_bytes, "d2h_bytes_per_step": d2h, "steps": pipe_steps,
+                    "in_flight": depth, "loss_checksum": acc,
+                    "api": "ctcb_pipe_submit / ctcb_pipe_wait (pinned HOST batches, one arena copy each): every step's "
+                           "inputs cross PCIe and its loss is read on the host inside the timed region; batch i+1's "
+                           "copy overlaps batch i's kernels (%d batches in flight); gradient left on the device; "
+                           "host wall clock around the loop including the drain" % depth}
+        lib.ctcb_pipe_destroy(ph)
+    except Exception as exc:  # noqa: BLE001
+        e2e_pipe = {"error": str(exc)[:200]}
+
     # ---- roofline of the dominant kernel: per-kernel CUDA events inside the library -------
     kms = np.zeros((8,), np.float64)
     nrep = 20
@@ -483,7 +548,9 @@ def run_cuda(args, rank, world, local_rank):
             "clocks": clocks,
             # headline end-to-end number: the C ABI's host entry (the drop-in boundary itself, HOST buffers in,
             # loss back on the host); the same step through the Python plugin + torch autograd is reported beside it
-            "e2e": e2e_cabi if e2e_cabi and "value" in e2e_cabi else e2e_plugin,
+            "e2e": (e2e_pipe if e2e_pipe and "value" in e2e_pipe else
+                    e2e_cabi if e2e_cabi and "value" in e2e_cabi else e2e_plugin),
+            "e2e_sync": e2e_cabi,
             "e2e_plugin": e2e_plugin,
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline,
@@ -547,6 +614,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--pipe-depth", type=int, default=2, help="batches in flight in the prefetching host entry (e2e)")
     ap.add_argument("--no-others", action="store_true", help="skip the context measurements of the other configs")
     ap.add_argument("--no-graph-allreduce", action="store_true",
                     help="N>1: issue the loss-sum all-reduce from the host every step instead of from the captured graph")

@@ -22,6 +22,7 @@ EXPORTS = (
     "ctcb_backward", "ctcb_loss_grad_host", "ctcb_greedy_decode", "ctcb_loss_sum_allreduce",
     "ctcb_last_launch_count", "ctcb_last_walk_config", "ctcb_loss_grad_dlpack", "ctcb_loss_grad_timed",
     "ctcb_scale_rows", "ctcb_edit_distance", "ctcb_loss_grad_host_resident",
+    "ctcb_pipe_create", "ctcb_pipe_submit", "ctcb_pipe_wait", "ctcb_pipe_destroy",
 )
 
 
@@ -71,6 +72,10 @@ def load():
     lib.ctcb_loss_grad_timed.argtypes = [PP, vp, sz, vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32)]
     lib.ctcb_loss_grad_host.argtypes = [PP, ctypes.c_int]
     lib.ctcb_loss_grad_host_resident.argtypes = [PP, ctypes.c_int, ctypes.POINTER(vp)]
+    lib.ctcb_pipe_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
+    lib.ctcb_pipe_submit.argtypes = [vp, PP, ctypes.POINTER(i64)]
+    lib.ctcb_pipe_wait.argtypes = [vp, i64, ctypes.POINTER(vp)]
+    lib.ctcb_pipe_destroy.argtypes = [vp]
     lib.ctcb_greedy_decode.argtypes = [vp, i64, i64, vp, i32, i32, i32, i32, i32, vp, vp, vp]
     lib.ctcb_scale_rows.argtypes = [vp, i64, i64, i32, i32, i32, vp, vp]
     lib.ctcb_edit_distance.argtypes = [vp, i64, vp, vp, i64, vp, i32, i32, i32, vp, vp, vp]

@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <new>
 #include <utility>
 #include <vector>
 
@@ -551,6 +552,188 @@ int loss_grad_host_impl(const ctcb_problem_t* hp, int device, float** dev_grad) 
     return CTCB_OK;
 }
 }  // namespace
+
+// ---- pipelined host entry ---------------------------------------------------------------------
+// ctcb_pipe_*: the host entry for a training loop that prefetches.  Batch i+1's inputs cross PCIe on
+// a copy stream while batch i's kernels run on the compute stream; the caller collects batch i's loss
+// (host) and gradient (device) with ctcb_pipe_wait.  `depth` slots of device buffers rotate; the
+// workspace is shared (the compute stream serialises the batches, and one workspace keeps the alpha/beta
+// history in L2).
+struct ctcb_pipe {
+    struct Slot {
+        char* in = nullptr; size_t in_bytes = 0;        // input arena (logits, labels, lengths, head)
+        char* out = nullptr; size_t out_bytes = 0;      // gradient, loss, loss sum, status
+        cudaEvent_t ev_in = nullptr, ev_done = nullptr;
+        bool busy = false;
+        int64_t ticket = -1;
+        float* grad = nullptr;
+    };
+    int device = 0, depth = 0;
+    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    void* ws = nullptr; size_t ws_bytes = 0;
+    std::vector<Slot> slots;
+    int64_t next = 0;
+};
+
+namespace {
+int pipe_grow(char** ptr, size_t* have, size_t need, cudaStream_t drain) {
+    if (*have >= need) return CTCB_OK;
+    if (drain) cudaStreamSynchronize(drain);
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr; *have = 0;
+    need = align_up(need + need / 8, 1 << 20);
+    if (cudaMalloc(reinterpret_cast<void**>(ptr), need) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(CTCB_MEMOPS_FAILED, "cudaMalloc(%zu) failed", need);
+    }
+    *have = need;
+    return CTCB_OK;
+}
+}  // namespace
+
+int ctcb_pipe_create(int device, int depth, ctcb_pipe_t** out) {
+    if (!out) return fail(CTCB_INVALID_VALUE, "out is NULL");
+    *out = nullptr;
+    if (depth < 1 || depth > 8) return fail(CTCB_INVALID_VALUE, "depth %d outside [1,8]", depth);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return fail(CTCB_UNSUPPORTED, "CUDA device %d not available (there is no CPU path)", device);
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    ctcb_pipe* p = new (std::nothrow) ctcb_pipe();
+    if (!p) return fail(CTCB_MEMOPS_FAILED, "out of host memory");
+    p->device = device; p->depth = depth;
+    p->slots.resize(depth);
+    bool ok = cudaStreamCreateWithFlags(&p->s_copy, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&p->s_comp, cudaStreamNonBlocking) == cudaSuccess;
+    for (auto& s : p->slots)
+        ok = ok && cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { ctcb_pipe_destroy(p); return fail(CTCB_MEMOPS_FAILED, "stream / event creation failed"); }
+    *out = p;
+    return CTCB_OK;
+}
+
+int ctcb_pipe_destroy(ctcb_pipe_t* p) {
+    if (!p) return CTCB_OK;
+    cudaSetDevice(p->device);
+    if (p->s_comp) cudaStreamSynchronize(p->s_comp);
+    if (p->s_copy) cudaStreamSynchronize(p->s_copy);
+    for (auto& s : p->slots) {
+        if (s.in) cudaFree(s.in);
+        if (s.out) cudaFree(s.out);
+        if (s.ev_in) cudaEventDestroy(s.ev_in);
+        if (s.ev_done) cudaEventDestroy(s.ev_done);
+    }
+    if (p->ws) cudaFree(p->ws);
+    if (p->s_copy) cudaStreamDestroy(p->s_copy);
+    if (p->s_comp) cudaStreamDestroy(p->s_comp);
+    cudaGetLastError();
+    delete p;
+    return CTCB_OK;
+}
+
+int ctcb_pipe_submit(ctcb_pipe_t* p, const ctcb_problem_t* hp, int64_t* ticket) {
+    if (!p || !ticket) return fail(CTCB_INVALID_VALUE, "pipe / ticket is NULL");
+    if (int rc = validate(hp)) return rc;
+    const int T = hp->T, B = hp->B, V = hp->V, Lmax = hp->Lmax;
+    const bool tnc = hp->logits_stride_t == (long long)B * V && hp->logits_stride_b == V;
+    const bool ntc = hp->logits_stride_t == V && hp->logits_stride_b == (long long)T * V;
+    if (!tnc && !ntc) return fail(CTCB_INVALID_VALUE, "host entry needs compact TNC or NTC logits");
+    if (Lmax > 0 && !((hp->label_stride_b == Lmax && hp->label_stride_l == 1) || (hp->label_stride_b == 1 && hp->label_stride_l == B)))
+        return fail(CTCB_INVALID_VALUE, "host entry needs compact NT or TN labels");
+    CUDA_TRY(cudaSetDevice(p->device));
+    ctcb_pipe::Slot& sl = p->slots[p->next % p->depth];
+    if (sl.busy) {   // the caller did not collect this slot's previous batch: its results are overwritten
+        CUDA_TRY(cudaEventSynchronize(sl.ev_done));
+        sl.busy = false;
+    }
+    // inputs: {host pointer, bytes}; one copy when they lie in one host arena (batch.py PinnedBatch,
+    // the reference's shared-memory collation batchify.py:51), one copy per array otherwise
+    struct In { const void* h; size_t n; size_t off; };
+    In in[5] = {
+        {hp->logits, sizeof(float) * (size_t)T * B * V, 0},
+        {Lmax > 0 ? hp->labels : nullptr, Lmax > 0 ? dt_size(hp->label_dtype) * (size_t)B * Lmax : 0, 0},
+        {hp->data_lengths, hp->data_lengths ? dt_size(hp->data_lengths_dtype) * (size_t)B : 0, 0},
+        {hp->label_lengths, hp->label_lengths ? dt_size(hp->label_lengths_dtype) * (size_t)B : 0, 0},
+        {hp->head_grad, hp->head_grad ? sizeof(float) * (size_t)B : 0, 0},
+    };
+    uintptr_t lo = UINTPTR_MAX, hi = 0;
+    size_t sum = 0;
+    for (const In& a : in)
+        if (a.n) {
+            const uintptr_t b = reinterpret_cast<uintptr_t>(a.h);
+            lo = b < lo ? b : lo; hi = b + a.n > hi ? b + a.n : hi;
+            sum += a.n;
+        }
+    const bool one_copy = hi - lo <= sum + 5 * 4096;
+    size_t in_need = 0;
+    const size_t skew = lo % 256;            // device addresses congruent to the host's mod 256 (vector loads)
+    if (one_copy) {
+        for (In& a : in) if (a.n) a.off = skew + (reinterpret_cast<uintptr_t>(a.h) - lo);
+        in_need = skew + (hi - lo);
+    } else {
+        for (In& a : in) if (a.n) { a.off = in_need; in_need = align_up(in_need + a.n, 256); }
+    }
+    const bool need_grad = true;
+    size_t ws_need = 0;
+    if (int rc = ctcb_workspace_bytes(T, B, V, Lmax, need_grad, &ws_need)) return rc;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+    const size_t o_grad = take(in[0].n), o_loss = take(sizeof(float) * B), o_sum = take(sizeof(double)),
+                 o_stat = take(sizeof(int) * B);
+    if (int rc = pipe_grow(&sl.in, &sl.in_bytes, in_need, nullptr)) return rc;
+    if (int rc = pipe_grow(&sl.out, &sl.out_bytes, o, nullptr)) return rc;
+    if (int rc = pipe_grow(reinterpret_cast<char**>(&p->ws), &p->ws_bytes, ws_need, p->s_comp)) return rc;
+#define COPY_TRY(expr) do { if ((expr) != cudaSuccess) return fail(CTCB_MEMOPS_FAILED, "%s: %s", #expr, cudaGetErrorString(cudaGetLastError())); } while (0)
+    if (one_copy) {
+        COPY_TRY(cudaMemcpyAsync(sl.in + skew, reinterpret_cast<const void*>(lo), hi - lo, cudaMemcpyHostToDevice, p->s_copy));
+    } else {
+        for (const In& a : in)
+            if (a.n) COPY_TRY(cudaMemcpyAsync(sl.in + a.off, a.h, a.n, cudaMemcpyHostToDevice, p->s_copy));
+    }
+    if (hp->loss_sum) COPY_TRY(cudaMemcpyAsync(sl.out + o_sum, hp->loss_sum, sizeof(double), cudaMemcpyHostToDevice, p->s_copy));
+    COPY_TRY(cudaEventRecord(sl.ev_in, p->s_copy));
+    COPY_TRY(cudaStreamWaitEvent(p->s_comp, sl.ev_in, 0));
+    ctcb_problem_t d = *hp;
+    d.logits = reinterpret_cast<const float*>(sl.in + in[0].off);
+    d.labels = in[1].n ? sl.in + in[1].off : nullptr;
+    d.data_lengths = in[2].n ? sl.in + in[2].off : nullptr;
+    d.label_lengths = in[3].n ? sl.in + in[3].off : nullptr;
+    d.head_grad = in[4].n ? reinterpret_cast<const float*>(sl.in + in[4].off) : nullptr;
+    d.grad = reinterpret_cast<float*>(sl.out + o_grad);
+    d.grad_stride_t = hp->logits_stride_t; d.grad_stride_b = hp->logits_stride_b;
+    d.loss = reinterpret_cast<float*>(sl.out + o_loss);
+    d.loss_sum = hp->loss_sum ? reinterpret_cast<double*>(sl.out + o_sum) : nullptr;
+    d.status = hp->status ? reinterpret_cast<int32_t*>(sl.out + o_stat) : nullptr;
+    if (int rc = ctcb_loss_grad(&d, p->ws, p->ws_bytes, p->s_comp)) return rc;
+    COPY_TRY(cudaMemcpyAsync(hp->loss, sl.out + o_loss, sizeof(float) * B, cudaMemcpyDeviceToHost, p->s_comp));
+    if (hp->loss_sum) COPY_TRY(cudaMemcpyAsync(hp->loss_sum, sl.out + o_sum, sizeof(double), cudaMemcpyDeviceToHost, p->s_comp));
+    if (hp->status) COPY_TRY(cudaMemcpyAsync(hp->status, sl.out + o_stat, sizeof(int) * B, cudaMemcpyDeviceToHost, p->s_comp));
+    COPY_TRY(cudaEventRecord(sl.ev_done, p->s_comp));
+#undef COPY_TRY
+    sl.busy = true;
+    sl.ticket = p->next;
+    sl.grad = d.grad;
+    *ticket = p->next++;
+    return CTCB_OK;
+}
+
+int ctcb_pipe_wait(ctcb_pipe_t* p, int64_t ticket, float** dev_grad) {
+    if (!p) return fail(CTCB_INVALID_VALUE, "pipe is NULL");
+    if (ticket < 0 || ticket >= p->next) return fail(CTCB_INVALID_VALUE, "ticket %lld was never issued", (long long)ticket);
+    ctcb_pipe::Slot& sl = p->slots[ticket % p->depth];
+    if (sl.ticket != ticket)
+        return fail(CTCB_INVALID_VALUE, "ticket %lld: its slot was reused by ticket %lld (depth %d)", (long long)ticket,
+                    (long long)sl.ticket, p->depth);
+    if (sl.busy) {
+        CUDA_TRY(cudaEventSynchronize(sl.ev_done));
+        sl.busy = false;
+    }
+    if (dev_grad) *dev_grad = sl.grad;
+    return CTCB_OK;
+}
 
 int ctcb_scale_rows(float* grad, int64_t stride_t, int64_t stride_b, int32_t T, int32_t B, int32_t V,
                     const float* head_grad, void* stream) {

@@ -127,6 +127,28 @@ int ctcb_loss_grad_host(const ctcb_problem_t* p, int device);
  * host-entry call on this device); p->grad is ignored. */
 int ctcb_loss_grad_host_resident(const ctcb_problem_t* p, int device, float** dev_grad);
 
+/* The host entry for a loop that prefetches (the reference's DataLoader hands the training loop the
+ * next collated batch while the current one is in flight: train_ctc_ce.py:348-355 over
+ * gluon DataLoader workers, batchify.py:51 shared-memory collation).  A pipe owns `depth` slots of
+ * device buffers, a copy stream and a compute stream on `device`:
+ *   ctcb_pipe_submit  enqueues host->device copies of the problem's inputs on the copy stream, the
+ *                     kernels and the loss (loss_sum, status) device->host copies on the compute
+ *                     stream, and returns a ticket WITHOUT waiting: the next batch's copy overlaps
+ *                     this batch's kernels.  All pointers of `host_problem` are HOST pointers (page-
+ *                     locked for the copies to be asynchronous); they must stay valid and untouched
+ *                     until ctcb_pipe_wait(ticket) returns.  p->grad is ignored.  Inputs that lie in
+ *                     one host arena (gaps < 4 KB) move in ONE copy.  Submitting when all slots hold
+ *                     uncollected batches first waits for the oldest.
+ *   ctcb_pipe_wait    blocks until the ticket's batch is complete: the loss is in host_problem->loss,
+ *                     *dev_grad (optional) is the device address of its gradient, in the logits'
+ *                     layout, valid until `depth` more batches have been submitted.
+ * One thread at a time per pipe.  Results are bit-identical to ctcb_loss_grad_host_resident. */
+typedef struct ctcb_pipe ctcb_pipe_t;
+int ctcb_pipe_create(int device, int depth, ctcb_pipe_t** out);
+int ctcb_pipe_submit(ctcb_pipe_t* pipe, const ctcb_problem_t* host_problem, int64_t* ticket);
+int ctcb_pipe_wait(ctcb_pipe_t* pipe, int64_t ticket, float** dev_grad);
+int ctcb_pipe_destroy(ctcb_pipe_t* pipe);
+
 /* The operator's Backward for a caller that ran ctcb_loss_grad with head_grad = NULL in its
  * Forward (what MXNet's operator does: Forward stores the gradient, Backward multiplies it by
  * the head gradient -- SURVEY 8a row a8): grad[b, t, :] *= head_grad[b], in place. */

@@ -139,3 +139,24 @@ def test_block_constructor_contract():
         CtcLoss(label_layout="NN")
     with pytest.raises(ValueError):
         CtcLoss(blank_label="middle")
+
+
+def test_pipe_entry_validation(lib):
+    """ctcb_pipe_*: argument errors are reported, and without a CUDA device the pipe cannot be made
+    (no CPU path behind the prefetching host entry either)."""
+    torch = pytest.importorskip("torch")
+    l = lib.load()
+    h = ctypes.c_void_p()
+    assert l.ctcb_pipe_create(0, 2, None) == lib.CTCB_INVALID_VALUE
+    assert l.ctcb_pipe_create(0, 0, ctypes.byref(h)) == lib.CTCB_INVALID_VALUE
+    assert l.ctcb_pipe_create(0, 9, ctypes.byref(h)) == lib.CTCB_INVALID_VALUE
+    t = ctypes.c_int64(0)
+    assert l.ctcb_pipe_submit(None, None, ctypes.byref(t)) == lib.CTCB_INVALID_VALUE
+    assert l.ctcb_pipe_wait(None, 0, None) == lib.CTCB_INVALID_VALUE
+    assert l.ctcb_pipe_destroy(None) == lib.CTCB_OK
+    if not torch.cuda.is_available():
+        assert l.ctcb_pipe_create(0, 2, ctypes.byref(h)) == lib.CTCB_UNSUPPORTED
+        assert not h.value
+        from gluon_e2e_asr_b200 import HostPipeline
+        with pytest.raises(RuntimeError):
+            HostPipeline(0)

@@ -506,6 +506,75 @@ def test_host_entry_pipelines_two_halves(dev):
         assert abs(ssum[0] - s_dev.item()) < 1e-9 * max(1.0, abs(s_dev.item()))
 
 
+def test_prefetching_pipe_matches_device_calls(dev):
+    """ctcb_pipe_*: batches of changing shape submitted back to back with `depth` in flight; every
+    ticket's loss (host) and gradient (device slot) carry the same bits as a plain device call, from
+    one-arena pinned batches (one copy) and from separately allocated pageable arrays (one copy per
+    array) alike; ticket misuse is an error."""
+    import ctypes
+    from gluon_e2e_asr_b200 import HostPipeline, PinnedBatch, _lib, ctc_loss_and_grad
+    shapes = [(6, 40, 46, 8), (6, 40, 46, 8), (3, 90, 46, 20), (9, 33, 80, 7), (6, 40, 46, 8), (2, 120, 5, 30), (6, 40, 46, 8)]
+    for depth in (1, 2, 3):
+        pipe = HostPipeline(0, depth=depth)
+        want, tickets, keep = [], [], []
+        for i, (B, T, V, L) in enumerate(shapes):
+            d = make_batch(B, T, V, L, seed=300 + i)
+            t = _to(dev, d)
+            want.append(ctc_loss_and_grad(t["pred"], t["label"], t["pred_lengths"], t["label_lengths"]))
+            pb = PinnedBatch.from_arrays(d["pred"], d["label"], d["pred_lengths"], d["label_lengths"])
+            lo = torch.full((B,), float("nan")).pin_memory()
+            keep.append((pb, lo))
+            tickets.append(pipe.submit(pb, lo))
+            if i >= depth - 1:                                   # collect the oldest batch in flight
+                j = i - (depth - 1)
+                g = pipe.wait(tickets[j])
+                assert torch.equal(keep[j][1], want[j][0].cpu()), (depth, j)
+                assert torch.equal(g, want[j][1]), (depth, j)
+        for j in range(len(shapes) - (depth - 1), len(shapes)):
+            g = pipe.wait(tickets[j])
+            assert torch.equal(keep[j][1], want[j][0].cpu()) and torch.equal(g, want[j][1])
+        l = _lib.load()
+        assert l.ctcb_pipe_wait(pipe._h, 99, None) == _lib.CTCB_INVALID_VALUE
+        if depth < len(shapes):
+            assert l.ctcb_pipe_wait(pipe._h, 0, None) == _lib.CTCB_INVALID_VALUE      # slot long reused
+        pipe.close()
+    # separately allocated pageable arrays, head gradient, loss sum and status through the raw ABI
+    B, T, V, L = 7, 44, 46, 10
+    d = make_batch(B, T, V, L, seed=311)
+    d["pred_lengths"][2] = 3.0; d["label_lengths"][2] = 8.0          # infeasible
+    t = _to(dev, d)
+    head = np.linspace(0.5, 1.5, B).astype(np.float32)
+    s_dev = torch.zeros((), dtype=torch.float64, device=dev)
+    st_dev = torch.zeros((B,), dtype=torch.int32, device=dev)
+    loss, grad = ctc_loss_and_grad(t["pred"], t["label"], t["pred_lengths"], t["label_lengths"],
+                                   head_grad=torch.tensor(head, device=dev), loss_sum=s_dev, status=st_dev)
+    x = np.ascontiguousarray(d["pred"].transpose(1, 0, 2))           # TNC this time
+    lab = np.ascontiguousarray(d["label"]); lh = np.empty((B,), np.float32)
+    st = np.zeros((B,), np.int32); ssum = np.zeros((1,), np.float64)
+    p = _lib.Problem()
+    p.T, p.B, p.V, p.Lmax, p.blank, p.label_pad = T, B, V, L, 0, 0
+    p.logits, p.logits_stride_t, p.logits_stride_b = x.ctypes.data, B * V, V
+    p.labels, p.label_dtype, p.label_stride_b, p.label_stride_l = lab.ctypes.data, _lib.DT_F32, L, 1
+    p.data_lengths, p.data_lengths_dtype = d["pred_lengths"].ctypes.data, _lib.DT_F32
+    p.label_lengths, p.label_lengths_dtype = d["label_lengths"].ctypes.data, _lib.DT_F32
+    p.head_grad, p.loss, p.status, p.loss_sum = head.ctypes.data, lh.ctypes.data, st.ctypes.data, ssum.ctypes.data
+    h = ctypes.c_void_p(); tk = ctypes.c_int64(-1); dg = ctypes.c_void_p()
+    l = _lib.load()
+    _lib.check(l.ctcb_pipe_create(0, 2, ctypes.byref(h)))
+    _lib.check(l.ctcb_pipe_submit(h, ctypes.byref(p), ctypes.byref(tk)))
+    _lib.check(l.ctcb_pipe_wait(h, tk, ctypes.byref(dg)))
+    got = torch.empty((T, B, V), device=dev)
+    ctypes.CDLL("libcudart.so.12").cudaMemcpy(ctypes.c_void_p(got.data_ptr()), dg, ctypes.c_size_t(got.numel() * 4), 3)
+    np.testing.assert_array_equal(lh, loss.cpu().numpy())
+    assert torch.equal(got.transpose(0, 1), grad)
+    np.testing.assert_array_equal(st, st_dev.cpu().numpy())
+    assert st[2] & 1 and lh[2] == 0
+    assert abs(ssum[0] - s_dev.item()) < 1e-9 * max(1.0, abs(s_dev.item()))
+    p.logits_stride_t = 3
+    assert l.ctcb_pipe_submit(h, ctypes.byref(p), ctypes.byref(tk)) == _lib.CTCB_INVALID_VALUE
+    assert l.ctcb_pipe_destroy(h) == _lib.CTCB_OK
+
+
 def test_random_small_problems_vs_oracle(dev):
     """Property test (hypothesis): random shapes, vocabularies on both sides of the fused limit, ragged
     and infeasible lengths, both blank conventions, both layouts, int or float labels -- loss, gradient
