@@ -92,13 +92,15 @@ bool pick_stages(int W, int NW, int fused_Lp, int* stages) {
     return false;
 }
 
-// k_grad overlaps k_walk only while every walker CTA of the batch can be resident together
-// ... and only for the fused (small-vocabulary) path: with a wide vocabulary the gradient kernel is
-// HBM-bound and wants the whole GPU; sharing it with the walkers measured no better than running after them
+// k_grad overlaps k_walk only while every walker CTA of the batch can be resident together.  Fused
+// (small-vocabulary) path: the walkers get SMs of their own (shared-memory reservation below).  Wide
+// vocabularies: the gradient kernel wants every SM's bandwidth, so the walkers reserve nothing and the
+// gradient CTAs share their SMs (measured at cfg3: 238 -> 216 us; with the reservation it was no gain)
 bool overlap_allowed(int B, bool fused) {
     const char* e = getenv("CTCB_OVERLAP");
     if (e) return atoi(e) != 0;
-    return fused && B <= 296;
+    (void)fused;
+    return B <= 296;
 }
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) only when a launch needs more than any before it
@@ -293,7 +295,7 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
             return fail(CTCB_UNSUPPORTED, "Lmax=%d V=%d: the emission ring does not fit in shared memory", p->Lmax, p->V);
         const WalkFn wfn = we->fn[lay.fused][need_grad ? 1 : 0];
         size_t smem = ctcb::walk_smem_bytes(lay.W, we->NW, stages, lay.fused ? lay.Lp : 0);
-        if (need_grad && (phases & PH_BACKWARD) && overlap_allowed(p->B, lay.fused != 0)) {
+        if (lay.fused && need_grad && (phases & PH_BACKWARD) && overlap_allowed(p->B, true)) {
             // SM partitioning by shared-memory reservation: the gradient kernel runs concurrently
             // (programmatic dependent launch); its CTAs must not share an SM with a walker, whose
             // T-step dependent chain is the critical path.  The walkers therefore ask for all the
@@ -313,14 +315,23 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
             if (want > smem) smem = want;
         }
         const int vec = pick_vec(p->logits, p->logits_stride_t, p->logits_stride_b, p->V);
-        const size_t esm = 2 * (size_t)lay.Lp * sizeof(int);
         CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(wfn), smem));
         if (!lay.fused) {
         // NQ: vector loads per lane that hold one logits row in registers (0 = two-pass)
         const int units = (p->V / vec + 31) / 32;
-        const int nq = units <= 1 ? 1 : units <= 2 ? 2 : units <= 4 ? 4 : units <= 8 ? 8 : units <= 16 ? 16 : 0;
+        int nq = units <= 1 ? 1 : units <= 2 ? 2 : units <= 4 ? 4 : units <= 8 ? 8 : units <= 16 ? 16 : 0;
+        // wide vocabularies with 16-byte aligned rows: the frame block's rows staged in shared memory by bulk copies
+        const char* est = getenv("CTCB_EMIT_STAGED");
+        const bool staged = vec == 4 && (nq == 0 || nq >= 8) && ctcb::emit_smem_bytes(lay.Lp, p->V) <= 75 * 1024 &&
+                            !(est && atoi(est) == 0);
+        if (staged) nq = -1;
         const int bpc = ctcb::emit_blocks_per_cta(nq);
         const dim3 egrid((lay.NB + bpc - 1) / bpc + 1, p->B);   // + the metadata CTA of each utterance
+        const size_t esm = ctcb::emit_smem_bytes(lay.Lp, staged ? p->V : 0);
+        if (staged) {
+            if (esm > 48 * 1024) CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(ctcb::k_emit<4, -1>), esm));
+            ctcb::k_emit<4, -1><<<egrid, 256, esm, stream>>>(dp, w);
+        } else
 #define EMIT_LAUNCH(V_, Q_) ctcb::k_emit<V_, Q_><<<egrid, 128, esm, stream>>>(dp, w)
 #define EMIT_NQ(V_) switch (nq) { case 1: EMIT_LAUNCH(V_, 1); break; case 2: EMIT_LAUNCH(V_, 2); break; \
                                   case 4: EMIT_LAUNCH(V_, 4); break; case 8: EMIT_LAUNCH(V_, 8); break;  \
@@ -343,7 +354,8 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
         ctcb::GradArgs ga{dp, w};
         const int gpairs = p->Lmax + 1;
         const int gch = gpairs <= 32 ? 1 : gpairs <= 64 ? 2 : gpairs <= 128 ? 4 : gpairs <= 256 ? 8 : gpairs <= 512 ? 16 : 0;
-        const size_t gsm = ctcb::grad_smem_bytes(lay.Lp, 32 * gch);
+        size_t gsm = ctcb::grad_smem_bytes(lay.Lp, 32 * gch);
+        int gthreads = 128;
         if (gsm > 200 * 1024) return fail(CTCB_UNSUPPORTED, "Lmax=%d too long for the gradient kernel", p->Lmax);
         int vec = pick_vec(p->logits, p->logits_stride_t, p->logits_stride_b, p->V);
         const int gvec = pick_vec(p->grad, p->grad_stride_t, p->grad_stride_b, p->V);
@@ -368,6 +380,15 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
 #undef GRADO_CH
 #undef GRADO_X
         }
+        // wide vocabularies with 16-byte aligned rows: the frame block's rows staged in shared memory by bulk copies
+        const size_t gsm_staged = ctcb::grad_smem_bytes(lay.Lp, 32 * gch, p->V);
+        const char* est = getenv("CTCB_GRAD_STAGED");
+        if (xq == 0 && vec == 4 && gsm_staged <= 75 * 1024 && !(est && atoi(est) == 0)) {
+            gfn = ch == 1 ? ctcb::k_grad<4, 1, -1> : ch == 2 ? ctcb::k_grad<4, 2, -1> : ch == 4 ? ctcb::k_grad<4, 4, -1> :
+                  ch == 8 ? ctcb::k_grad<4, 8, -1> : ch == 16 ? ctcb::k_grad<4, 16, -1> : ctcb::k_grad<4, 0, -1>;
+            gsm = gsm_staged;
+            gthreads = 256;                      // 8 warps, one frame each
+        }
         if (gsm > 48 * 1024) CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(gfn), gsm));
         // programmatic dependent of k_walk when both are enqueued by this call: the gradient CTAs
         // start while the walkers run and wait per frame block on Workspace::gprog.  Not when
@@ -375,7 +396,7 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
         // walkers do not fit the GPU at once (the waiting CTAs would hold slots the walkers need).
         const bool overlap = (phases & PH_FORWARD) && !g_prof_events && overlap_allowed(p->B, lay.fused != 0);
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = ggrid; cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = gsm; cfg.stream = stream;
+        cfg.gridDim = ggrid; cfg.blockDim = dim3(gthreads); cfg.dynamicSmemBytes = gsm; cfg.stream = stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;

@@ -149,17 +149,34 @@ template <> __device__ __forceinline__ float vec_fill<1>(float v) { return v; }
 template <> __device__ __forceinline__ float2 vec_fill<2>(float v) { return make_float2(v, v); }
 template <> __device__ __forceinline__ float4 vec_fill<4>(float v) { return make_float4(v, v, v, v); }
 
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count);
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes);
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity);
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar);
+
 // NQ = VEC-wide loads per lane that cover one logits row (power of two, <= 16): the rows of
 // F = 16/NQ frames (at most 8) are held in registers, so every global load of those frames is
 // in flight before the first reduction.  NQ = 0: rows too wide for registers, two passes.
-__host__ __device__ constexpr int emit_blocks_per_cta(int nq) { return nq >= 8 ? 1 : 4; }
+// NQ = -1 (wide vocabularies, 16-byte aligned rows): the frame block's kG rows are fetched into shared
+// memory by 1-D bulk copies (TMA) before the parameter layer runs -- 8 rows in flight per CTA, several
+// CTAs per SM -- and row maximum, normaliser and the gathered emission columns all read shared memory:
+// every logit crosses HBM exactly once.
+__host__ __device__ constexpr int emit_blocks_per_cta(int nq) { return (nq >= 8 || nq < 0) ? 1 : 4; }
+__host__ __device__ inline size_t emit_slab_bytes(int Lp) { return ((size_t)2 * Lp * sizeof(int) + 127) / 128 * 128; }
+__host__ __device__ inline size_t emit_smem_bytes(int Lp, int staged_V) {
+    return staged_V ? emit_slab_bytes(Lp) + (size_t)kG * staged_V * 4 + 64 : (size_t)2 * Lp * sizeof(int);
+}
 
 template <int VEC, int NQ>
-__global__ void __launch_bounds__(128) k_emit(Problem p, Workspace w) {
+__global__ void __launch_bounds__(NQ < 0 ? 256 : 128) k_emit(Problem p, Workspace w) {
     using V_t = typename VecT<VEC>::type;
-    extern __shared__ int slab[];                 // 2*Lp ints: this utterance's labels, metadata scratch
+    extern __shared__ __align__(128) int slab[];  // 2*Lp ints: this utterance's labels, metadata scratch
     __shared__ int s_L, s_rep, s_flags;
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr bool STAGED = NQ < 0;
+    constexpr int NT = STAGED ? 256 : 128;        // staged rows: 8 warps, one row each
+    float* srow = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(slab) + emit_slab_bytes(w.Lp));   // kG rows of V floats
+    uint64_t* rbar = reinterpret_cast<uint64_t*>(srow + (size_t)kG * p.V);
     if (tid == 0) { s_L = p.Lmax; s_rep = 0; s_flags = 0; }
     __syncthreads();
     // operator parameter layer: lengths (trunc + clamp) and labels (trunc + clamp)
@@ -177,15 +194,26 @@ __global__ void __launch_bounds__(128) k_emit(Problem p, Workspace w) {
         if (l64 > p.Lmax) { l64 = p.Lmax; lenflags = UTT_LEN_CLAMPED; }
         L = (int)l64;
     } else {
-        for (int j = tid; j < p.Lmax; j += 128)
+        for (int j = tid; j < p.Lmax; j += NT)
             if (load_as_int(p.labels, p.label_dtype, b * p.lst_b + j * p.lst_l) == p.label_pad) atomicMin(&s_L, j);
         __syncthreads();
         L = s_L;
     }
     const bool meta_cta = blockIdx.x == gridDim.x - 1;       // one extra CTA per utterance: metadata only
+    if (STAGED && !meta_cta && lane == 0 && (int)blockIdx.x * kG < Tb) {
+        // this warp's row: requested before anything else, consumed below
+        const int t = blockIdx.x * kG + warp;
+        mbar_init(rbar + warp, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (t < Tb) {
+            mbar_expect_tx(rbar + warp, (uint32_t)p.V * 4);
+            tma_load_1d(srow + (size_t)warp * p.V, p.logits + b * p.st_b + (long long)t * p.st_t, (uint32_t)p.V * 4, rbar + warp);
+        }
+    }
+    __syncwarp();
     if (!w.dense || meta_cta) {
         int bad = 0;
-        for (int j = tid; j < L; j += 128) {
+        for (int j = tid; j < L; j += NT) {
             long long v = load_as_int(p.labels, p.label_dtype, b * p.lst_b + j * p.lst_l);
             if (v < 0 || v >= p.V || v == p.blank) bad = 1;
             slab[j] = (int)(v < 0 ? 0 : (v >= p.V ? p.V - 1 : v));
@@ -204,7 +232,49 @@ __global__ void __launch_bounds__(128) k_emit(Problem p, Workspace w) {
     if (!meta_cta && t0 < Tb) {
         float mxs[kG];
         const float* rows = p.logits + b * p.st_b + (long long)t0 * p.st_t;
-        if (NQ > 0) {
+        if (STAGED) {
+            __shared__ float s_mx[kG];
+            if (t0 + warp < Tb) {
+                mbar_wait(rbar + warp, 0);
+                const float4* sv = reinterpret_cast<const float4*>(srow + (size_t)warp * p.V);
+                float m0 = -INFINITY, m1 = -INFINITY;
+                for (int k = lane; k < nvec; k += 64) {
+                    const float4 a = sv[k];
+                    m0 = fmaxf(m0, fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)));
+                    if (k + 32 < nvec) { const float4 c = sv[k + 32]; m1 = fmaxf(m1, fmaxf(fmaxf(c.x, c.y), fmaxf(c.z, c.w))); }
+                }
+                const float mx = warp_max(fmaxf(m0, m1));
+                float s0 = 0.0f, s1 = 0.0f;
+                for (int k = lane; k < nvec; k += 64) {
+                    const float4 a = sv[k];
+                    s0 += fast_ex2((a.x - mx) * kLog2e) + fast_ex2((a.y - mx) * kLog2e);
+                    s1 += fast_ex2((a.z - mx) * kLog2e) + fast_ex2((a.w - mx) * kLog2e);
+                    if (k + 32 < nvec) {
+                        const float4 c = sv[k + 32];
+                        s0 += fast_ex2((c.x - mx) * kLog2e) + fast_ex2((c.y - mx) * kLog2e);
+                        s1 += fast_ex2((c.z - mx) * kLog2e) + fast_ex2((c.w - mx) * kLog2e);
+                    }
+                }
+                const float sum = warp_sum(s0 + s1);
+                if (lane == 0) { w.fr[(size_t)b * p.T + t0 + warp] = make_float2(mx, log2f(sum)); s_mx[warp] = mx; }
+            } else if (lane == 0) s_mx[warp] = 0.0f;
+            __syncthreads();
+            // the emission columns of the block's 8 frames, gathered from the staged rows: one thread per column,
+            // 64 contiguous bytes each
+            const int ncol = w.dense ? p.V : L + 1;
+            const int nval = min(kG, Tb - t0);
+            double* eblk = w.E + ((size_t)b * w.NB + blk) * w.W * kEC;
+            for (int col = tid; col < ncol; col += NT) {
+                const int v = w.dense ? col : (col == 0 ? p.blank : slab[col - 1]);
+                double y[kG];
+#pragma unroll
+                for (int j = 0; j < kG; ++j)
+                    y[j] = j < nval ? (double)fast_ex2(fmaxf((srow[(size_t)j * p.V + v] - s_mx[j]) * kLog2e, kMinLog2)) : 0.0;
+                double2* dst = reinterpret_cast<double2*>(eblk + (size_t)col * kEC);
+#pragma unroll
+                for (int j = 0; j < kG; j += 2) dst[j / 2] = make_double2(y[j], y[j + 1]);
+            }
+        } else if (NQ > 0) {
             constexpr int NQ1 = NQ > 0 ? NQ : 1;
             constexpr int F = NQ1 >= 16 ? 1 : (NQ1 >= 8 ? 2 : (NQ1 >= 4 ? 4 : 8));
 #pragma unroll
@@ -299,7 +369,7 @@ __global__ void __launch_bounds__(128) k_emit(Problem p, Workspace w) {
                 mxs[j] = mx;
             }
         }
-        const int ncol = NQ > 0 ? 0 : (w.dense ? p.V : L + 1);      // NQ > 0: already written frame by frame
+        const int ncol = NQ != 0 ? 0 : (w.dense ? p.V : L + 1);     // NQ != 0: already written frame by frame
         double* eblk = w.E + ((size_t)b * w.NB + blk) * w.W * kEC;
         for (int col = lane; col < ncol; col += 32) {
             const int v = w.dense ? col : (col == 0 ? p.blank : slab[col - 1]);
@@ -329,7 +399,7 @@ __global__ void __launch_bounds__(128) k_emit(Problem p, Workspace w) {
     __shared__ int s_nd;
     if (tid == 0) s_nd = 0;
     int rep = 0;
-    for (int j = tid; j < L; j += 128) {
+    for (int j = tid; j < L; j += NT) {
         const int v = slab[j];
         lab[j] = v;
         if (j > 0 && slab[j - 1] == v) ++rep;
@@ -341,7 +411,7 @@ __global__ void __launch_bounds__(128) k_emit(Problem p, Workspace w) {
     if (rep) atomicAdd(&s_rep, rep);
     __syncthreads();
     int mine = 0;
-    for (int j = tid; j < L; j += 128) {
+    for (int j = tid; j < L; j += NT) {
         if (s_run[j] < 0) continue;
         const int v = slab[j];
         int d = 0;
@@ -408,6 +478,16 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// shared -> global bulk copy (asynchronous proxy): the row was written with ordinary stores, hence the proxy fence
+__device__ __forceinline__ void tma_store_1d(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() {   // the source rows may be reused / the CTA may exit
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
     double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr)); return v;
@@ -1093,20 +1173,28 @@ constexpr int kGradFramesPerWarp = 2;  // 4 warps x 2 frames = one frame block p
 
 // occupancy row of one frame in rank order: Lp label slots, or a slot per register-resident pair
 __host__ __device__ inline int grad_row_floats(int Lp, int pairs_cap) { return ((Lp > pairs_cap ? Lp : pairs_cap) + 3) & ~3; }
-__host__ __device__ inline size_t grad_smem_bytes(int Lp, int pairs_cap) {
-    return (size_t)(Lp + 1) * 8 + (size_t)4 * kGradFramesPerWarp * grad_row_floats(Lp, pairs_cap) * 4 + 16;
+// staged_V != 0: the frame block's kG logits rows are staged in shared memory (XQ < 0)
+__host__ __device__ inline size_t grad_staged_bytes(int staged_V) { return staged_V ? (size_t)kG * staged_V * 4 + 64 : 0; }
+__host__ __device__ inline size_t grad_smem_bytes(int Lp, int pairs_cap, int staged_V = 0) {
+    return grad_staged_bytes(staged_V) + (size_t)(Lp + 1) * 8 + (size_t)4 * kGradFramesPerWarp * grad_row_floats(Lp, pairs_cap) * 4 + 16;
 }
 
 // XQ = VEC-wide loads per lane that hold the frame's logits row in registers (issued together
-// with the history loads so that one memory round trip covers both); 0 = row loaded when needed.
+// with the history loads so that one memory round trip covers both); 0 = row loaded when needed;
+// -1 (wide vocabularies, 16-byte aligned rows): the CTA's kG rows are fetched into shared memory by
+// 1-D bulk copies (TMA) issued before anything else -- 8 rows in flight per CTA, several CTAs per SM,
+// while the occupancies are computed -- the gradient row is formed in place, label columns included,
+// and leaves with one bulk store per row.
 // OCC = 1: registers capped at 64 (8 CTAs per SM instead of 7, a few spilled words) for batches
 // that run after the walkers: measured -14 % at cfg5, but +5 % on the overlapped cfg2 step, where
 // the kernel shares the GPU with the walkers and its tail is what counts -- hence a variant.
 template <int VEC, int CH, int XQ, int OCC = 0>
-__global__ void __launch_bounds__(128, (CH == 0 || CH == 8) ? 5 : (CH <= 4 ? (OCC ? 8 : 1) : 3)) k_grad(GradArgs a) {
+__global__ void __launch_bounds__(XQ < 0 ? 256 : 128, XQ < 0 ? (CH == 16 ? 2 : 3) : ((CH == 0 || CH == 8) ? 5 : (CH <= 4 ? (OCC ? 8 : 1) : 3))) k_grad(GradArgs a) {
     using V_t = typename VecT<VEC>::type;
     constexpr int NCH = CH > 0 ? CH : 1, NXQ = XQ > 0 ? XQ : 1;
-    constexpr int F = (CH > 0 && CH <= 4) ? kGradFramesPerWarp : 1;      // frames in flight per warp
+    // staged rows: 8 warps, one frame each (the compute phase is latency-bound: twice the warps per SM)
+    constexpr int FPW = XQ < 0 ? 1 : kGradFramesPerWarp, NT = XQ < 0 ? 256 : 128;
+    constexpr int F = (CH > 0 && CH <= 4) ? FPW : 1;      // frames in flight per warp
     const Problem& p = a.p; const Workspace& w = a.w;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // the utterance's metadata is written by k_emit (complete before this grid exists) or, in the
@@ -1124,15 +1212,33 @@ __global__ void __launch_bounds__(128, (CH == 0 || CH == 8) ? 5 : (CH <= 4 ? (OC
     const int t_first = blk * kG;
     const bool cta_live = blk < NQ;
     const int GW = grad_row_floats(w.Lp, 32 * CH);
-    extern __shared__ __align__(16) unsigned char gsm_raw[];
-    float* gbuf0 = reinterpret_cast<float*>(gsm_raw) + (size_t)warp * kGradFramesPerWarp * GW;
+    constexpr bool STAGED = XQ < 0;
+    extern __shared__ __align__(128) unsigned char gsm_all[];
+    unsigned char* gsm_raw = gsm_all + (STAGED ? grad_staged_bytes(p.V) : 0);
+    float* srow = reinterpret_cast<float*>(gsm_all);                                         // kG rows of V floats
+    uint64_t* rbar = reinterpret_cast<uint64_t*>(gsm_all + (size_t)kG * p.V * 4);            // one barrier per row
+    if (STAGED && cta_live && lane == 0) {
+        // this warp's rows: requested now, consumed after the occupancies of their frames
+#pragma unroll
+        for (int f = 0; f < FPW; ++f) mbar_init(rbar + warp * FPW + f, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+        for (int f = 0; f < FPW; ++f) {
+            const int j = warp * FPW + f, t = t_first + j;
+            if (t < Tb) {
+                mbar_expect_tx(rbar + j, (uint32_t)p.V * 4);
+                tma_load_1d(srow + (size_t)j * p.V, p.logits + b * p.st_b + (long long)t * p.st_t, (uint32_t)p.V * 4, rbar + j);
+            }
+        }
+    }
+    float* gbuf0 = reinterpret_cast<float*>(gsm_raw) + (size_t)warp * FPW * GW;
     int2* s_dl = reinterpret_cast<int2*>(reinterpret_cast<float*>(gsm_raw) + (size_t)4 * kGradFramesPerWarp * GW);   // Lp + 1
     const int* rank = w.rank + (size_t)b * w.Lp;
     int nd = 0;
     if (cta_live) {
         nd = __ldcg(w.nd + b);
         const int2* dl = w.dl + (size_t)b * (w.Lp + 1);
-        for (int j = tid; j <= nd; j += 128) s_dl[j] = __ldcg(dl + j);
+        for (int j = tid; j <= nd; j += NT) s_dl[j] = __ldcg(dl + j);
         if (tid == 0) {
             // block n is frame block n of the alpha walker and block NQ-1-n of the beta walker
             const int* gp = w.gprog + 4 * b;
@@ -1168,14 +1274,14 @@ __global__ void __launch_bounds__(128, (CH == 0 || CH == 8) ? 5 : (CH <= 4 ? (OC
     const int nvec = p.V / VEC;
 
 #pragma unroll
-    for (int r = 0; r < kGradFramesPerWarp / F; ++r) {
+    for (int r = 0; r < FPW / F; ++r) {
         int tt[F]; bool live[F];
         int2 ha[F][NCH]; int hbb[F][NCH], hbl[F][NCH];
         V_t xr[F][NXQ]; float2 fr[F];
         // ---- every global load of the F frames ----
 #pragma unroll
         for (int f = 0; f < F; ++f) {
-            tt[f] = t_first + warp * kGradFramesPerWarp + r * F + f;
+            tt[f] = t_first + warp * FPW + r * F + f;
             live[f] = cta_live && tt[f] < Tb;
             fr[f] = make_float2(0.0f, 0.0f);
             if (live[f]) {
@@ -1277,6 +1383,35 @@ __global__ void __launch_bounds__(128, (CH == 0 || CH == 8) ? 5 : (CH <= 4 ? (OC
                         gv[k] = o;
                     }
                 }
+            } else if (STAGED) {
+                // the row is in shared memory: gradient formed in place, then one bulk store
+                float* sr = srow + (size_t)(warp * FPW + r * F + f) * p.V;
+                mbar_wait(rbar + warp * FPW + r * F + f, 0);
+                float4* sv = reinterpret_cast<float4*>(sr);
+                for (int k = lane; k < nvec; k += 32) {
+                    float4 v = sv[k];
+                    v.x = head * fast_ex2(fmaf(v.x - fmx, kLog2e, -flz));
+                    v.y = head * fast_ex2(fmaf(v.y - fmx, kLog2e, -flz));
+                    v.z = head * fast_ex2(fmaf(v.z - fmx, kLog2e, -flz));
+                    v.w = head * fast_ex2(fmaf(v.w - fmx, kLog2e, -flz));
+                    sv[k] = v;
+                }
+                __syncwarp();
+                // sr[v] now holds head * y_v: the corrections subtract head * occupancy.  Blank first, then
+                // the label columns (a label equal to the blank -- invalid input -- lands on top of it: both kept)
+                if (lane == 0) sr[p.blank] = fmaf(-head, gblank, sr[p.blank]);
+                __syncwarp();
+                const float hz = head * rZ;
+                for (int d = lane; d < nd; d += 32) {
+                    const int2 e = s_dl[d];
+                    const int end = s_dl[d + 1].y;
+                    float occ = 0.0f;
+                    for (int k = e.y; k < end; ++k) occ += gbuf[k];
+                    sr[e.x] = fmaf(-hz, occ, sr[e.x]);
+                }
+                __syncwarp();
+                if (lane == 0) tma_store_1d(grow, sr, (uint32_t)p.V * 4);
+                continue;
             } else {
                 // wide rows: four vector loads in flight per lane; the blank column is fixed afterwards
                 const V_t* xv = reinterpret_cast<const V_t*>(xrow);
@@ -1324,6 +1459,7 @@ __global__ void __launch_bounds__(128, (CH == 0 || CH == 8) ? 5 : (CH <= 4 ? (OC
             }
         }
     }
+    if (STAGED && lane == 0) tma_store_wait_read();      // the rows leave shared memory before the CTA does
     // the stream's next kernel must also see what the walkers write last (loss, loss_sum): one CTA
     // holds this grid open until the walker grid has completed and flushed
     if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
