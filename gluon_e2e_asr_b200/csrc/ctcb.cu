@@ -123,8 +123,25 @@ cudaError_t ensure_dynamic_smem(const void* fn, size_t bytes) {
     return rc;
 }
 
+// CUDA loads a kernel lazily at its first launch, and that load can wait for the device to drain.  A
+// kernel that running kernels WAIT FOR (k_emit, launched after the walkers that consume its blocks) must
+// therefore be resident before those are launched: cudaFuncGetAttributes forces the load.  Once per
+// device and kernel.
+cudaError_t ensure_loaded(const void* fn) {
+    static std::mutex mu;
+    static std::vector<std::pair<int, const void*>> seen;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& e : seen) if (e.first == dev && e.second == fn) return cudaSuccess;
+    cudaFuncAttributes fa{};
+    const cudaError_t rc = cudaFuncGetAttributes(&fa, fn);
+    if (rc == cudaSuccess) seen.push_back({dev, fn});
+    return rc;
+}
+
 struct Layout {
-    size_t off_Tb, off_Lb, off_flags, off_lab, off_rank, off_dl, off_nd, off_fr, off_E, off_hA, off_hB, off_oA, off_oB, off_gprog, total;
+    size_t off_Tb, off_Lb, off_flags, off_lab, off_rank, off_dl, off_nd, off_fr, off_E, off_hA, off_hB, off_oA, off_oB, off_gprog, off_eprog, total;
     int Lp, W, NB, dense, fused, P, NW;
     const WalkEntry* walk;
 };
@@ -161,6 +178,7 @@ Layout make_layout(int T, int B, int V, int Lmax, int need_grad) {
     l.off_dl = take(sizeof(int2) * (size_t)B * (l.Lp + 1));
     l.off_nd = take(sizeof(int) * B);
     l.off_gprog = take(sizeof(int) * 4 * (size_t)B);
+    l.off_eprog = take(l.fused ? 0 : sizeof(int) * (size_t)B * l.NB);
     l.off_fr = take(sizeof(float2) * (size_t)B * T);
     l.off_E = take(l.fused ? 0 : sizeof(double) * (size_t)B * l.NB * l.W * ctcb::kEC);
     if (need_grad) {
@@ -190,6 +208,8 @@ ctcb::Workspace carve(const Layout& l, void* ws) {
     w.oA = reinterpret_cast<int2*>(base + l.off_oA);
     w.oB = reinterpret_cast<int2*>(base + l.off_oB);
     w.gprog = reinterpret_cast<int*>(base + l.off_gprog);
+    w.eprog = reinterpret_cast<int*>(base + l.off_eprog);
+    w.ew = 0;
     w.Lp = l.Lp; w.W = l.W; w.NB = l.NB; w.dense = l.dense; w.P = l.P; w.NW = l.NW;
     w.fused = l.fused;
     return w;
@@ -284,7 +304,7 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
         return fail(CTCB_INVALID_VALUE, "logits/labels/loss/grad/workspace must be CUDA device memory (there is no CPU path)");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const ctcb::Problem dp = to_device_problem(p);
-    const ctcb::Workspace w = carve(lay, workspace);
+    ctcb::Workspace w = carve(lay, workspace);
 
     if (phases & PH_FORWARD) {
         const WalkEntry* we = lay.walk;
@@ -316,39 +336,71 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
         }
         const int vec = pick_vec(p->logits, p->logits_stride_t, p->logits_stride_b, p->V);
         CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(wfn), smem));
-        if (!lay.fused) {
         // NQ: vector loads per lane that hold one logits row in registers (0 = two-pass)
         const int units = (p->V / vec + 31) / 32;
         int nq = units <= 1 ? 1 : units <= 2 ? 2 : units <= 4 ? 4 : units <= 8 ? 8 : units <= 16 ? 16 : 0;
         // wide vocabularies with 16-byte aligned rows: the frame block's rows staged in shared memory by bulk copies
         const char* est = getenv("CTCB_EMIT_STAGED");
-        const bool staged = vec == 4 && (nq == 0 || nq >= 8) && ctcb::emit_smem_bytes(lay.Lp, p->V) <= 75 * 1024 &&
+        const bool staged = !lay.fused && vec == 4 && (nq == 0 || nq >= 8) && ctcb::emit_smem_bytes(lay.Lp, p->V) <= 75 * 1024 &&
                             !(est && atoi(est) == 0);
         if (staged) nq = -1;
-        const int bpc = ctcb::emit_blocks_per_cta(nq);
-        const dim3 egrid((lay.NB + bpc - 1) / bpc + 1, p->B);   // + the metadata CTA of each utterance
-        const size_t esm = ctcb::emit_smem_bytes(lay.Lp, staged ? p->V : 0);
-        if (staged) {
-            if (esm > 48 * 1024) CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(ctcb::k_emit<4, -1>), esm));
-            ctcb::k_emit<4, -1><<<egrid, 256, esm, stream>>>(dp, w);
-        } else
+        // ... and then k_emit runs CONCURRENTLY with the walkers: k_walk is launched first, k_emit as its
+        // programmatic dependent, publishing every emission block (Workspace::eprog) in the order the two
+        // walkers consume them.  One walker CTA per SM at most, so that the emission CTAs keep their room.
+        const char* eew = getenv("CTCB_EW_OVERLAP");
+        // Measured at cfg3 and NOT faster (forward 114 -> 143 us, whole step 216 -> 213 us: the walkers' history
+        // stores stall behind the emission kernel's traffic), so it is opt-in: CTCB_EW_OVERLAP=1.
+        const bool ew = staged && !g_prof_events && 2 * p->B <= 148 && overlap_allowed(p->B, false) && eew && atoi(eew) != 0;
+        w.ew = ew ? 1 : 0;
+        auto launch_emit = [&]() -> int {
+            const int bpc = ctcb::emit_blocks_per_cta(nq);
+            const int nblk = (lay.NB + bpc - 1) / bpc + 1;          // + the metadata CTA of each utterance
+            const dim3 egrid = ew ? dim3(p->B, nblk) : dim3(nblk, p->B);
+            const size_t esm = ctcb::emit_smem_bytes(lay.Lp, staged ? p->V : 0);
+            if (staged) {
+                auto efn = ctcb::k_emit<4, -1>;
+                if (esm > 48 * 1024) CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(efn), esm));
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = egrid; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = esm; cfg.stream = stream;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = attr; cfg.numAttrs = ew ? 1 : 0;
+                CUDA_TRY(cudaLaunchKernelEx(&cfg, efn, dp, w));
+            } else {
 #define EMIT_LAUNCH(V_, Q_) ctcb::k_emit<V_, Q_><<<egrid, 128, esm, stream>>>(dp, w)
 #define EMIT_NQ(V_) switch (nq) { case 1: EMIT_LAUNCH(V_, 1); break; case 2: EMIT_LAUNCH(V_, 2); break; \
                                   case 4: EMIT_LAUNCH(V_, 4); break; case 8: EMIT_LAUNCH(V_, 8); break;  \
                                   case 16: EMIT_LAUNCH(V_, 16); break; default: EMIT_LAUNCH(V_, 0); break; }
-        switch (vec) {
-            case 4: EMIT_NQ(4); break;
-            case 2: EMIT_NQ(2); break;
-            default: EMIT_NQ(1); break;
-        }
+                switch (vec) {
+                    case 4: EMIT_NQ(4); break;
+                    case 2: EMIT_NQ(2); break;
+                    default: EMIT_NQ(1); break;
+                }
 #undef EMIT_NQ
 #undef EMIT_LAUNCH
-        mark(stream);
+            }
+            mark(stream);
+            return CTCB_OK;
+        };
+        auto launch_walk = [&]() -> int {
+            ctcb::WalkArgs wa{dp, w, p->T, stages, p->blank, p->loss, p->loss_sum, nullptr};
+            const int wthreads = (we->NW + (lay.fused ? ctcb::kFusedProducers + 1 : 1)) * 32;
+            wfn<<<dim3(p->B, need_grad ? 2 : 1), wthreads, smem, stream>>>(wa);
+            mark(stream);
+            return CTCB_OK;
+        };
+        if (ew) {
+            // the walkers spin on what k_emit publishes: k_emit must be loaded and configured before they start
+            const void* efn = reinterpret_cast<const void*>(ctcb::k_emit<4, -1>);
+            CUDA_TRY(ensure_loaded(efn));
+            CUDA_TRY(ensure_dynamic_smem(efn, ctcb::emit_smem_bytes(lay.Lp, p->V)));
+            if (int rc = launch_walk()) return rc;
+            if (int rc = launch_emit()) return rc;
+        } else {
+            if (!lay.fused) { if (int rc = launch_emit()) return rc; }
+            if (int rc = launch_walk()) return rc;
         }
-        ctcb::WalkArgs wa{dp, w, p->T, stages, p->blank, p->loss, p->loss_sum, nullptr};
-        const int wthreads = (we->NW + (lay.fused ? ctcb::kFusedProducers + 1 : 1)) * 32;
-        wfn<<<dim3(p->B, need_grad ? 2 : 1), wthreads, smem, stream>>>(wa);
-        mark(stream);
     }
     if (phases & PH_BACKWARD) {
         ctcb::GradArgs ga{dp, w};

@@ -72,8 +72,11 @@ struct Workspace {        // carved out of the caller's workspace by the host (c
     int2* oA;                         // (B, NB, NW*PW) exponent offsets {blank, label} valid for frame block n
     int2* oB;
     int* gprog;                       // (B, 4) {frame blocks whose history is complete: alpha walker, beta walker;
-                                      //   metadata ready (Tb, Lb, flags, rank, dl, nd); unused}: published with
-                                      //   release/gpu scope, polled by the gradient CTAs
+                                      //   metadata ready (Tb, Lb, flags, rank, dl, nd), twice: one word per reader
+                                      //   class}: published with release/gpu scope, polled by the gradient CTAs
+                                      //   (and, when k_emit runs concurrently, by the walkers)
+    int* eprog;                       // (B, NB) emission block written (k_emit concurrent with the walkers only)
+    int ew;                           // k_emit runs concurrently with (and is launched after) k_walk
     int Lp, W, NB, dense, P, NW;      // PW = 32*P pairs per walker warp
     int fused;                        // emissions made by the walkers' producer warps (no k_emit, no E)
 };
@@ -149,6 +152,7 @@ template <> __device__ __forceinline__ float vec_fill<1>(float v) { return v; }
 template <> __device__ __forceinline__ float2 vec_fill<2>(float v) { return make_float2(v, v); }
 template <> __device__ __forceinline__ float4 vec_fill<4>(float v) { return make_float4(v, v, v, v); }
 
+__device__ __forceinline__ void st_release_gpu(int* p, int v);
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count);
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes);
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity);
@@ -172,8 +176,16 @@ __global__ void __launch_bounds__(NQ < 0 ? 256 : 128) k_emit(Problem p, Workspac
     using V_t = typename VecT<VEC>::type;
     extern __shared__ __align__(128) int slab[];  // 2*Lp ints: this utterance's labels, metadata scratch
     __shared__ int s_L, s_rep, s_flags;
-    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr bool STAGED = NQ < 0;
+    // Concurrent with the walkers (launched after them as a programmatic dependent): CTAs are dispatched
+    // utterance-fastest, the metadata CTAs first, then the frame blocks of every utterance from both ends
+    // towards the middle -- the order in which the alpha and the beta walker consume them; each block is
+    // published in Workspace::eprog.
+    const bool ew = STAGED && w.ew != 0;
+    if (STAGED) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int b = ew ? blockIdx.x : blockIdx.y;
+    const int xi = ew ? (int)blockIdx.y - 1 : (int)blockIdx.x;
     constexpr int NT = STAGED ? 256 : 128;        // staged rows: 8 warps, one row each
     float* srow = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(slab) + emit_slab_bytes(w.Lp));   // kG rows of V floats
     uint64_t* rbar = reinterpret_cast<uint64_t*>(srow + (size_t)kG * p.V);
@@ -199,10 +211,15 @@ __global__ void __launch_bounds__(NQ < 0 ? 256 : 128) k_emit(Problem p, Workspac
         __syncthreads();
         L = s_L;
     }
-    const bool meta_cta = blockIdx.x == gridDim.x - 1;       // one extra CTA per utterance: metadata only
-    if (STAGED && !meta_cta && lane == 0 && (int)blockIdx.x * kG < Tb) {
+    const bool meta_cta = ew ? xi < 0 : blockIdx.x == gridDim.x - 1;       // one extra CTA per utterance: metadata only
+    int sblk = xi;
+    if (ew && !meta_cta) {
+        const int NQb = (Tb + kG - 1) / kG;
+        sblk = xi < NQb ? ((xi & 1) ? NQb - 1 - (xi >> 1) : (xi >> 1)) : w.NB;
+    }
+    if (STAGED && !meta_cta && lane == 0 && sblk * kG < Tb) {
         // this warp's row: requested before anything else, consumed below
-        const int t = blockIdx.x * kG + warp;
+        const int t = sblk * kG + warp;
         mbar_init(rbar + warp, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (t < Tb) {
@@ -227,7 +244,7 @@ __global__ void __launch_bounds__(NQ < 0 ? 256 : 128) k_emit(Problem p, Workspac
     // one block per CTA with two frames per warp: four times as many CTAs, so the grid is several
     // waves deep and every SM keeps more row loads in flight
     constexpr int BPC = emit_blocks_per_cta(NQ), FPW = kG * BPC / 4;
-    const int blk = BPC == 4 ? blockIdx.x * 4 + warp : blockIdx.x, t0 = blk * kG;
+    const int blk = BPC == 4 ? blockIdx.x * 4 + warp : (STAGED ? sblk : (int)blockIdx.x), t0 = blk * kG;
     const int jbeg = BPC == 4 ? 0 : warp * FPW;
     if (!meta_cta && t0 < Tb) {
         float mxs[kG];
@@ -273,6 +290,10 @@ __global__ void __launch_bounds__(NQ < 0 ? 256 : 128) k_emit(Problem p, Workspac
                 double2* dst = reinterpret_cast<double2*>(eblk + (size_t)col * kEC);
 #pragma unroll
                 for (int j = 0; j < kG; j += 2) dst[j / 2] = make_double2(y[j], y[j + 1]);
+            }
+            if (ew) {
+                __syncthreads();
+                if (tid == 0) { __threadfence(); st_release_gpu(w.eprog + (size_t)b * w.NB + blk, 1); }
             }
         } else if (NQ > 0) {
             constexpr int NQ1 = NQ > 0 ? NQ : 1;
@@ -426,9 +447,17 @@ __global__ void __launch_bounds__(NQ < 0 ? 256 : 128) k_emit(Problem p, Workspac
         if (Tb <= 0 || L + s_rep > Tb) flags |= UTT_INFEASIBLE;
         w.Tb[b] = Tb; w.Lb[b] = L; w.flags[b] = flags;
         w.nd[b] = s_nd; dl[s_nd] = make_int2(-1, L);
-        w.gprog[4 * b] = 0; w.gprog[4 * b + 1] = 0; w.gprog[4 * b + 2] = 1;
         if (p.status) p.status[b] = flags;
         if (flags & UTT_INFEASIBLE) p.loss[b] = 0.0f;   // defined behaviour, SURVEY 7.3-6
+        if (ew) {      // the walkers reset the progress words before this grid could exist, and wait for these
+            __threadfence();
+            st_release_gpu(w.gprog + 4 * b + 2, 1);
+            st_release_gpu(w.gprog + 4 * b + 3, 1);
+            // the stream's next kernel must see what the walkers write last: this grid stays open until they are done
+            if (b == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
+        } else {
+            w.gprog[4 * b] = 0; w.gprog[4 * b + 1] = 0; w.gprog[4 * b + 2] = 1;
+        }
     }
 }
 
@@ -731,6 +760,39 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
             tma_load_1d(smem_raw + (size_t)st * stage_bytes, Eb + (size_t)blk * W * kEC, stage_bytes, &full[st]);
         };
         const int npro = min(NS, NQ);
+        if (w.ew) {
+            // k_emit runs concurrently: a block is requested once its flag is up; the alpha CTA's lanes add the
+            // block's log2(softmax denominator) terms as they go (lane = t mod 32, increasing t: the order of the
+            // serial schedule below, so the loss carries the same bits)
+            const int* ep = w.eprog + (size_t)b * w.NB;
+            double s = 0.0;
+            auto acquire = [&](int n) {
+                const int blk = DIR ? NQ - 1 - n : n;
+                while (ld_acquire_gpu(ep + blk) == 0) __nanosleep(100);
+                if (DIR == 0) {
+                    const int j = (lane - blk * kG) & 31, t = blk * kG + j;
+                    if (j < kG && t < Tb) s += (double)__ldcg(&w.fr[(size_t)b * a.T + t].y);
+                }
+                if (lane == 0) asm volatile("fence.proxy.async;" ::: "memory");
+            };
+            for (int n = 0; n < npro; ++n) { acquire(n); if (lane == 0) issue(n, n); }
+            int* gp = HIST ? w.gprog + 4 * b + DIR : nullptr;
+            int st = 0; uint32_t par = 0;
+            for (int n = 0; n < NQ; ++n) {
+                mbar_wait_relaxed(&empty[st], par);                   // group n is complete, its stage is free
+                const int sn = st + 1 == NS ? 0 : st + 1; const uint32_t pn = st + 1 == NS ? par ^ 1 : par;
+                if (HIST && lane == 0 && (n + 1 == NQ || !mbar_test(&empty[sn], pn))) st_release_gpu(gp, n + 1);
+                if (n + NS < NQ) { acquire(n + NS); if (lane == 0) issue(n + NS, st); }
+                st = sn; par = pn;
+            }
+            if (DIR == 0) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+                    s += __hiloint2double(__shfl_xor_sync(FULL, __double2hiint(s), o), __shfl_xor_sync(FULL, __double2loint(s), o));
+                if (lane == 0) { sts_f64(lsum, s); sts_release(lsum + 8, 1); }
+            }
+            return;
+        }
         if (lane == 0) for (int n = 0; n < npro; ++n) issue(n, n);
         if (DIR == 0) {                         // sum_t log2(softmax denominator), fixed order
             double s = 0.0;
@@ -1049,8 +1111,23 @@ __global__ void __launch_bounds__((NW + (FUSED ? kFusedProducers + 1 : 1)) * 32)
     if (!FUSED) {
         // the gradient kernel may start as soon as every walker CTA is resident: its CTAs wait per
         // frame block on the progress this kernel publishes (Workspace::gprog)
+        if (a.w.ew) {
+            // this grid is the first of the call: the progress words start at 0 before k_emit (the dependent
+            // launched next) or k_grad (launched after it) can exist; then wait for k_emit's metadata CTA
+            if (blockIdx.y == 0) for (int j = threadIdx.x; j < a.w.NB; j += blockDim.x) a.w.eprog[(size_t)b * a.w.NB + j] = 0;
+            if (threadIdx.x == 0) {
+                a.w.gprog[4 * b + blockIdx.y] = 0;
+                a.w.gprog[4 * b + 2 + blockIdx.y] = 0;
+            }
+            __threadfence();
+            __syncthreads();
+        }
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-        const int flags = a.w.flags[b], Tb = a.w.Tb[b], Lb = a.w.Lb[b];
+        if (a.w.ew) {
+            if (threadIdx.x == 0) { while (ld_acquire_gpu(a.w.gprog + 4 * b + 2 + blockIdx.y) == 0) __nanosleep(200); }
+            __syncthreads();
+        }
+        const int flags = __ldcg(a.w.flags + b), Tb = __ldcg(a.w.Tb + b), Lb = __ldcg(a.w.Lb + b);
         if (flags & UTT_INFEASIBLE) return;
         if (blockIdx.y == 0) walk_dir<P, NW, 0, HIST, false>(a, smem_raw, Tb, Lb, flags);
         else                 walk_dir<P, NW, 1, HIST, false>(a, smem_raw, Tb, Lb, flags);

@@ -340,6 +340,44 @@ def test_overlapped_and_serial_schedules_agree(dev):
     assert torch.equal(ref[0], l2) and torch.equal(ref[1], g2)
 
 
+def test_wide_vocabulary_concurrent_schedule(dev):
+    """Wide vocabularies (rows staged by bulk copies).  Default schedule: k_emit, then k_walk with k_grad
+    as its programmatic dependent sharing the walkers' SMs.  Opt-in schedule (CTCB_EW_OVERLAP=1): k_walk
+    launched first, k_emit as its programmatic dependent publishing emission blocks from both ends
+    inwards, k_grad behind it -- three grids running concurrently.  Both against the same kernels
+    launched one after the other: same BITS (loss, gradient, status), run after run, for ragged batches
+    with an infeasible utterance; and inside the tolerance of the fp64 oracle."""
+    from gluon_e2e_asr_b200 import ctc_loss_and_grad, ops
+    for (B, T, V, L, seed) in ((9, 75, 600, 14, 41), (5, 130, 2000, 40, 42), (64, 40, 1024, 9, 43)):
+        d = make_batch(B, T, V, L, seed=seed)
+        d["pred_lengths"][1] = 4.0; d["label_lengths"][1] = float(min(L, 9))       # infeasible
+        t = _to(dev, d)
+        args = (t["pred"], t["label"], t["pred_lengths"], t["label_lengths"])
+        head = torch.linspace(0.5, 1.5, B, device=dev)
+        with _env(CTCB_OVERLAP=0, CTCB_EW_OVERLAP=0):
+            ops._ws_cache.clear()
+            st0 = torch.zeros((B,), dtype=torch.int32, device=dev)
+            l0, g0 = ctc_loss_and_grad(*args, head_grad=head, status=st0)
+            l0, g0 = l0.clone(), g0.clone()
+            assert _lib_launches() == 3
+        for rep in range(4):
+            st1 = torch.zeros((B,), dtype=torch.int32, device=dev)
+            with _env(CTCB_EW_OVERLAP=rep % 2):            # opt-in: k_emit concurrent with the walkers too
+                l1, g1 = ctc_loss_and_grad(*args, head_grad=head, status=st1, out_grad=torch.full_like(g0, float("nan")))
+            assert _lib_launches() == 3
+            assert torch.equal(l0, l1) and torch.equal(st0, st1), "loss/status differ (run %d)" % rep
+            assert torch.equal(g0, g1), "gradient differs (run %d)" % rep
+        lo, go, ok = O.CtcLossOracle("NTC", "NT")(d["pred"], d["label"], d["pred_lengths"], d["label_lengths"],
+                                                 head_grad=head.cpu().numpy().astype(np.float64))
+        _check(l1.cpu().numpy(), g1.cpu().numpy(), lo, go, "wide concurrent B%d T%d V%d" % (B, T, V))
+        assert (st1.cpu().numpy()[1] & 1) == 1 and not ok[1]
+
+
+def _lib_launches():
+    from gluon_e2e_asr_b200 import _lib
+    return _lib.last_launch_count()
+
+
 def test_fused_and_unfused_emissions_agree(dev):
     """Emission blocks made by the walkers' producer warps (V <= 64) against k_emit + TMA: the same
     numerators; only the summation order of the loss normaliser differs."""
