@@ -221,7 +221,7 @@ def run_cuda(args, rank, world, local_rank):
     if nset % 2:
         nset -= 1
         sets = sets[:nset]
-    graph_allreduce = world > 1 and not args.no_graph_allreduce
+    graph_allreduce = world > 1 and not args.no_graph_allreduce and not args.no_allreduce
 
     def step_eager(s, slot=0):
         ops.ctc_loss_and_grad(s["pred"], s["label"], s["pl"], s["ll"], head_grad=head, loss_sum=loss_sums[slot],
@@ -271,7 +271,7 @@ def run_cuda(args, rank, world, local_rank):
                 else:
                     step_eager(s, i % 2)
                 frames += s["frames"]
-                if world > 1 and allreduce and not (graph and graph_allreduce):
+                if world > 1 and allreduce and not args.no_allreduce and not (graph and graph_allreduce):
                     # scalar loss-sum all-reduce on a side stream: never blocks the next step
                     ev = torch.cuda.Event()
                     ev.record(stream)
@@ -616,6 +616,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--pipe-depth", type=int, default=2, help="batches in flight in the prefetching host entry (e2e)")
     ap.add_argument("--no-others", action="store_true", help="skip the context measurements of the other configs")
+    ap.add_argument("--no-allreduce", action="store_true", help="experiment: no loss-sum collective at all (N>1)")
     ap.add_argument("--no-graph-allreduce", action="store_true",
                     help="N>1: issue the loss-sum all-reduce from the host every step instead of from the captured graph")
     args = ap.parse_args()
