@@ -216,21 +216,48 @@ def run_cuda(args, rank, world, local_rank):
     # accumulates into slot i % 2 while the side branch of the same graph reduces slot (i-1) % 2 --
     # the previous step's sum -- over NCCL, so the collective never sits on the kernels' critical path
     # and costs no host call per step (it is part of the captured graph).
-    loss_sums = torch.zeros((2,), dtype=torch.float64, device=dev)
+    part = torch.zeros((2, 3), dtype=torch.float64, device=dev)         # per slot: partial {loss sum, frames, utterances}
+    loss_sums = part[:, 0]                                               # the walkers accumulate straight into the partials
     red_buf = torch.zeros((2, 3), dtype=torch.float64, device=dev)      # {loss sum, frames, utterances} per slot
     if nset % 2:
         nset -= 1
         sets = sets[:nset]
     graph_allreduce = world > 1 and not args.no_graph_allreduce and not args.no_allreduce
+    force_x = world == 1 and os.environ.get("CTCB_BENCH_FORCE_EXCHANGE") == "1"    # experiment: the exchange's own cost on one GPU
+    graph_allreduce = graph_allreduce or force_x
 
     def step_eager(s, slot=0):
         ops.ctc_loss_and_grad(s["pred"], s["label"], s["pl"], s["ll"], head_grad=head, loss_sum=loss_sums[slot],
                               out_loss=s["loss"], out_grad=s["grad"], handoff="pointer")
 
+    # The exchange: by default the library's peer mailbox (ctcb_mailbox_*: one tiny kernel that stores the partial sums
+    # into every rank's mailbox over NVLink peer access and picks up the previous exchange -- no collective kernel and
+    # no rendezvous on the step's path); --collective nccl keeps torch.distributed's all-reduce.
+    peer = None
+    collective = "none"
+    if force_x:
+        from gluon_e2e_asr_b200 import PeerLossSum
+        peer = PeerLossSum(dev)
+        collective = "peer"
+    if world > 1 and not args.no_allreduce:
+        collective = "nccl"
+        if args.collective == "peer":
+            try:
+                from gluon_e2e_asr_b200 import PeerLossSum
+                peer = PeerLossSum(dev)
+                collective = "peer"
+            except Exception as exc:  # noqa: BLE001
+                if rank == 0:
+                    print("bench.py: peer mailbox unavailable (%s); using the NCCL all-reduce" % str(exc)[:160], file=sys.stderr)
+
     def reduce_slot(slot):
-        red_buf[slot, 0].copy_(loss_sums[slot], non_blocking=True)
-        loss_sums[slot].zero_()
-        dist.all_reduce(red_buf[slot])
+        if peer is not None:
+            # ONE kernel: red_buf <- all-rank sum of the previous exchange; this slot's partials stored to every rank, zeroed
+            peer.exchange(part[slot], red_buf[slot])
+        else:
+            red_buf[slot].copy_(part[slot], non_blocking=True)
+            part[slot].zero_()
+            dist.all_reduce(red_buf[slot])
 
     stream = torch.cuda.Stream(dev)
     comm_stream = torch.cuda.Stream(dev)
@@ -238,20 +265,23 @@ def run_cuda(args, rank, world, local_rank):
     with torch.cuda.stream(stream):
         for i, s in enumerate(sets[:2]):
             step_eager(s, i % 2)
-        if world > 1:
-            reduce_slot(0); reduce_slot(1)              # NCCL warm-up outside any capture
-        torch.cuda.synchronize()
         launches_per_step = _lib.last_launch_count()
+        if world > 1 and not args.no_allreduce:
+            reduce_slot(0); reduce_slot(1)              # warm-up of the exchange outside any capture (same count on every rank)
+        torch.cuda.synchronize()
         walk_cfg = _lib.last_walk_config()
         for i, s in enumerate(sets):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=stream):
-                if graph_allreduce:
+                if graph_allreduce and peer is not None:
+                    # the previous step's slot rides on this step's gradient kernel: no extra launch, no side branch
+                    peer.exchange_with_next(part[(i + 1) % 2], red_buf[(i + 1) % 2])
+                elif graph_allreduce:
                     comm_stream.wait_stream(stream)
                     with torch.cuda.stream(comm_stream):
                         reduce_slot((i + 1) % 2)        # the previous step's slot
                 step_eager(s, i % 2)
-                if graph_allreduce:
+                if graph_allreduce and peer is None:
                     stream.wait_stream(comm_stream)
             graphs.append(g)
     torch.cuda.synchronize()
@@ -541,10 +571,13 @@ def run_cuda(args, rank, world, local_rank):
                        "launch": "%d kernels per step (k_grad a programmatic dependent of k_walk) replayed from a CUDA graph; "
                                  "eager_ms_per_step=%.4f" % (launches_per_step, eager_ms),
                        "walker": {"pairs_per_lane": walk_cfg[0], "warps": walk_cfg[1]},
-                       "collective": ("none on the data path; float64 loss-sum all-reduce (NCCL) of the previous step's sum on a side "
-                                      "branch of each step's CUDA graph" if graph_allreduce else
-                                      "none on the data path; float64 loss-sum all-reduce per step on a side stream")
-                       if world > 1 else "none"},
+                       "collective": ("none" if world == 1 or collective == "none" else
+                                      "none on the data path; float64 loss-sum exchange of the previous step's sum inside each step's CUDA graph: " +
+                                      ("ctcb_mailbox_exchange_with_next: one warp of the step's own gradient kernel stores the partial sums into "
+                                       "every rank's mailbox over NVLink peer memory and picks up the sums before (no collective kernel, no "
+                                       "rendezvous, no extra launch)"
+                                       if collective == "peer" else "NCCL all-reduce on a side branch") if graph_allreduce else
+                                      "none on the data path; float64 loss-sum all-reduce (%s) per step on a side stream" % collective)},
             "clocks": clocks,
             # headline end-to-end number: the C ABI's host entry (the drop-in boundary itself, HOST buffers in,
             # loss back on the host); the same step through the Python plugin + torch autograd is reported beside it
@@ -616,6 +649,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--pipe-depth", type=int, default=2, help="batches in flight in the prefetching host entry (e2e)")
     ap.add_argument("--no-others", action="store_true", help="skip the context measurements of the other configs")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="N>1: loss-sum exchange through the library's peer mailbox (default) or torch.distributed's NCCL all-reduce")
     ap.add_argument("--no-allreduce", action="store_true", help="experiment: no loss-sum collective at all (N>1)")
     ap.add_argument("--no-graph-allreduce", action="store_true",
                     help="N>1: issue the loss-sum all-reduce from the host every step instead of from the captured graph")

@@ -24,6 +24,8 @@ EXPORTS = (
     "ctcb_last_launch_count", "ctcb_last_walk_config", "ctcb_loss_grad_dlpack", "ctcb_loss_grad_timed",
     "ctcb_scale_rows", "ctcb_edit_distance", "ctcb_loss_grad_host_resident",
     "ctcb_pipe_create", "ctcb_pipe_submit", "ctcb_pipe_wait", "ctcb_pipe_destroy",
+    "ctcb_mailbox_create", "ctcb_mailbox_handle", "ctcb_mailbox_connect", "ctcb_mailbox_exchange",
+    "ctcb_mailbox_flush", "ctcb_mailbox_destroy", "ctcb_mailbox_exchange_with_next",
 )
 
 
@@ -77,6 +79,13 @@ def load():
     lib.ctcb_pipe_submit.argtypes = [vp, PP, ctypes.POINTER(i64)]
     lib.ctcb_pipe_wait.argtypes = [vp, i64, ctypes.POINTER(vp)]
     lib.ctcb_pipe_destroy.argtypes = [vp]
+    lib.ctcb_mailbox_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
+    lib.ctcb_mailbox_handle.argtypes = [vp, vp]
+    lib.ctcb_mailbox_connect.argtypes = [vp, vp]
+    lib.ctcb_mailbox_exchange.argtypes = [vp, vp, i32, vp, vp]
+    lib.ctcb_mailbox_flush.argtypes = [vp, i32, vp, vp]
+    lib.ctcb_mailbox_exchange_with_next.argtypes = [vp, vp, i32, vp]
+    lib.ctcb_mailbox_destroy.argtypes = [vp]
     lib.ctcb_greedy_decode.argtypes = [vp, i64, i64, vp, i32, i32, i32, i32, i32, vp, vp, vp]
     lib.ctcb_scale_rows.argtypes = [vp, i64, i64, i32, i32, i32, vp, vp]
     lib.ctcb_edit_distance.argtypes = [vp, i64, vp, vp, i64, vp, i32, i32, i32, vp, vp, vp]

@@ -18,11 +18,27 @@
 #include "ctcb_dlpack.h"
 #include "ctcb_kernels.cuh"
 
+struct ctcb_mailbox {
+    int device = 0, rank = 0, world = 0;
+    double* local = nullptr;                       // [2][world][kMailRow] doubles + the counter, cudaMalloc'ed (IPC-exportable)
+    void* opened[ctcb::kMailMaxRanks] = {};        // peers' mailboxes mapped by cudaIpcOpenMemHandle
+    ctcb::MailboxDev dev{};
+    bool connected = false;
+};
+
 namespace {
 
 thread_local char g_err[512] = "";
 thread_local int g_launches = 0;
 thread_local int g_walk_p = 0, g_walk_nw = 0;
+struct PendingXchg { struct ctcb_mailbox* mb = nullptr; double* values = nullptr; double* out = nullptr; int count = 0; };
+thread_local PendingXchg g_xchg;                      // ctcb_mailbox_exchange_with_next: consumed by the next gradient launch
+bool take_pending_xchg(ctcb::MailXchg* x) {
+    if (!g_xchg.mb) return false;
+    x->m = g_xchg.mb->dev; x->values = g_xchg.values; x->out = g_xchg.out; x->count = g_xchg.count;
+    g_xchg = PendingXchg{};
+    return true;
+}
 thread_local cudaEvent_t* g_prof_events = nullptr;   // when set: one event recorded after every launch
 thread_local int g_prof_count = 0;
 
@@ -403,7 +419,8 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
         }
     }
     if (phases & PH_BACKWARD) {
-        ctcb::GradArgs ga{dp, w};
+        ctcb::GradArgs ga{dp, w, {}};
+        take_pending_xchg(&ga.x);
         const int gpairs = p->Lmax + 1;
         const int gch = gpairs <= 32 ? 1 : gpairs <= 64 ? 2 : gpairs <= 128 ? 4 : gpairs <= 256 ? 8 : gpairs <= 512 ? 16 : 0;
         size_t gsm = ctcb::grad_smem_bytes(lay.Lp, 32 * gch);
@@ -877,6 +894,107 @@ int ctcb_loss_sum_allreduce(void* nccl_comm, double* dev_values, int32_t count, 
     const int ncclFloat64 = 8, ncclSum = 0;
     const int rc = fn(dev_values, dev_values, (size_t)count, ncclFloat64, ncclSum, nccl_comm, static_cast<cudaStream_t>(stream));
     if (rc != 0) return fail(CTCB_EXECUTION_FAILED, "ncclAllReduce returned %d", rc);
+    return CTCB_OK;
+}
+
+// ---- loss-sum exchange over NVLink peer memory ----------------------------------------------
+int ctcb_mailbox_create(int device, int rank, int world, ctcb_mailbox_t** out) {
+    if (!out) return fail(CTCB_INVALID_VALUE, "out is NULL");
+    *out = nullptr;
+    if (world < 1 || world > ctcb::kMailMaxRanks || rank < 0 || rank >= world)
+        return fail(CTCB_INVALID_VALUE, "rank %d / world %d outside [0,%d]", rank, world, ctcb::kMailMaxRanks);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return fail(CTCB_UNSUPPORTED, "CUDA device %d not available (there is no CPU path)", device);
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    ctcb_mailbox* m = new (std::nothrow) ctcb_mailbox();
+    if (!m) return fail(CTCB_MEMOPS_FAILED, "out of host memory");
+    m->device = device; m->rank = rank; m->world = world;
+    const size_t bytes = sizeof(double) * (2 * (size_t)world * ctcb::kMailRow + 8);
+    if (cudaMalloc(reinterpret_cast<void**>(&m->local), bytes) != cudaSuccess || cudaMemset(m->local, 0, bytes) != cudaSuccess ||
+        cudaDeviceSynchronize() != cudaSuccess) {
+        cudaGetLastError();
+        if (m->local) cudaFree(m->local);
+        delete m;
+        return fail(CTCB_MEMOPS_FAILED, "mailbox allocation failed");
+    }
+    m->dev.rank = rank; m->dev.world = world;
+    m->dev.counter = reinterpret_cast<unsigned long long*>(m->local + 2 * (size_t)world * ctcb::kMailRow);
+    m->dev.peer[rank] = m->local;
+    m->connected = world == 1;
+    *out = m;
+    return CTCB_OK;
+}
+
+int ctcb_mailbox_handle(ctcb_mailbox_t* m, void* handle64) {
+    if (!m || !handle64) return fail(CTCB_INVALID_VALUE, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    CUDA_TRY(cudaSetDevice(m->device));
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, m->local));
+    memcpy(handle64, &h, 64);
+    return CTCB_OK;
+}
+
+int ctcb_mailbox_connect(ctcb_mailbox_t* m, const void* handles) {
+    if (!m || !handles) return fail(CTCB_INVALID_VALUE, "NULL argument");
+    CUDA_TRY(cudaSetDevice(m->device));
+    for (int r = 0; r < m->world; ++r) {
+        if (r == m->rank || m->opened[r]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char*>(handles) + 64 * (size_t)r, 64);
+        void* ptr = nullptr;
+        const cudaError_t rc = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (rc != cudaSuccess) {
+            cudaGetLastError();
+            return fail(CTCB_UNSUPPORTED, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(rc));
+        }
+        m->opened[r] = ptr;
+        m->dev.peer[r] = static_cast<double*>(ptr);
+    }
+    m->connected = true;
+    return CTCB_OK;
+}
+
+static int mailbox_launch(ctcb_mailbox_t* m, double* dev_values, int32_t count, double* dev_out, void* stream, int flush) {
+    if (!m || !dev_out || (!flush && !dev_values)) return fail(CTCB_INVALID_VALUE, "NULL argument");
+    if (count < 1 || count > ctcb::kMailMaxCount) return fail(CTCB_INVALID_VALUE, "count %d outside [1,%d]", count, ctcb::kMailMaxCount);
+    if (!m->connected) return fail(CTCB_INVALID_VALUE, "mailbox is not connected to its peers");
+    if (!is_device_ptr(dev_values) || !is_device_ptr(dev_out)) return fail(CTCB_INVALID_VALUE, "buffers must be CUDA device memory");
+    ctcb::k_mailbox_exchange<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(m->dev, dev_values, count, dev_out, flush);
+    CUDA_TRY(cudaGetLastError());
+    g_launches = 1;
+    return CTCB_OK;
+}
+
+int ctcb_mailbox_exchange(ctcb_mailbox_t* m, double* dev_values, int32_t count, double* dev_out, void* stream) {
+    return mailbox_launch(m, dev_values, count, dev_out, stream, 0);
+}
+
+int ctcb_mailbox_exchange_with_next(ctcb_mailbox_t* m, double* dev_values, int32_t count, double* dev_out) {
+    if (!m || !dev_out || !dev_values) return fail(CTCB_INVALID_VALUE, "NULL argument");
+    if (count < 1 || count > ctcb::kMailMaxCount) return fail(CTCB_INVALID_VALUE, "count %d outside [1,%d]", count, ctcb::kMailMaxCount);
+    if (!m->connected) return fail(CTCB_INVALID_VALUE, "mailbox is not connected to its peers");
+    if (!is_device_ptr(dev_values) || !is_device_ptr(dev_out)) return fail(CTCB_INVALID_VALUE, "buffers must be CUDA device memory");
+    if (g_xchg.mb) return fail(CTCB_INVALID_VALUE, "an exchange is already waiting for the next gradient launch on this thread");
+    g_xchg.mb = m; g_xchg.values = dev_values; g_xchg.out = dev_out; g_xchg.count = count;
+    return CTCB_OK;
+}
+
+int ctcb_mailbox_flush(ctcb_mailbox_t* m, int32_t count, double* dev_out, void* stream) {
+    return mailbox_launch(m, nullptr, count, dev_out, stream, 1);
+}
+
+int ctcb_mailbox_destroy(ctcb_mailbox_t* m) {
+    if (!m) return CTCB_OK;
+    cudaSetDevice(m->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < m->world; ++r) if (m->opened[r]) cudaIpcCloseMemHandle(m->opened[r]);
+    if (m->local) cudaFree(m->local);
+    cudaGetLastError();
+    delete m;
     return CTCB_OK;
 }
 

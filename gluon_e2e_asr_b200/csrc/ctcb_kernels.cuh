@@ -1210,6 +1210,79 @@ __global__ void __launch_bounds__((NW + (FUSED ? kFusedProducers + 1 : 1)) * 32)
 }
 
 // ---------------------------------------------------------------------------------------
+// k_mailbox_exchange: the loss-sum exchange of section 8e over NVLink peer memory.  One warp.
+// Exchange k of a rank (k = its device-side counter): lane r stores this rank's partial sums
+// into rank r's mailbox (slot k & 1, row = this rank) with a release at system scope; lane r then
+// takes rank r's row of exchange k-1 from the LOCAL mailbox (acquire; the peers stored it one
+// exchange ago, so the wait is normally over before it starts) and lane 0 adds the rows in rank
+// order -- every rank forms the same sum with the same bits.  No NCCL kernel, no rendezvous on the
+// step's path: one step of slack between the ranks.  A peer that never shows up ends the wait
+// after ~2 s with NaN instead of hanging the GPU.
+// ---------------------------------------------------------------------------------------
+constexpr int kMailMaxRanks = 16, kMailMaxCount = 6, kMailRow = 8;      // row: 6 values, pad, sequence number
+struct MailboxDev {
+    double* peer[kMailMaxRanks];        // rank r's mailbox as mapped into this process ([2][world][kMailRow] doubles)
+    unsigned long long* counter;        // exchanges done by this rank
+    int rank, world;
+};
+
+// what one warp does; also run by a warp of k_grad's first CTA when the exchange rides on a step (MailXchg)
+__device__ __forceinline__ void mailbox_exchange_warp(const MailboxDev& m, double* values, int count, double* out, int flush, int lane) {
+    const unsigned long long k = *m.counter;          // exchanges completed so far = index of this one
+    __shared__ double rows[kMailMaxRanks][kMailMaxCount];
+    __shared__ int timed_out;
+    // a wait that timed out once poisons the mailbox: later exchanges report NaN at once instead of waiting again
+    if (lane == 0) timed_out = m.counter[1] != 0ull;
+    __syncwarp();
+    // 1. gather exchange k-1 from the local mailbox.  Gather BEFORE publish: a peer can then be at most one
+    //    exchange ahead when it stores, i.e. it stores into the other slot -- two slots suffice.
+    if (k > 0 && lane < m.world) {
+        const unsigned long long kk = k - 1;
+        const double* src = m.peer[m.rank] + ((size_t)(kk & 1) * m.world + lane) * kMailRow;
+        const unsigned long long* seq = reinterpret_cast<const unsigned long long*>(src + kMailRow - 1);
+        const long long t0 = clock64();
+        for (; !timed_out;) {
+            unsigned long long got;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(seq) : "memory");
+            if (got >= kk + 1) break;
+            if (clock64() - t0 > 4000000000LL) { timed_out = 1; break; }
+            __nanosleep(200);
+        }
+        for (int c = 0; c < count; ++c) {
+            double v; asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(src + c) : "memory");
+            rows[lane][c] = v;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        for (int c = 0; c < count; ++c) {
+            double s = 0.0;
+            if (k > 0) for (int r = 0; r < m.world; ++r) s += rows[r][c];           // rank order: same bits on every rank
+            out[c] = timed_out ? __longlong_as_double(0x7ff8000000000000LL) : s;
+        }
+        if (timed_out) m.counter[1] = 1ull;
+    }
+    if (flush) return;                                 // flush: read the last exchange only
+    // 2. publish this rank's partial sums of exchange k into every rank's mailbox (its own included)
+    if (lane < m.world) {
+        double* dst = m.peer[lane] + ((size_t)(k & 1) * m.world + m.rank) * kMailRow;
+        for (int c = 0; c < count; ++c) asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst + c), "d"(values[c]) : "memory");
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(reinterpret_cast<unsigned long long*>(dst + kMailRow - 1)), "l"(k + 1) : "memory");
+    }
+    __syncwarp();
+    if (lane == 0) {
+        for (int c = 0; c < count; ++c) values[c] = 0.0;
+        *m.counter = k + 1;
+    }
+}
+
+__global__ void __launch_bounds__(32) k_mailbox_exchange(MailboxDev m, double* values, int count, double* out, int flush) {
+    mailbox_exchange_warp(m, values, count, out, flush, threadIdx.x);
+}
+
+struct MailXchg { MailboxDev m; double* values; double* out; int count; };   // count == 0: none
+
+// ---------------------------------------------------------------------------------------
 // k_grad<VEC,CH,XQ>: grid (NB, B), block 128: one frame block (kG = 8 frames) per CTA, two
 // frames per warp.  Rows a7 (accumulation, gradient) and a8 (head-gradient scaling), written
 // once in the caller's layout.
@@ -1223,7 +1296,7 @@ __global__ void __launch_bounds__((NW + (FUSED ? kFusedProducers + 1 : 1)) * 32)
 // nothing large is ever subtracted.  The offsets of alpha and beta' are combined once per
 // warp (they are constant over the frame block).
 // ---------------------------------------------------------------------------------------
-struct GradArgs { Problem p; Workspace w; };
+struct GradArgs { Problem p; Workspace w; MailXchg x; };
 
 template <int VEC>
 __device__ __forceinline__ void zero_row(float* row, int V, int lane) {
@@ -1274,6 +1347,10 @@ __global__ void __launch_bounds__(XQ < 0 ? 256 : 128, XQ < 0 ? (CH == 16 ? 2 : 3
     constexpr int F = (CH > 0 && CH <= 4) ? FPW : 1;      // frames in flight per warp
     const Problem& p = a.p; const Workspace& w = a.w;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // the loss-sum exchange of the PREVIOUS step rides on this grid: one warp of the first CTA -- a CTA that
+    // waits for the walkers anyway -- stores the partial sums to the peers and picks up the sums before
+    if (a.x.count > 0 && blockIdx.x == 0 && blockIdx.y == 0 && warp == 3)
+        mailbox_exchange_warp(a.x.m, a.x.values, a.x.count, a.x.out, 0, lane);
     // the utterance's metadata is written by k_emit (complete before this grid exists) or, in the
     // fused path, by the concurrently running alpha walker CTA
     if (tid == 0) { while (ld_acquire_gpu(w.gprog + 4 * b + 2) == 0) __nanosleep(256); }

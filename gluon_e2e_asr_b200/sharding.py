@@ -13,7 +13,7 @@ from __future__ import annotations
 import torch
 
 __all__ = ["split_slices", "split_and_load", "balanced_assignment", "shard_for_rank",
-           "loss_sum_allreduce"]
+           "loss_sum_allreduce", "PeerLossSum"]
 
 
 def split_slices(n, k):
@@ -60,3 +60,79 @@ def loss_sum_allreduce(values, group=None, async_op=False):
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return None
     return dist.all_reduce(values, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
+class PeerLossSum:
+    """The loss-sum exchange without a collective kernel on the step's path (``ctcb_mailbox_*``).
+
+    One process per GPU (``torch.distributed`` initialised): every rank owns a small mailbox in
+    device memory that its peers map through CUDA IPC; ``exchange(values, out)`` enqueues one tiny
+    kernel on the current stream that (1) writes into ``out`` the all-rank sum of the values handed
+    to the *previous* exchange and (2) stores ``values`` into every rank's mailbox over NVLink peer
+    access and zeroes them.  Ranks never rendezvous: a rank only waits for what its peers stored one
+    exchange earlier, so a slow rank costs the others nothing until it is a whole step behind.
+    ``flush(out)`` returns the sum of the last exchange.  Replaces the reference's host-side ``+=`` of
+    two ``.asscalar()`` values per shard and step (train_ctc_ce.py:367-368).  CUDA only.
+    """
+
+    def __init__(self, device, group=None):
+        import ctypes
+        import torch.distributed as dist
+        from . import _lib
+        self._lib, self._ct = _lib, ctypes
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("PeerLossSum has no CPU path: a CUDA device is required")
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        lib = _lib.load()
+        self._h = ctypes.c_void_p()
+        _lib.check(lib.ctcb_mailbox_create(self.device.index or 0, self.rank, self.world, ctypes.byref(self._h)))
+        if self.world > 1:
+            mine = (ctypes.c_ubyte * 64)()
+            _lib.check(lib.ctcb_mailbox_handle(self._h, mine))
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(mine), group=group)
+            buf = (ctypes.c_ubyte * (64 * self.world)).from_buffer_copy(b"".join(handles))
+            rc = lib.ctcb_mailbox_connect(self._h, buf)
+            err = lib.ctcb_last_error().decode("utf-8", "replace") if rc else ""
+            # every rank learns whether every rank connected: a one-sided failure must not leave the others waiting
+            oks = [None] * self.world
+            dist.all_gather_object(oks, rc == 0, group=group)
+            if not all(oks):
+                self.close()
+                raise RuntimeError("PeerLossSum: peer mapping failed on rank(s) %s %s" %
+                                   ([r for r, ok in enumerate(oks) if not ok], err))
+
+    def exchange(self, values, out):
+        """values, out: float64 CUDA tensors of the same length (<= 6), contiguous."""
+        self._check(values); self._check(out)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._lib.check(self._lib.load().ctcb_mailbox_exchange(self._h, values.data_ptr(), values.numel(), out.data_ptr(), stream))
+
+    def exchange_with_next(self, values, out):
+        """The same exchange without a launch of its own: it rides on the next ``ctc_loss_and_grad`` /
+        backward call of this thread (``ctcb_mailbox_exchange_with_next``).  ``values`` must be the
+        PREVIOUS step's partial sums, not the tensor that call accumulates into."""
+        self._check(values); self._check(out)
+        self._lib.check(self._lib.load().ctcb_mailbox_exchange_with_next(self._h, values.data_ptr(), values.numel(), out.data_ptr()))
+
+    def flush(self, out):
+        self._check(out)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._lib.check(self._lib.load().ctcb_mailbox_flush(self._h, out.numel(), out.data_ptr(), stream))
+
+    def _check(self, t):
+        if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and 1 <= t.numel() <= 6):
+            raise ValueError("expected a contiguous float64 CUDA tensor of 1..6 elements")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.load().ctcb_mailbox_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass

