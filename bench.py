@@ -274,7 +274,7 @@ def run_cuda(args, rank, world, local_rank):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=stream):
                 if graph_allreduce and peer is not None:
-                    # the previous step's slot rides on this step's gradient kernel: no extra launch, no side branch
+                    # the previous step's slot: a one-warp kernel ahead of the step, the step's first kernel its programmatic dependent
                     peer.exchange_with_next(part[(i + 1) % 2], red_buf[(i + 1) % 2])
                 elif graph_allreduce:
                     comm_stream.wait_stream(stream)
@@ -573,9 +573,9 @@ def run_cuda(args, rank, world, local_rank):
                        "walker": {"pairs_per_lane": walk_cfg[0], "warps": walk_cfg[1]},
                        "collective": ("none" if world == 1 or collective == "none" else
                                       "none on the data path; float64 loss-sum exchange of the previous step's sum inside each step's CUDA graph: " +
-                                      ("ctcb_mailbox_exchange_with_next: one warp of the step's own gradient kernel stores the partial sums into "
-                                       "every rank's mailbox over NVLink peer memory and picks up the sums before (no collective kernel, no "
-                                       "rendezvous, no extra launch)"
+                                      ("ctcb_mailbox_exchange_with_next: a one-warp kernel stores the partial sums into every rank's mailbox over "
+                                       "NVLink peer memory and picks up the sums before (no collective kernel, no rendezvous); the step's "
+                                       "recursion kernel is its programmatic dependent and starts at once"
                                        if collective == "peer" else "NCCL all-reduce on a side branch") if graph_allreduce else
                                       "none on the data path; float64 loss-sum all-reduce (%s) per step on a side stream" % collective)},
             "clocks": clocks,
@@ -585,7 +585,7 @@ def run_cuda(args, rank, world, local_rank):
                     e2e_cabi if e2e_cabi and "value" in e2e_cabi else e2e_plugin),
             "e2e_sync": e2e_cabi,
             "e2e_plugin": e2e_plugin,
-            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches": (launches_per_step + (1 if (peer is not None and graph_allreduce) else 0)) * args.steps,
             "roofline": roofline,
         }
         if cpu_baseline:

@@ -22,7 +22,8 @@ struct ctcb_mailbox {
     int device = 0, rank = 0, world = 0;
     double* local = nullptr;                       // [2][world][kMailRow] doubles + the counter, cudaMalloc'ed (IPC-exportable)
     void* opened[ctcb::kMailMaxRanks] = {};        // peers' mailboxes mapped by cudaIpcOpenMemHandle
-    ctcb::MailboxDev dev{};
+    ctcb::MailboxDev dev{};                        // host copy of the descriptor ...
+    ctcb::MailboxDev* dev_d = nullptr;             // ... and where the kernels read it (inside `local`)
     bool connected = false;
 };
 
@@ -33,9 +34,10 @@ thread_local int g_launches = 0;
 thread_local int g_walk_p = 0, g_walk_nw = 0;
 struct PendingXchg { struct ctcb_mailbox* mb = nullptr; double* values = nullptr; double* out = nullptr; int count = 0; };
 thread_local PendingXchg g_xchg;                      // ctcb_mailbox_exchange_with_next: consumed by the next gradient launch
-bool take_pending_xchg(ctcb::MailXchg* x) {
+// enqueues the pending exchange (if any) on `stream`; true when a kernel was launched
+bool launch_pending_xchg(cudaStream_t stream) {
     if (!g_xchg.mb) return false;
-    x->m = g_xchg.mb->dev; x->values = g_xchg.values; x->out = g_xchg.out; x->count = g_xchg.count;
+    ctcb::k_mailbox_exchange<<<1, 32, 0, stream>>>(g_xchg.mb->dev_d, g_xchg.values, g_xchg.count, g_xchg.out, 0);
     g_xchg = PendingXchg{};
     return true;
 }
@@ -399,10 +401,20 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
             mark(stream);
             return CTCB_OK;
         };
-        auto launch_walk = [&]() -> int {
+        // ctcb_mailbox_exchange_with_next: the exchange kernel goes first and the step's first kernel is its
+        // programmatic dependent -- it starts while the exchange's one warp talks to the peers
+        const bool xchg = launch_pending_xchg(stream);
+        if (xchg) mark(stream);
+        auto launch_walk = [&](bool after_xchg) -> int {
             ctcb::WalkArgs wa{dp, w, p->T, stages, p->blank, p->loss, p->loss_sum, nullptr};
             const int wthreads = (we->NW + (lay.fused ? ctcb::kFusedProducers + 1 : 1)) * 32;
-            wfn<<<dim3(p->B, need_grad ? 2 : 1), wthreads, smem, stream>>>(wa);
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(p->B, need_grad ? 2 : 1); cfg.blockDim = dim3(wthreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr; cfg.numAttrs = after_xchg ? 1 : 0;
+            CUDA_TRY(cudaLaunchKernelEx(&cfg, wfn, wa));
             mark(stream);
             return CTCB_OK;
         };
@@ -411,16 +423,16 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
             const void* efn = reinterpret_cast<const void*>(ctcb::k_emit<4, -1>);
             CUDA_TRY(ensure_loaded(efn));
             CUDA_TRY(ensure_dynamic_smem(efn, ctcb::emit_smem_bytes(lay.Lp, p->V)));
-            if (int rc = launch_walk()) return rc;
+            if (int rc = launch_walk(false)) return rc;
             if (int rc = launch_emit()) return rc;
         } else {
             if (!lay.fused) { if (int rc = launch_emit()) return rc; }
-            if (int rc = launch_walk()) return rc;
+            if (int rc = launch_walk(xchg && lay.fused != 0)) return rc;
         }
     }
     if (phases & PH_BACKWARD) {
-        ctcb::GradArgs ga{dp, w, {}};
-        take_pending_xchg(&ga.x);
+        ctcb::GradArgs ga{dp, w};
+        if (!(phases & PH_FORWARD) && launch_pending_xchg(stream)) mark(stream);     // backward-only call: a launch of its own
         const int gpairs = p->Lmax + 1;
         const int gch = gpairs <= 32 ? 1 : gpairs <= 64 ? 2 : gpairs <= 128 ? 4 : gpairs <= 256 ? 8 : gpairs <= 512 ? 16 : 0;
         size_t gsm = ctcb::grad_smem_bytes(lay.Lp, 32 * gch);
@@ -912,7 +924,7 @@ int ctcb_mailbox_create(int device, int rank, int world, ctcb_mailbox_t** out) {
     ctcb_mailbox* m = new (std::nothrow) ctcb_mailbox();
     if (!m) return fail(CTCB_MEMOPS_FAILED, "out of host memory");
     m->device = device; m->rank = rank; m->world = world;
-    const size_t bytes = sizeof(double) * (2 * (size_t)world * ctcb::kMailRow + 8);
+    const size_t bytes = sizeof(double) * (2 * (size_t)world * ctcb::kMailRow + 8) + sizeof(ctcb::MailboxDev);
     if (cudaMalloc(reinterpret_cast<void**>(&m->local), bytes) != cudaSuccess || cudaMemset(m->local, 0, bytes) != cudaSuccess ||
         cudaDeviceSynchronize() != cudaSuccess) {
         cudaGetLastError();
@@ -923,7 +935,12 @@ int ctcb_mailbox_create(int device, int rank, int world, ctcb_mailbox_t** out) {
     m->dev.rank = rank; m->dev.world = world;
     m->dev.counter = reinterpret_cast<unsigned long long*>(m->local + 2 * (size_t)world * ctcb::kMailRow);
     m->dev.peer[rank] = m->local;
+    m->dev_d = reinterpret_cast<ctcb::MailboxDev*>(m->local + 2 * (size_t)world * ctcb::kMailRow + 8);
     m->connected = world == 1;
+    if (cudaMemcpy(m->dev_d, &m->dev, sizeof(m->dev), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaGetLastError(); cudaFree(m->local); delete m;
+        return fail(CTCB_MEMOPS_FAILED, "mailbox descriptor upload failed");
+    }
     *out = m;
     return CTCB_OK;
 }
@@ -954,6 +971,7 @@ int ctcb_mailbox_connect(ctcb_mailbox_t* m, const void* handles) {
         m->opened[r] = ptr;
         m->dev.peer[r] = static_cast<double*>(ptr);
     }
+    CUDA_TRY(cudaMemcpy(m->dev_d, &m->dev, sizeof(m->dev), cudaMemcpyHostToDevice));
     m->connected = true;
     return CTCB_OK;
 }
@@ -963,7 +981,7 @@ static int mailbox_launch(ctcb_mailbox_t* m, double* dev_values, int32_t count, 
     if (count < 1 || count > ctcb::kMailMaxCount) return fail(CTCB_INVALID_VALUE, "count %d outside [1,%d]", count, ctcb::kMailMaxCount);
     if (!m->connected) return fail(CTCB_INVALID_VALUE, "mailbox is not connected to its peers");
     if (!is_device_ptr(dev_values) || !is_device_ptr(dev_out)) return fail(CTCB_INVALID_VALUE, "buffers must be CUDA device memory");
-    ctcb::k_mailbox_exchange<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(m->dev, dev_values, count, dev_out, flush);
+    ctcb::k_mailbox_exchange<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(m->dev_d, dev_values, count, dev_out, flush);
     CUDA_TRY(cudaGetLastError());
     g_launches = 1;
     return CTCB_OK;

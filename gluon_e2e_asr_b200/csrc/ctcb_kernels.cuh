@@ -1226,8 +1226,9 @@ struct MailboxDev {
     int rank, world;
 };
 
-// what one warp does; also run by a warp of k_grad's first CTA when the exchange rides on a step (MailXchg)
-__device__ __forceinline__ void mailbox_exchange_warp(const MailboxDev& m, double* values, int count, double* out, int flush, int lane) {
+// what the kernel's one warp does
+__device__ __forceinline__ void mailbox_exchange_warp(const MailboxDev* md, double* values, int count, double* out, int flush, int lane) {
+    const MailboxDev& m = *md;
     const unsigned long long k = *m.counter;          // exchanges completed so far = index of this one
     __shared__ double rows[kMailMaxRanks][kMailMaxCount];
     __shared__ int timed_out;
@@ -1276,11 +1277,12 @@ __device__ __forceinline__ void mailbox_exchange_warp(const MailboxDev& m, doubl
     }
 }
 
-__global__ void __launch_bounds__(32) k_mailbox_exchange(MailboxDev m, double* values, int count, double* out, int flush) {
+__global__ void __launch_bounds__(32) k_mailbox_exchange(const MailboxDev* m, double* values, int count, double* out, int flush) {
+    // riding on a step: the recursion kernel is launched right behind this one as a programmatic dependent and
+    // starts at once (it shares nothing with the exchange)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     mailbox_exchange_warp(m, values, count, out, flush, threadIdx.x);
 }
-
-struct MailXchg { MailboxDev m; double* values; double* out; int count; };   // count == 0: none
 
 // ---------------------------------------------------------------------------------------
 // k_grad<VEC,CH,XQ>: grid (NB, B), block 128: one frame block (kG = 8 frames) per CTA, two
@@ -1296,7 +1298,7 @@ struct MailXchg { MailboxDev m; double* values; double* out; int count; };   // 
 // nothing large is ever subtracted.  The offsets of alpha and beta' are combined once per
 // warp (they are constant over the frame block).
 // ---------------------------------------------------------------------------------------
-struct GradArgs { Problem p; Workspace w; MailXchg x; };
+struct GradArgs { Problem p; Workspace w; };
 
 template <int VEC>
 __device__ __forceinline__ void zero_row(float* row, int V, int lane) {
@@ -1347,10 +1349,6 @@ __global__ void __launch_bounds__(XQ < 0 ? 256 : 128, XQ < 0 ? (CH == 16 ? 2 : 3
     constexpr int F = (CH > 0 && CH <= 4) ? FPW : 1;      // frames in flight per warp
     const Problem& p = a.p; const Workspace& w = a.w;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // the loss-sum exchange of the PREVIOUS step rides on this grid: one warp of the first CTA -- a CTA that
-    // waits for the walkers anyway -- stores the partial sums to the peers and picks up the sums before
-    if (a.x.count > 0 && blockIdx.x == 0 && blockIdx.y == 0 && warp == 3)
-        mailbox_exchange_warp(a.x.m, a.x.values, a.x.count, a.x.out, 0, lane);
     // the utterance's metadata is written by k_emit (complete before this grid exists) or, in the
     // fused path, by the concurrently running alpha walker CTA
     if (tid == 0) { while (ld_acquire_gpu(w.gprog + 4 * b + 2) == 0) __nanosleep(256); }

@@ -194,11 +194,12 @@ int ctcb_loss_sum_allreduce(void* nccl_comm, double* dev_values, int32_t count, 
  *                          the rows in rank order: identical bits everywhere.  Ranks need not meet:
  *                          a rank only waits for what its peers stored one exchange earlier.  All
  *                          ranks must issue the same number of exchanges.
- *   ctcb_mailbox_exchange_with_next   the same exchange WITHOUT a launch of its own: it rides on the
- *                          next ctcb_loss_grad / ctcb_backward this thread enqueues (one warp of the
- *                          gradient kernel's first CTA, a CTA that waits for the recursion anyway),
- *                          so a step stays two kernels.  dev_values must not be the loss_sum that
- *                          step accumulates into: hand over the PREVIOUS step's partial sums (two
+ *   ctcb_mailbox_exchange_with_next   the same exchange as part of the next ctcb_loss_grad /
+ *                          ctcb_forward / ctcb_backward this thread enqueues: the exchange kernel goes
+ *                          first on that call's stream and the step's recursion kernel is launched as
+ *                          its programmatic dependent, so the step starts at once and the exchange
+ *                          costs it nothing.  dev_values must not be the loss_sum that step
+ *                          accumulates into: hand over the PREVIOUS step's partial sums (two
  *                          alternating slots).  Counts as one exchange.
  *   ctcb_mailbox_flush     dev_out = the all-rank sum of the LAST exchange's values (end of an epoch)
  * Replaces the host-side `+=` of `.asscalar()` values (train_ctc_ce.py:367-368) like
