@@ -17,6 +17,13 @@ WANT = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__regis
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "smsp__inst_executed.sum", "sm__inst_executed_pipe_xu.sum", "sm__inst_executed_pipe_fp64.sum",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
         "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio",
         "smsp__average_warp_latency_issue_stalled_short_scoreboard.ratio",
         "smsp__average_warp_latency_issue_stalled_barrier.ratio", "smsp__average_warp_latency_issue_stalled_wait.ratio",
@@ -25,8 +32,10 @@ WANT = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__regis
         "smsp__average_warp_latency_issue_stalled_no_instruction.ratio",
         "smsp__average_warp_latency_issue_stalled_lg_throttle.ratio",
         "smsp__average_warp_latency_issue_stalled_membar.ratio"]
-if os.path.exists(rep):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rawcsv = args.get("--raw")          # `ncu -i rep --page raw --csv` exported on the GPU box (a .ncu-rep can exceed what travels back)
+if os.path.exists(rep) or (rawcsv and os.path.exists(rawcsv)):
+    raw = (open(rawcsv).read() if rawcsv and os.path.exists(rawcsv) else
+           subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout)
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     cols = [c for c in WANT if c in hdr]
