@@ -448,11 +448,17 @@ def run_cuda(args, rank, world, local_rank):
         npb = len(pprobs)
         tk = ctypes.c_int64(-1)
 
-        def pipe_run(k):
+        moved = {}                                      # bytes each host batch moves host -> device (asked from the library)
+        hb, pulled = ctypes.c_int64(0), ctypes.c_int32(0)
+
+        def pipe_run(k, record=False):
             """k batches through the pipe, `depth` in flight; returns the sum of all losses read on the host."""
             acc, pending = 0.0, []
             for i in range(k):
                 _lib.check(lib.ctcb_pipe_submit(ph, ctypes.byref(pprobs[i % npb]), ctypes.byref(tk)))
+                if record:
+                    _lib.check(lib.ctcb_pipe_last_h2d_bytes(ph, ctypes.byref(hb), ctypes.byref(pulled)))
+                    moved[i % npb] = (hb.value, pulled.value)
                 pending.append((tk.value, i % npb))
                 if len(pending) >= depth:
                     t_, j = pending.pop(0)
@@ -463,7 +469,7 @@ def run_cuda(args, rank, world, local_rank):
                 acc += float(loss_np[j].sum())
             return acc
 
-        pipe_run(max(2 * depth, 6))
+        pipe_run(max(2 * depth, npb), record=True)
         # same bits as the synchronous host entry
         _lib.check(lib.ctcb_loss_grad_host_resident(ctypes.byref(probs[0]), local_rank, ctypes.byref(dgrad)))
         ref_loss = loss_host.clone()
@@ -482,11 +488,16 @@ def run_cuda(args, rank, world, local_rank):
             b = tp_.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
             pipe_ms, pipe_frames = a[0].item(), b[1].item()
         e2e_pipe = {"value": pipe_frames / (pipe_ms * 1e-3), "unit": UNIT, "ms_per_step": pipe_ms / pipe_steps,
-                    "h2d_bytes_per_step": hsets[0].h2d_bytes, "d2h_bytes_per_step": d2h, "steps": pipe_steps,
+                    "h2d_bytes_per_step": sum(moved[i % npb][0] for i in range(pipe_steps)) / pipe_steps,
+                    "d2h_bytes_per_step": d2h, "steps": pipe_steps,
                     "in_flight": depth, "loss_checksum": acc,
-                    "api": "ctcb_pipe_submit / ctcb_pipe_wait (pinned HOST batches, one arena copy each): every step's "
+                    "h2d": ("the GPU pulls the VALID frames of the pinned logits itself (k_pull_valid, zero-copy loads over PCIe: "
+                            "padded frames never cross the bus); labels and lengths in one copy"
+                            if moved and all(v[1] for v in moved.values()) else "one cudaMemcpyAsync of the batch's pinned arena"),
+                    "h2d_bytes_per_step_dense": hsets[0].h2d_bytes,
+                    "api": "ctcb_pipe_submit / ctcb_pipe_wait (pinned HOST batches): every step's "
                            "inputs cross PCIe and its loss is read on the host inside the timed region; batch i+1's "
-                           "copy overlaps batch i's kernels (%d batches in flight); gradient left on the device; "
+                           "transfer overlaps batch i's kernels (%d batches in flight); gradient left on the device; "
                            "host wall clock around the loop including the drain" % depth}
         lib.ctcb_pipe_destroy(ph)
     except Exception as exc:  # noqa: BLE001

@@ -23,7 +23,7 @@ EXPORTS = (
     "ctcb_backward", "ctcb_loss_grad_host", "ctcb_greedy_decode", "ctcb_loss_sum_allreduce",
     "ctcb_last_launch_count", "ctcb_last_walk_config", "ctcb_loss_grad_dlpack", "ctcb_loss_grad_timed",
     "ctcb_scale_rows", "ctcb_edit_distance", "ctcb_loss_grad_host_resident",
-    "ctcb_pipe_create", "ctcb_pipe_submit", "ctcb_pipe_wait", "ctcb_pipe_destroy",
+    "ctcb_pipe_create", "ctcb_pipe_submit", "ctcb_pipe_wait", "ctcb_pipe_destroy", "ctcb_pipe_last_h2d_bytes",
     "ctcb_mailbox_create", "ctcb_mailbox_handle", "ctcb_mailbox_connect", "ctcb_mailbox_exchange",
     "ctcb_mailbox_flush", "ctcb_mailbox_destroy", "ctcb_mailbox_exchange_with_next",
 )
@@ -79,6 +79,7 @@ def load():
     lib.ctcb_pipe_submit.argtypes = [vp, PP, ctypes.POINTER(i64)]
     lib.ctcb_pipe_wait.argtypes = [vp, i64, ctypes.POINTER(vp)]
     lib.ctcb_pipe_destroy.argtypes = [vp]
+    lib.ctcb_pipe_last_h2d_bytes.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i32)]
     lib.ctcb_mailbox_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
     lib.ctcb_mailbox_handle.argtypes = [vp, vp]
     lib.ctcb_mailbox_connect.argtypes = [vp, vp]

@@ -1618,6 +1618,38 @@ __global__ void __launch_bounds__(XQ < 0 ? 256 : 128, XQ < 0 ? (CH == 16 ? 2 : 3
 }
 
 // ---------------------------------------------------------------------------------------
+// k_pull_valid: the host->device step of the prefetching host entry for utterance-major (NTC) logits in
+// page-locked host memory.  The GPU reads the host buffer itself (zero-copy loads over PCIe) and takes only
+// the VALID frames of every utterance -- rows t < T_b, one contiguous run per utterance -- so the padded
+// frames of a length-bucketed batch (a fifth of cfg2's bytes) never cross the bus.  grid (chunks, B), 256
+// threads, 16-byte loads, four in flight per thread; lengths come from the device copy made just before.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pull_valid(const float* __restrict__ src, float* __restrict__ dst, const void* data_len,
+                                                    int data_len_dtype, int T, int V, long long st_b) {
+    const int b = blockIdx.y;
+    long long t64 = load_as_int(data_len, data_len_dtype, b);
+    t64 = t64 < 0 ? 0 : (t64 > T ? T : t64);
+    const long long n = t64 * V;                                     // valid floats of this utterance
+    const float* s = src + (long long)b * st_b;
+    float* d = dst + (long long)b * st_b;
+    const long long stride = (long long)gridDim.x * blockDim.x, i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
+        const long long n4 = n >> 2;
+        const float4* s4 = reinterpret_cast<const float4*>(s);
+        float4* d4 = reinterpret_cast<float4*>(d);
+        long long i = i0;
+        for (; i + 3 * stride < n4; i += 4 * stride) {
+            const float4 a0 = s4[i], a1 = s4[i + stride], a2 = s4[i + 2 * stride], a3 = s4[i + 3 * stride];
+            d4[i] = a0; d4[i + stride] = a1; d4[i + 2 * stride] = a2; d4[i + 3 * stride] = a3;
+        }
+        for (; i < n4; i += stride) d4[i] = s4[i];
+        for (long long j = (n4 << 2) + i0; j < n; j += stride) d[j] = s[j];
+    } else {
+        for (long long j = i0; j < n; j += stride) d[j] = s[j];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // k_scale_rows: grad[b,t,:] *= head[b] in place.  Row a8 (the operator's Backward: the
 // gradient stored by Forward times the head gradient) for callers that ran the fused
 // forward+gradient with head = 1.  grid (ceil(T*ceil(V/128)... ) flat over (b, t) rows.

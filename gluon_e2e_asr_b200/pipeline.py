@@ -90,6 +90,12 @@ class HostPipeline:
             return g.value
         return torch.as_tensor(_DevView(g.value, (q.B, q.T, q.V)), device=self.device)
 
+    def last_h2d_bytes(self):
+        """(bytes the last submit moved host->device, whether the logits were pulled by the GPU: valid frames only)."""
+        b, pulled = ctypes.c_int64(0), ctypes.c_int32(0)
+        _lib.check(self._lib.ctcb_pipe_last_h2d_bytes(self._h, ctypes.byref(b), ctypes.byref(pulled)))
+        return b.value, bool(pulled.value)
+
     def close(self):
         if self._h:
             self._lib.ctcb_pipe_destroy(self._h)

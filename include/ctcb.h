@@ -148,6 +148,12 @@ int ctcb_pipe_create(int device, int depth, ctcb_pipe_t** out);
 int ctcb_pipe_submit(ctcb_pipe_t* pipe, const ctcb_problem_t* host_problem, int64_t* ticket);
 int ctcb_pipe_wait(ctcb_pipe_t* pipe, int64_t ticket, float** dev_grad);
 int ctcb_pipe_destroy(ctcb_pipe_t* pipe);
+/* bytes the last ctcb_pipe_submit moved host -> device.  *pulled = 1 when the logits did not go through a
+ * copy: for utterance-major (NTC) logits in page-locked memory with explicit data_lengths the GPU reads
+ * the host buffer itself and takes only the valid frames (t < T_b) of every utterance, so the padded
+ * frames of a length-bucketed batch never cross PCIe.  Opt-in (CTCB_PIPE_PULL=1): on B200 the SMs' loads
+ * over PCIe reach about half the copy engine's rate, so moving a fifth fewer bytes this way is slower. */
+int ctcb_pipe_last_h2d_bytes(ctcb_pipe_t* pipe, int64_t* bytes, int32_t* pulled);
 
 /* The operator's Backward for a caller that ran ctcb_loss_grad with head_grad = NULL in its
  * Forward (what MXNet's operator does: Forward stores the gradient, Backward multiplies it by

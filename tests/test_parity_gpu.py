@@ -576,6 +576,32 @@ def test_prefetching_pipe_matches_device_calls(dev):
         if depth < len(shapes):
             assert l.ctcb_pipe_wait(pipe._h, 0, None) == _lib.CTCB_INVALID_VALUE      # slot long reused
         pipe.close()
+    # pinned utterance-major logits with explicit lengths, opt-in CTCB_PIPE_PULL=1: the GPU pulls the valid frames itself;
+    # padded frames (NaN on the host) never reach the device and nothing reads them; same bits as the plain copy
+    B, T, V, L = 8, 64, 46, 9
+    d = make_batch(B, T, V, L, seed=320)
+    d["pred_lengths"][:] = np.array([64, 40, 33, 64, 21, 50, 12, 64], np.float32)
+    d["label_lengths"][:] = np.minimum(d["label_lengths"], 5)
+    for b in range(B):
+        d["pred"][b, int(d["pred_lengths"][b]):] = np.nan
+    t = _to(dev, d)
+    want = ctc_loss_and_grad(t["pred"], t["label"], t["pred_lengths"], t["label_lengths"])
+    pb = PinnedBatch.from_arrays(d["pred"], d["label"], d["pred_lengths"], d["label_lengths"])
+    valid_bytes = int(d["pred_lengths"].sum()) * V * 4
+    for pull in (1, 0):
+        with _env(CTCB_PIPE_PULL=pull):
+            pipe = HostPipeline(0, depth=2)
+            lo = torch.full((B,), float("nan")).pin_memory()
+            g = pipe.wait(pipe.submit(pb, lo))
+            moved, pulled = pipe.last_h2d_bytes()
+            assert pulled == bool(pull)
+            if pull:
+                assert valid_bytes < moved < valid_bytes + 4096 and moved < pb.nbytes
+            else:
+                assert moved == pb.nbytes
+            assert torch.equal(lo, want[0].cpu()) and torch.equal(g, want[1])
+            assert not torch.isnan(g).any()
+            pipe.close()
     # separately allocated pageable arrays, head gradient, loss sum and status through the raw ABI
     B, T, V, L = 7, 44, 46, 10
     d = make_batch(B, T, V, L, seed=311)
