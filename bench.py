@@ -274,7 +274,7 @@ def run_cuda(args, rank, world, local_rank):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=stream):
                 if graph_allreduce and peer is not None:
-                    # the previous step's slot: a one-warp kernel ahead of the step, the step's first kernel its programmatic dependent
+                    # the previous step's slot: a one-warp kernel behind the step's gradient kernel, as its programmatic dependent
                     peer.exchange_with_next(part[(i + 1) % 2], red_buf[(i + 1) % 2])
                 elif graph_allreduce:
                     comm_stream.wait_stream(stream)
@@ -585,8 +585,8 @@ def run_cuda(args, rank, world, local_rank):
                        "collective": ("none" if world == 1 or collective == "none" else
                                       "none on the data path; float64 loss-sum exchange of the previous step's sum inside each step's CUDA graph: " +
                                       ("ctcb_mailbox_exchange_with_next: a one-warp kernel stores the partial sums into every rank's mailbox over "
-                                       "NVLink peer memory and picks up the sums before (no collective kernel, no rendezvous); the step's "
-                                       "recursion kernel is its programmatic dependent and starts at once"
+                                       "NVLink peer memory and picks up the sums before (no collective kernel, no rendezvous); it is the "
+                                       "programmatic dependent of the step's gradient kernel and runs beside that kernel's last wave"
                                        if collective == "peer" else "NCCL all-reduce on a side branch") if graph_allreduce else
                                       "none on the data path; float64 loss-sum all-reduce (%s) per step on a side stream" % collective)},
             "clocks": clocks,

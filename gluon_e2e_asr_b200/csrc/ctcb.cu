@@ -34,10 +34,18 @@ thread_local int g_launches = 0;
 thread_local int g_walk_p = 0, g_walk_nw = 0;
 struct PendingXchg { struct ctcb_mailbox* mb = nullptr; double* values = nullptr; double* out = nullptr; int count = 0; };
 thread_local PendingXchg g_xchg;                      // ctcb_mailbox_exchange_with_next: consumed by the next gradient launch
-// enqueues the pending exchange (if any) on `stream`; true when a kernel was launched
-bool launch_pending_xchg(cudaStream_t stream) {
+// enqueues the pending exchange (if any) on `stream`; true when a kernel was launched.  programmatic: as the
+// programmatic dependent of the kernel launched just before it (the step's gradient kernel).
+bool launch_pending_xchg(cudaStream_t stream, bool programmatic = false) {
     if (!g_xchg.mb) return false;
-    ctcb::k_mailbox_exchange<<<1, 32, 0, stream>>>(g_xchg.mb->dev_d, g_xchg.values, g_xchg.count, g_xchg.out, 0);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(1); cfg.blockDim = dim3(32); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = programmatic ? 1 : 0;
+    const ctcb::MailboxDev* md = g_xchg.mb->dev_d;
+    cudaLaunchKernelEx(&cfg, ctcb::k_mailbox_exchange, md, g_xchg.values, g_xchg.count, g_xchg.out, 0);
     g_xchg = PendingXchg{};
     return true;
 }
@@ -401,9 +409,10 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
             mark(stream);
             return CTCB_OK;
         };
-        // ctcb_mailbox_exchange_with_next: the exchange kernel goes first and the step's first kernel is its
-        // programmatic dependent -- it starts while the exchange's one warp talks to the peers
-        const bool xchg = launch_pending_xchg(stream);
+        // ctcb_mailbox_exchange_with_next on a forward-only call: the exchange kernel goes first and the recursion
+        // kernel is its programmatic dependent -- it starts while the exchange's one warp talks to the peers.
+        // (With a gradient kernel in the call the exchange goes behind that one instead, see below.)
+        const bool xchg = !(phases & PH_BACKWARD) && launch_pending_xchg(stream);
         if (xchg) mark(stream);
         auto launch_walk = [&](bool after_xchg) -> int {
             ctcb::WalkArgs wa{dp, w, p->T, stages, p->blank, p->loss, p->loss_sum, nullptr};
@@ -432,7 +441,6 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
     }
     if (phases & PH_BACKWARD) {
         ctcb::GradArgs ga{dp, w};
-        if (!(phases & PH_FORWARD) && launch_pending_xchg(stream)) mark(stream);     // backward-only call: a launch of its own
         const int gpairs = p->Lmax + 1;
         const int gch = gpairs <= 32 ? 1 : gpairs <= 64 ? 2 : gpairs <= 128 ? 4 : gpairs <= 256 ? 8 : gpairs <= 512 ? 16 : 0;
         size_t gsm = ctcb::grad_smem_bytes(lay.Lp, 32 * gch);
@@ -484,6 +492,8 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
         cfg.attrs = attr; cfg.numAttrs = overlap ? 1 : 0;
         CUDA_TRY(cudaLaunchKernelEx(&cfg, gfn, ga));
         mark(stream);
+        // ctcb_mailbox_exchange_with_next: behind the gradient kernel, as its programmatic dependent
+        if (launch_pending_xchg(stream, true)) mark(stream);
     }
     CUDA_TRY(cudaGetLastError());
     return CTCB_OK;

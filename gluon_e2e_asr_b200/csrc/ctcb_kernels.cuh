@@ -1278,10 +1278,13 @@ __device__ __forceinline__ void mailbox_exchange_warp(const MailboxDev* md, doub
 }
 
 __global__ void __launch_bounds__(32) k_mailbox_exchange(const MailboxDev* m, double* values, int count, double* out, int flush) {
-    // riding on a step: the recursion kernel is launched right behind this one as a programmatic dependent and
-    // starts at once (it shares nothing with the exchange)
+    // Riding on a step, either BEHIND its gradient kernel as that kernel's programmatic dependent (this grid starts when
+    // the gradient kernel's last wave of CTAs has started, works beside it -- it shares nothing with the step -- and stays
+    // open until the step is complete and flushed, so the stream's next kernel sees both), or AHEAD of a forward-only
+    // call, whose recursion kernel is then this grid's programmatic dependent and starts at once.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     mailbox_exchange_warp(m, values, count, out, flush, threadIdx.x);
+    if (threadIdx.x == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1349,6 +1352,8 @@ __global__ void __launch_bounds__(XQ < 0 ? 256 : 128, XQ < 0 ? (CH == 16 ? 2 : 3
     constexpr int F = (CH > 0 && CH <= 4) ? FPW : 1;      // frames in flight per warp
     const Problem& p = a.p; const Workspace& w = a.w;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // a loss-sum exchange launched behind this grid as its programmatic dependent may start once every CTA is here
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // the utterance's metadata is written by k_emit (complete before this grid exists) or, in the
     // fused path, by the concurrently running alpha walker CTA
     if (tid == 0) { while (ld_acquire_gpu(w.gprog + 4 * b + 2) == 0) __nanosleep(256); }

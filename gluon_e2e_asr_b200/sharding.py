@@ -112,10 +112,10 @@ class PeerLossSum:
 
     def exchange_with_next(self, values, out):
         """The same exchange as part of the next ``ctc_loss_and_grad`` / forward / backward call of this
-        thread (``ctcb_mailbox_exchange_with_next``): the exchange kernel goes first on that call's
-        stream and the step's recursion kernel is its programmatic dependent, so the step starts at
-        once.  ``values`` must be the PREVIOUS step's partial sums, not the tensor that call
-        accumulates into."""
+        thread (``ctcb_mailbox_exchange_with_next``): the exchange kernel is launched behind that
+        call's gradient kernel as its programmatic dependent and runs beside its last wave.
+        ``values`` must be the PREVIOUS step's partial sums, not the tensor that call accumulates
+        into."""
         self._check(values); self._check(out)
         self._lib.check(self._lib.load().ctcb_mailbox_exchange_with_next(self._h, values.data_ptr(), values.numel(), out.data_ptr()))
 

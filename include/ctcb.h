@@ -201,10 +201,11 @@ int ctcb_loss_sum_allreduce(void* nccl_comm, double* dev_values, int32_t count, 
  *                          a rank only waits for what its peers stored one exchange earlier.  All
  *                          ranks must issue the same number of exchanges.
  *   ctcb_mailbox_exchange_with_next   the same exchange as part of the next ctcb_loss_grad /
- *                          ctcb_forward / ctcb_backward this thread enqueues: the exchange kernel goes
- *                          first on that call's stream and the step's recursion kernel is launched as
- *                          its programmatic dependent, so the step starts at once and the exchange
- *                          costs it nothing.  dev_values must not be the loss_sum that step
+ *                          ctcb_forward / ctcb_backward this thread enqueues: the exchange kernel is
+ *                          launched behind that call's gradient kernel as its programmatic dependent
+ *                          and works beside the gradient kernel's last wave (ahead of the recursion
+ *                          kernel, which then starts at once, on a forward-only call), so it is off
+ *                          the step's path.  dev_values must not be the loss_sum that step
  *                          accumulates into: hand over the PREVIOUS step's partial sums (two
  *                          alternating slots).  Counts as one exchange.
  *   ctcb_mailbox_flush     dev_out = the all-rank sum of the LAST exchange's values (end of an epoch)
