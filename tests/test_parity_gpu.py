@@ -598,7 +598,7 @@ def test_prefetching_pipe_matches_device_calls(dev):
             if pull:
                 assert valid_bytes < moved < valid_bytes + 4096 and moved < pb.nbytes
             else:
-                assert moved == pb.nbytes
+                assert pb.nbytes - 256 < moved <= pb.nbytes          # one copy of the arena (its last field is not padded)
             assert torch.equal(lo, want[0].cpu()) and torch.equal(g, want[1])
             assert not torch.isnan(g).any()
             pipe.close()
