@@ -237,14 +237,14 @@ def run_cuda(args, rank, world, local_rank):
     collective = "none"
     if force_x:
         from gluon_e2e_asr_b200 import PeerLossSum
-        peer = PeerLossSum(dev)
+        peer = PeerLossSum(dev, lag=args.peer_lag)
         collective = "peer"
     if world > 1 and not args.no_allreduce:
         collective = "nccl"
         if args.collective == "peer":
             try:
                 from gluon_e2e_asr_b200 import PeerLossSum
-                peer = PeerLossSum(dev)
+                peer = PeerLossSum(dev, lag=args.peer_lag)
                 collective = "peer"
             except Exception as exc:  # noqa: BLE001
                 if rank == 0:
@@ -585,7 +585,7 @@ def run_cuda(args, rank, world, local_rank):
                        "collective": ("none" if world == 1 or collective == "none" else
                                       "none on the data path; float64 loss-sum exchange of the previous step's sum inside each step's CUDA graph: " +
                                       ("ctcb_mailbox_exchange_with_next: a one-warp kernel stores the partial sums into every rank's mailbox over "
-                                       "NVLink peer memory and picks up the sums before (no collective kernel, no rendezvous); it is the "
+                                       "NVLink peer memory and picks up the sums of %d steps before (no collective kernel, no rendezvous); it is the " % args.peer_lag +
                                        "programmatic dependent of the step's gradient kernel and runs beside that kernel's last wave"
                                        if collective == "peer" else "NCCL all-reduce on a side branch") if graph_allreduce else
                                       "none on the data path; float64 loss-sum all-reduce (%s) per step on a side stream" % collective)},
@@ -662,6 +662,7 @@ def main():
     ap.add_argument("--no-others", action="store_true", help="skip the context measurements of the other configs")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="N>1: loss-sum exchange through the library's peer mailbox (default) or torch.distributed's NCCL all-reduce")
+    ap.add_argument("--peer-lag", type=int, default=4, help="slack between the ranks of the peer mailbox exchange, in steps")
     ap.add_argument("--no-allreduce", action="store_true", help="experiment: no loss-sum collective at all (N>1)")
     ap.add_argument("--no-graph-allreduce", action="store_true",
                     help="N>1: issue the loss-sum all-reduce from the host every step instead of from the captured graph")

@@ -80,7 +80,7 @@ def load():
     lib.ctcb_pipe_wait.argtypes = [vp, i64, ctypes.POINTER(vp)]
     lib.ctcb_pipe_destroy.argtypes = [vp]
     lib.ctcb_pipe_last_h2d_bytes.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i32)]
-    lib.ctcb_mailbox_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
+    lib.ctcb_mailbox_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
     lib.ctcb_mailbox_handle.argtypes = [vp, vp]
     lib.ctcb_mailbox_connect.argtypes = [vp, vp]
     lib.ctcb_mailbox_exchange.argtypes = [vp, vp, i32, vp, vp]

@@ -973,11 +973,12 @@ int ctcb_loss_sum_allreduce(void* nccl_comm, double* dev_values, int32_t count, 
 }
 
 // ---- loss-sum exchange over NVLink peer memory ----------------------------------------------
-int ctcb_mailbox_create(int device, int rank, int world, ctcb_mailbox_t** out) {
+int ctcb_mailbox_create(int device, int rank, int world, int lag, ctcb_mailbox_t** out) {
     if (!out) return fail(CTCB_INVALID_VALUE, "out is NULL");
     *out = nullptr;
     if (world < 1 || world > ctcb::kMailMaxRanks || rank < 0 || rank >= world)
         return fail(CTCB_INVALID_VALUE, "rank %d / world %d outside [0,%d]", rank, world, ctcb::kMailMaxRanks);
+    if (lag < 1 || lag > ctcb::kMailMaxLag) return fail(CTCB_INVALID_VALUE, "lag %d outside [1,%d]", lag, ctcb::kMailMaxLag);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
         cudaGetLastError();
@@ -987,7 +988,7 @@ int ctcb_mailbox_create(int device, int rank, int world, ctcb_mailbox_t** out) {
     ctcb_mailbox* m = new (std::nothrow) ctcb_mailbox();
     if (!m) return fail(CTCB_MEMOPS_FAILED, "out of host memory");
     m->device = device; m->rank = rank; m->world = world;
-    const size_t bytes = sizeof(double) * (2 * (size_t)world * ctcb::kMailRow + 8) + sizeof(ctcb::MailboxDev);
+    const size_t bytes = sizeof(double) * (2 * (size_t)lag * world * ctcb::kMailRow + 8) + sizeof(ctcb::MailboxDev);
     if (cudaMalloc(reinterpret_cast<void**>(&m->local), bytes) != cudaSuccess || cudaMemset(m->local, 0, bytes) != cudaSuccess ||
         cudaDeviceSynchronize() != cudaSuccess) {
         cudaGetLastError();
@@ -995,10 +996,10 @@ int ctcb_mailbox_create(int device, int rank, int world, ctcb_mailbox_t** out) {
         delete m;
         return fail(CTCB_MEMOPS_FAILED, "mailbox allocation failed");
     }
-    m->dev.rank = rank; m->dev.world = world;
-    m->dev.counter = reinterpret_cast<unsigned long long*>(m->local + 2 * (size_t)world * ctcb::kMailRow);
+    m->dev.rank = rank; m->dev.world = world; m->dev.lag = lag;
+    m->dev.counter = reinterpret_cast<unsigned long long*>(m->local + 2 * (size_t)lag * world * ctcb::kMailRow);
     m->dev.peer[rank] = m->local;
-    m->dev_d = reinterpret_cast<ctcb::MailboxDev*>(m->local + 2 * (size_t)world * ctcb::kMailRow + 8);
+    m->dev_d = reinterpret_cast<ctcb::MailboxDev*>(m->local + 2 * (size_t)lag * world * ctcb::kMailRow + 8);
     m->connected = world == 1;
     if (cudaMemcpy(m->dev_d, &m->dev, sizeof(m->dev), cudaMemcpyHostToDevice) != cudaSuccess) {
         cudaGetLastError(); cudaFree(m->local); delete m;

@@ -1211,19 +1211,23 @@ __global__ void __launch_bounds__((NW + (FUSED ? kFusedProducers + 1 : 1)) * 32)
 
 // ---------------------------------------------------------------------------------------
 // k_mailbox_exchange: the loss-sum exchange of section 8e over NVLink peer memory.  One warp.
-// Exchange k of a rank (k = its device-side counter): lane r stores this rank's partial sums
-// into rank r's mailbox (slot k & 1, row = this rank) with a release at system scope; lane r then
-// takes rank r's row of exchange k-1 from the LOCAL mailbox (acquire; the peers stored it one
-// exchange ago, so the wait is normally over before it starts) and lane 0 adds the rows in rank
-// order -- every rank forms the same sum with the same bits.  No NCCL kernel, no rendezvous on the
-// step's path: one step of slack between the ranks.  A peer that never shows up ends the wait
+// Exchange k of a rank (k = its device-side counter): lane r takes rank r's row of exchange k-lag
+// from the LOCAL mailbox (acquire; the peers stored it `lag` exchanges ago, so the wait is normally
+// over before it starts) and lane 0 adds the rows in rank order -- every rank forms the same sum
+// with the same bits; lane r then stores this rank's partial sums into rank r's mailbox (slot
+// k mod 2*lag, row = this rank) with a release at system scope.  No NCCL kernel, no rendezvous on
+// the step's path: `lag` steps of slack between the ranks, which absorbs the step-to-step jitter of
+// data-dependent step times (with one step of slack two ranks ran at E[max] of their step times,
+// +2.7 us at cfg2).  A peer that never shows up ends the wait
 // after ~2 s with NaN instead of hanging the GPU.
 // ---------------------------------------------------------------------------------------
 constexpr int kMailMaxRanks = 16, kMailMaxCount = 6, kMailRow = 8;      // row: 6 values, pad, sequence number
+constexpr int kMailMaxLag = 8;
 struct MailboxDev {
-    double* peer[kMailMaxRanks];        // rank r's mailbox as mapped into this process ([2][world][kMailRow] doubles)
+    double* peer[kMailMaxRanks];        // rank r's mailbox as mapped into this process ([2*lag][world][kMailRow] doubles)
     unsigned long long* counter;        // exchanges done by this rank
     int rank, world;
+    int lag;                            // exchange k returns the sums of exchange k - lag: the ranks' slack, in steps
 };
 
 // what the kernel's one warp does
@@ -1235,11 +1239,15 @@ __device__ __forceinline__ void mailbox_exchange_warp(const MailboxDev* md, doub
     // a wait that timed out once poisons the mailbox: later exchanges report NaN at once instead of waiting again
     if (lane == 0) timed_out = m.counter[1] != 0ull;
     __syncwarp();
-    // 1. gather exchange k-1 from the local mailbox.  Gather BEFORE publish: a peer can then be at most one
-    //    exchange ahead when it stores, i.e. it stores into the other slot -- two slots suffice.
-    if (k > 0 && lane < m.world) {
-        const unsigned long long kk = k - 1;
-        const double* src = m.peer[m.rank] + ((size_t)(kk & 1) * m.world + lane) * kMailRow;
+    // 1. gather exchange k-lag (flush: the last one, k-1) from the local mailbox.  Gather BEFORE publish: a peer
+    //    that stores exchange j has gathered this rank's exchange j-lag, so j <= k-1+lag while this rank is still
+    //    reading slot (k-lag) mod S -- with S = 2*lag slots the peer's store cannot land on that slot.
+    const unsigned long long back = flush ? 1ull : (unsigned long long)m.lag;
+    const unsigned S = 2u * (unsigned)m.lag;
+    const bool have = k >= back;
+    if (have && lane < m.world) {
+        const unsigned long long kk = k - back;
+        const double* src = m.peer[m.rank] + ((size_t)(kk % S) * m.world + lane) * kMailRow;
         const unsigned long long* seq = reinterpret_cast<const unsigned long long*>(src + kMailRow - 1);
         const long long t0 = clock64();
         for (; !timed_out;) {
@@ -1258,7 +1266,7 @@ __device__ __forceinline__ void mailbox_exchange_warp(const MailboxDev* md, doub
     if (lane == 0) {
         for (int c = 0; c < count; ++c) {
             double s = 0.0;
-            if (k > 0) for (int r = 0; r < m.world; ++r) s += rows[r][c];           // rank order: same bits on every rank
+            if (have) for (int r = 0; r < m.world; ++r) s += rows[r][c];            // rank order: same bits on every rank
             out[c] = timed_out ? __longlong_as_double(0x7ff8000000000000LL) : s;
         }
         if (timed_out) m.counter[1] = 1ull;
@@ -1266,7 +1274,7 @@ __device__ __forceinline__ void mailbox_exchange_warp(const MailboxDev* md, doub
     if (flush) return;                                 // flush: read the last exchange only
     // 2. publish this rank's partial sums of exchange k into every rank's mailbox (its own included)
     if (lane < m.world) {
-        double* dst = m.peer[lane] + ((size_t)(k & 1) * m.world + m.rank) * kMailRow;
+        double* dst = m.peer[lane] + ((size_t)(k % S) * m.world + m.rank) * kMailRow;
         for (int c = 0; c < count; ++c) asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst + c), "d"(values[c]) : "memory");
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(reinterpret_cast<unsigned long long*>(dst + kMailRow - 1)), "l"(k + 1) : "memory");
     }

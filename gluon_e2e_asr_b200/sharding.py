@@ -68,14 +68,15 @@ class PeerLossSum:
     One process per GPU (``torch.distributed`` initialised): every rank owns a small mailbox in
     device memory that its peers map through CUDA IPC; ``exchange(values, out)`` enqueues one tiny
     kernel on the current stream that (1) writes into ``out`` the all-rank sum of the values handed
-    to the *previous* exchange and (2) stores ``values`` into every rank's mailbox over NVLink peer
-    access and zeroes them.  Ranks never rendezvous: a rank only waits for what its peers stored one
-    exchange earlier, so a slow rank costs the others nothing until it is a whole step behind.
+    to the exchange ``lag`` calls earlier and (2) stores ``values`` into every rank's mailbox over
+    NVLink peer access and zeroes them.  Ranks never rendezvous: a rank only waits for what its peers
+    stored ``lag`` exchanges earlier, so a slow rank costs the others nothing until it is ``lag`` steps
+    behind (the slack absorbs the jitter of data-dependent step times).
     ``flush(out)`` returns the sum of the last exchange.  Replaces the reference's host-side ``+=`` of
     two ``.asscalar()`` values per shard and step (train_ctc_ce.py:367-368).  CUDA only.
     """
 
-    def __init__(self, device, group=None):
+    def __init__(self, device, group=None, lag=4):
         import ctypes
         import torch.distributed as dist
         from . import _lib
@@ -87,7 +88,8 @@ class PeerLossSum:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         lib = _lib.load()
         self._h = ctypes.c_void_p()
-        _lib.check(lib.ctcb_mailbox_create(self.device.index or 0, self.rank, self.world, ctypes.byref(self._h)))
+        self.lag = int(lag)
+        _lib.check(lib.ctcb_mailbox_create(self.device.index or 0, self.rank, self.world, self.lag, ctypes.byref(self._h)))
         if self.world > 1:
             mine = (ctypes.c_ubyte * 64)()
             _lib.check(lib.ctcb_mailbox_handle(self._h, mine))

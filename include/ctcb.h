@@ -189,16 +189,18 @@ int ctcb_loss_sum_allreduce(void* nccl_comm, double* dev_values, int32_t count, 
 
 /* The same sum WITHOUT a collective kernel on the step's path: a mailbox per rank in device memory,
  * mapped into every peer process (CUDA IPC; the stores travel over NVLink / NVSwitch peer access).
- *   ctcb_mailbox_create    allocates this rank's mailbox on `device` (world <= 16)
+ *   ctcb_mailbox_create    allocates this rank's mailbox on `device` (world <= 16).  `lag` (1..8, the same
+ *                          on every rank) is the slack between the ranks in exchanges: an exchange
+ *                          returns the sums handed over `lag` exchanges earlier
  *   ctcb_mailbox_handle    64-byte handle of the local mailbox; the caller gathers the handles of all
  *                          ranks in rank order (torch.distributed all_gather, MPI, a file ...)
  *   ctcb_mailbox_connect   maps the peers' mailboxes (handles: world x 64 bytes, rank order)
  *   ctcb_mailbox_exchange  one tiny kernel on `stream`: writes into dev_out[0..count) the all-rank sum
- *                          of the values handed to the PREVIOUS exchange (zeros for the first), then
+ *                          of the values handed to the exchange `lag` calls earlier (zeros before), then
  *                          stores dev_values[0..count) into every rank's mailbox and zeroes them
  *                          (count <= 6 doubles, e.g. loss sum, frames, utterances).  Every rank adds
  *                          the rows in rank order: identical bits everywhere.  Ranks need not meet:
- *                          a rank only waits for what its peers stored one exchange earlier.  All
+ *                          a rank only waits for what its peers stored `lag` exchanges earlier.  All
  *                          ranks must issue the same number of exchanges.
  *   ctcb_mailbox_exchange_with_next   the same exchange as part of the next ctcb_loss_grad /
  *                          ctcb_forward / ctcb_backward this thread enqueues: the exchange kernel is
@@ -212,7 +214,7 @@ int ctcb_loss_sum_allreduce(void* nccl_comm, double* dev_values, int32_t count, 
  * Replaces the host-side `+=` of `.asscalar()` values (train_ctc_ce.py:367-368) like
  * ctcb_loss_sum_allreduce does; bench.py --gpus N measures both. */
 typedef struct ctcb_mailbox ctcb_mailbox_t;
-int ctcb_mailbox_create(int device, int rank, int world, ctcb_mailbox_t** out);
+int ctcb_mailbox_create(int device, int rank, int world, int lag, ctcb_mailbox_t** out);
 int ctcb_mailbox_handle(ctcb_mailbox_t* mailbox, void* handle64);
 int ctcb_mailbox_connect(ctcb_mailbox_t* mailbox, const void* handles);
 int ctcb_mailbox_exchange(ctcb_mailbox_t* mailbox, double* dev_values, int32_t count, double* dev_out, void* stream);

@@ -106,7 +106,7 @@ def test_loss_sum_allreduce_is_a_noop_without_a_group():
     assert v.tolist() == [1.0, 2.0]
 
 
-def _peer_rank_main(rank, world, port, q, steps):
+def _peer_rank_main(rank, world, port, q, steps, lag):
     """One process per rank, all on cuda:0 (CUDA IPC maps a mailbox into another process whether or not
     it lives on another GPU): the exchange kernel's protocol -- gather exchange k-1, publish exchange k,
     two slots, rank-ordered sums -- against plain host arithmetic, with the ranks deliberately skewed."""
@@ -117,7 +117,7 @@ def _peer_rank_main(rank, world, port, q, steps):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     dev = torch.device("cuda", rank % torch.cuda.device_count())
     torch.cuda.set_device(dev)
-    ps = S.PeerLossSum(dev)
+    ps = S.PeerLossSum(dev, lag=lag)
     got = []
     vals = torch.zeros(3, dtype=torch.float64, device=dev)
     out = torch.zeros(3, dtype=torch.float64, device=dev)
@@ -140,7 +140,7 @@ def _peer_rank_main(rank, world, port, q, steps):
     red = torch.zeros((1,), dtype=torch.float64, device=dev)
     ride = []
     nstep = 5
-    for k in range(nstep + 2):
+    for k in range(nstep + lag + 1):
         d = make_batch(3, 30, 46, 5, seed=100 * rank + min(k, nstep - 1))
         t = {n: torch.tensor(v, device=dev) for n, v in d.items()}
         ps.exchange_with_next(part[(k + 1) % 2], red)          # the previous step's slot
@@ -158,8 +158,8 @@ def _peer_rank_main(rank, world, port, q, steps):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world", [2, 3])
-def test_peer_mailbox_loss_sum(world):
+@pytest.mark.parametrize("world,lag", [(2, 1), (3, 3)])
+def test_peer_mailbox_loss_sum(world, lag):
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
     import torch.multiprocessing as mp
@@ -167,27 +167,29 @@ def test_peer_mailbox_loss_sum(world):
     q = ctx.Queue()
     port = _free_port()
     steps = 9
-    procs = [ctx.Process(target=_peer_rank_main, args=(r, world, port, q, steps)) for r in range(world)]
+    procs = [ctx.Process(target=_peer_rank_main, args=(r, world, port, q, steps, lag)) for r in range(world)]
     for p in procs:
         p.start()
     res = dict(q.get(timeout=300) for _ in range(world))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    want = [[0.0, 0.0, 0.0]]
+    sums = []
     for k in range(steps):
         rows = [[0.1 * (k + 1) * (r + 1), float(100 * k + r), 1.0] for r in range(world)]
         tot = [0.0, 0.0, 0.0]
         for r in range(world):                                # rank order, like the kernel
             tot = [a + b for a, b in zip(tot, rows[r])]
-        want.append(tot)
+        sums.append(tot)
+    # exchange k returns the sums of exchange k - lag (zeros before), the flush the sums of the last exchange
+    want = [sums[k - lag] if k >= lag else [0.0, 0.0, 0.0] for k in range(steps)] + [sums[-1]]
     for r in range(world):
         ride = res[r].pop()
         assert res[r] == want, "rank %d" % r                  # bit-identical on every rank
-        # exchange k returns the sum handed over by exchange k-1, which carried step k-2's losses
-        for k in range(2, len(ride)):
-            np.testing.assert_allclose(ride[k][0], ride[k - 2][1], rtol=1e-6)
-        assert ride == res[0][-1] if False else True
+        # exchange k returns the sum handed over by exchange k-lag, which carried step k-lag-1's losses
+        assert len(ride) > lag + 1
+        for k in range(lag + 1, len(ride)):
+            np.testing.assert_allclose(ride[k][0], ride[k - lag - 1][1], rtol=1e-6)
     assert all(res[r] == res[0] for r in range(world))
 
 
@@ -196,11 +198,13 @@ def test_peer_loss_sum_needs_cuda():
     import ctypes
     l = _lib.load()
     h = ctypes.c_void_p()
-    assert l.ctcb_mailbox_create(0, 2, 2, ctypes.byref(h)) == _lib.CTCB_INVALID_VALUE
-    assert l.ctcb_mailbox_create(0, 0, 17, ctypes.byref(h)) == _lib.CTCB_INVALID_VALUE
+    assert l.ctcb_mailbox_create(0, 2, 2, 1, ctypes.byref(h)) == _lib.CTCB_INVALID_VALUE
+    assert l.ctcb_mailbox_create(0, 0, 17, 1, ctypes.byref(h)) == _lib.CTCB_INVALID_VALUE
+    assert l.ctcb_mailbox_create(0, 0, 2, 0, ctypes.byref(h)) == _lib.CTCB_INVALID_VALUE
+    assert l.ctcb_mailbox_create(0, 0, 2, 9, ctypes.byref(h)) == _lib.CTCB_INVALID_VALUE
     assert l.ctcb_mailbox_exchange(None, None, 1, None, None) == _lib.CTCB_INVALID_VALUE
     assert l.ctcb_mailbox_destroy(None) == _lib.CTCB_OK
     with pytest.raises(RuntimeError):
         S.PeerLossSum("cpu")
     if not torch.cuda.is_available():
-        assert l.ctcb_mailbox_create(0, 0, 1, ctypes.byref(h)) == _lib.CTCB_UNSUPPORTED
+        assert l.ctcb_mailbox_create(0, 0, 1, 4, ctypes.byref(h)) == _lib.CTCB_UNSUPPORTED
