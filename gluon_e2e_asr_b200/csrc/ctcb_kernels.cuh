@@ -1216,9 +1216,9 @@ __global__ void __launch_bounds__((NW + (FUSED ? kFusedProducers + 1 : 1)) * 32)
 // over before it starts) and lane 0 adds the rows in rank order -- every rank forms the same sum
 // with the same bits; lane r then stores this rank's partial sums into rank r's mailbox (slot
 // k mod 2*lag, row = this rank) with a release at system scope.  No NCCL kernel, no rendezvous on
-// the step's path: `lag` steps of slack between the ranks, which absorbs the step-to-step jitter of
-// data-dependent step times (with one step of slack two ranks ran at E[max] of their step times,
-// +2.7 us at cfg2).  A peer that never shows up ends the wait
+// the step's path: `lag` steps of slack between the ranks, for loops whose step times differ from
+// rank to rank and step to step (bench.py's uniform shards measure the same with lag 1, 4 and 8;
+// DESIGN.md section 8).  A peer that never shows up ends the wait
 // after ~2 s with NaN instead of hanging the GPU.
 // ---------------------------------------------------------------------------------------
 constexpr int kMailMaxRanks = 16, kMailMaxCount = 6, kMailRow = 8;      // row: 6 values, pad, sequence number
