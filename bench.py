@@ -239,6 +239,9 @@ def run_cuda(args, rank, world, local_rank):
         from gluon_e2e_asr_b200 import PeerLossSum
         peer = PeerLossSum(dev, lag=args.peer_lag)
         collective = "peer"
+    if world > 1 and args.no_allreduce and os.environ.get("CTCB_BENCH_CONNECT_ONLY") == "1":
+        from gluon_e2e_asr_b200 import PeerLossSum
+        _connected_only = PeerLossSum(dev, lag=args.peer_lag)      # experiment: peer mailboxes mapped, never used
     if world > 1 and not args.no_allreduce:
         collective = "nccl"
         if args.collective == "peer":
