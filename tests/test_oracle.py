@@ -169,3 +169,18 @@ def test_greedy_decode_and_split():
     s = O.split_and_load_slices(10, 4)
     assert [(x.start, x.stop) for x in s] == [(0, 2), (2, 4), (4, 6), (6, 10)]
     assert [(x.start, x.stop) for x in O.split_and_load_slices(3, 4)] == [(0, 3)]
+
+
+def test_c_fp64_matches_numpy_at_size():
+    """The C restatement in fp64 is the checker of the full-batch-size GPU parity tests
+    (tests/test_parity_gpu.py::test_baseline_configs_at_full_batch_size): pin it to the numpy oracle
+    on BASELINE-shaped utterances (NTC strides, ragged lengths, repeats, head gradient, peaky logits)."""
+    for seed, peaky, shape in ((5, True, (6, 300, 46, 80)), (6, False, (4, 500, 46, 120)), (7, False, (2, 120, 300, 40))):
+        d = make_batch(*shape, seed=seed, peaky=peaky)
+        head = np.random.default_rng(seed).uniform(0.5, 1.5, shape[0])
+        lo, go, ok = O.CtcLossOracle("NTC", "NT")(d["pred"], d["label"], d["pred_lengths"], d["label_lengths"], head_grad=head)
+        lc, gc, okc = R.ctc_ref(d["pred"], d["label"], d["pred_lengths"], d["label_lengths"], head_grad=head,
+                                layout="NTC", dtype=np.float64)
+        assert ok.all() and okc.all()
+        np.testing.assert_allclose(lc, lo, rtol=1e-12, atol=1e-11)
+        np.testing.assert_allclose(gc, go, rtol=1e-9, atol=1e-12)

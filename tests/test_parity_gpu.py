@@ -680,3 +680,55 @@ def test_random_small_problems_vs_oracle(dev):
         np.testing.assert_array_equal((status.cpu().numpy() & 1) == 0, ok)
 
     run()
+
+
+# ---- BASELINE.json configs at their REAL batch sizes ------------------------------------------------
+# The numpy oracle is a Python loop over T; at full batch sizes the checker is the oracle's C
+# restatement in fp64 (oracle/ctc_ref.c), itself pinned to the numpy oracle at 1e-11 on the golden
+# fixtures (tests/test_oracle.py::test_torch_fp64_fixtures_numpy_and_c, test_c_fp64_matches_numpy_at_size).
+def _c_oracle(d, head=None):
+    from oracle import ctc_ref
+    lo, go, ok = ctc_ref.ctc_ref(d["pred"], d["label"], d["pred_lengths"], d["label_lengths"], blank=0,
+                                 head_grad=head, layout="NTC", dtype=np.float64)
+    return lo, go, ok
+
+
+@pytest.mark.parametrize("cfg,seed,peaky,full", [
+    ("cfg2", 0, False, False), ("cfg2", 1, True, False),
+    ("cfg3", 0, False, False),
+    ("cfg4", 0, False, False), ("cfg4", 1, True, False),
+    ("cfg5", 0, False, False), ("cfg5", 1, False, True), ("cfg5", 2, True, False),
+])
+def test_baseline_configs_at_full_batch_size(dev, cfg, seed, peaky, full):
+    """Loss and gradient at rtol 1e-4 / atol 1e-5 for the BASELINE shapes at their real B (cfg2 32,
+    cfg3 64, cfg4 16, cfg5 1024), through ctc_loss_and_grad AND CtcLoss(...).mean().backward()
+    (train_ctc_ce.py:363-366)."""
+    from gluon_e2e_asr_b200 import CtcLoss, ctc_loss_and_grad
+    B, T, V, L = CONFIGS[cfg]
+    d = make_batch(B, T, V, L, seed=seed, peaky=peaky, full_lengths=full)
+    head = np.full((B,), 1.0 / B)
+    lo, go, ok = _c_oracle(d, head=head)
+    assert ok.all()
+    t = _to(dev, d)
+    loss, grad = ctc_loss_and_grad(t["pred"], t["label"], t["pred_lengths"], t["label_lengths"],
+                                   head_grad=torch.tensor(head, device=dev, dtype=torch.float32))
+    _check(loss.cpu().numpy(), grad.cpu().numpy(), lo, go, cfg + " fused")
+    del grad
+    pred = t["pred"].requires_grad_(True)
+    l2 = CtcLoss(layout="NTC", label_layout="NT")(pred, t["label"], t["pred_lengths"], t["label_lengths"])
+    l2.mean().backward()
+    _check(l2.detach().cpu().numpy(), pred.grad.cpu().numpy(), lo, go, cfg + " block.mean().backward()")
+
+
+@pytest.mark.parametrize("B,T,V,L,seed", [
+    (300, 120, 46, 120, 60),     # B > 296 AND L > 32: the plain-launch, register-capped gradient kernel of cfg5
+    (100, 200, 46, 50, 61),      # 75 <= B <= 148: two walker CTAs per SM in the shared-memory partition
+    (150, 96, 30, 20, 62),       # 149..296: the walkers still fit the GPU at once
+])
+def test_batch_size_regimes_vs_c_oracle(dev, B, T, V, L, seed):
+    from gluon_e2e_asr_b200 import ctc_loss_and_grad
+    d = make_batch(B, T, V, L, seed=seed)
+    lo, go, ok = _c_oracle(d)
+    t = _to(dev, d)
+    loss, grad = ctc_loss_and_grad(t["pred"], t["label"], t["pred_lengths"], t["label_lengths"])
+    _check(loss.cpu().numpy(), grad.cpu().numpy(), lo, go, "B=%d" % B)
