@@ -1,6 +1,6 @@
 """ctypes binding of libctcb.so (include/ctcb.h, include/ctcb_dlpack.h).
 
-The library is built in-tree by ``__graft_entry__.build()`` / ``build_ext.py``; importing the
+The library is built in-tree by ``__graft_entry__.build()``; importing the
 compute API without it fails loudly -- there is no Python or CPU fallback for the path.
 """
 from __future__ import annotations
@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("CTCB_LIB_PATH") or os.path.join(_HERE, "libctcb.so")
 
 CTCB_OK, CTCB_INVALID_VALUE, CTCB_WORKSPACE_TOO_SMALL, CTCB_EXECUTION_FAILED, CTCB_MEMOPS_FAILED, CTCB_UNSUPPORTED = range(6)
 DT_I32, DT_I64, DT_F32, DT_F64 = range(4)
-UTT_INFEASIBLE, UTT_BAD_LABEL, UTT_LEN_CLAMPED = 1, 2, 4
+UTT_INFEASIBLE, UTT_BAD_LABEL, UTT_LEN_CLAMPED, UTT_WIDE_LOGITS = 1, 2, 4, 8
 LAYOUT_NTC, LABEL_TN, KEEP_FOR_BACKWARD = 1, 2, 4
 PHASE_FUSED, PHASE_FORWARD, PHASE_BACKWARD = 0 << 8, 1 << 8, 2 << 8
 
@@ -26,6 +26,7 @@ EXPORTS = (
     "ctcb_pipe_create", "ctcb_pipe_submit", "ctcb_pipe_wait", "ctcb_pipe_destroy", "ctcb_pipe_last_h2d_bytes",
     "ctcb_mailbox_create", "ctcb_mailbox_handle", "ctcb_mailbox_connect", "ctcb_mailbox_exchange",
     "ctcb_mailbox_flush", "ctcb_mailbox_destroy", "ctcb_mailbox_exchange_with_next",
+    "ctcb_set_option", "ctcb_get_option", "ctcb_greedy_decode_unk",
 )
 
 
@@ -88,11 +89,14 @@ def load():
     lib.ctcb_mailbox_exchange_with_next.argtypes = [vp, vp, i32, vp]
     lib.ctcb_mailbox_destroy.argtypes = [vp]
     lib.ctcb_greedy_decode.argtypes = [vp, i64, i64, vp, i32, i32, i32, i32, i32, vp, vp, vp]
+    lib.ctcb_greedy_decode_unk.argtypes = [vp, i64, i64, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]
     lib.ctcb_scale_rows.argtypes = [vp, i64, i64, i32, i32, i32, vp, vp]
     lib.ctcb_edit_distance.argtypes = [vp, i64, vp, vp, i64, vp, i32, i32, i32, vp, vp, vp]
     lib.ctcb_loss_sum_allreduce.argtypes = [vp, vp, i32, vp]
     lib.ctcb_last_walk_config.argtypes = [ctypes.POINTER(i32), ctypes.POINTER(i32)]
     lib.ctcb_loss_grad_dlpack.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, sz, vp]
+    lib.ctcb_set_option.argtypes = [ctypes.c_char_p, i32]
+    lib.ctcb_get_option.argtypes = [ctypes.c_char_p, ctypes.POINTER(i32)]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name != "ctcb_last_error":
@@ -107,11 +111,42 @@ def check(rc):
 
 
 _ws_bytes = {}
+_opt_epoch = 0          # bumped by set_option: cached workspace sizes depend on walk_p / walk_nw / fused
+
+
+def set_option(name, value):
+    """ctcb_set_option: tuning / experiment switch (tests, A/B runs); -1 = automatic."""
+    global _opt_epoch
+    check(load().ctcb_set_option(name.encode(), int(value)))
+    _opt_epoch += 1
+
+
+def get_option(name):
+    v = ctypes.c_int32(0)
+    check(load().ctcb_get_option(name.encode(), ctypes.byref(v)))
+    return int(v.value)
+
+
+class options:
+    """``with options(overlap=0, fused=0): ...`` -- sets the switches, restores the previous values."""
+
+    def __init__(self, **kw):
+        self.kw, self.old = kw, {}
+
+    def __enter__(self):
+        for k, v in self.kw.items():
+            self.old[k] = get_option(k)
+            set_option(k, v)
+        return self
+
+    def __exit__(self, *exc):
+        for k, v in self.old.items():
+            set_option(k, v)
+        return False
 
 
 def workspace_bytes(T, B, V, Lmax, need_grad=True):
-    key = (T, B, V, Lmax, bool(need_grad), os.environ.get("CTCB_WALK_P"), os.environ.get("CTCB_WALK_NW"),
-           os.environ.get("CTCB_FUSED"))
+    key = (T, B, V, Lmax, bool(need_grad), _opt_epoch)
     n = _ws_bytes.get(key)
     if n is None:
         out = ctypes.c_size_t(0)

@@ -52,6 +52,29 @@ bool launch_pending_xchg(cudaStream_t stream, bool programmatic = false) {
 thread_local cudaEvent_t* g_prof_events = nullptr;   // when set: one event recorded after every launch
 thread_local int g_prof_count = 0;
 
+// ---- tuning / experiment switches -----------------------------------------------------------
+// Read from the environment ONCE (CTCB_<NAME>, at first use) and changeable through ctcb_set_option (tests, A/B
+// runs): nothing on the per-call host path calls getenv.  -1 = automatic.
+enum Opt { OPT_WALK_P, OPT_WALK_NW, OPT_WALK_STAGES, OPT_OVERLAP, OPT_FUSED, OPT_WALK_PER_SM, OPT_EMIT_STAGED,
+           OPT_GRAD_STAGED, OPT_COUNT };
+const char* const kOptNames[OPT_COUNT] = {"walk_p", "walk_nw", "walk_stages", "overlap", "fused", "walk_per_sm",
+                                          "emit_staged", "grad_staged"};
+struct Options {
+    int v[OPT_COUNT];
+    Options() {
+        for (int i = 0; i < OPT_COUNT; ++i) {
+            char name[64] = "CTCB_";
+            size_t k = 5;
+            for (const char* c = kOptNames[i]; *c && k + 1 < sizeof(name); ++c) name[k++] = (char)(*c >= 'a' && *c <= 'z' ? *c - 32 : *c);
+            name[k] = 0;
+            const char* e = getenv(name);
+            v[i] = e ? atoi(e) : -1;
+        }
+    }
+};
+Options& options() { static Options o; return o; }
+inline int opt(Opt i) { return options().v[i]; }
+
 int fail(int code, const char* fmt, ...) {
     va_list ap; va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
@@ -94,10 +117,8 @@ const WalkEntry* find_walk(int P, int NW) {
 // default choice per capacity (pairs = Lmax+1); tuned on B200, see DESIGN.md section 5.
 // The choice is part of the workspace layout (history chunks are per walker warp).
 const WalkEntry* choose_walk(int pairs) {
-    const char* ep = getenv("CTCB_WALK_P");
-    const char* en = getenv("CTCB_WALK_NW");
-    if (ep && en) {
-        const WalkEntry* e = find_walk(atoi(ep), atoi(en));
+    if (opt(OPT_WALK_P) > 0 && opt(OPT_WALK_NW) > 0) {
+        const WalkEntry* e = find_walk(opt(OPT_WALK_P), opt(OPT_WALK_NW));
         if (e && e->P * e->NW * 32 >= pairs) return e;
     }
     static const WalkCfg pref[] = {{1, 1}, {2, 1}, {2, 2}, {2, 3}, {2, 4}, {2, 5}, {2, 6}, {2, 8}, {2, 12}, {2, 16}, {4, 16}};
@@ -108,9 +129,8 @@ const WalkEntry* choose_walk(int pairs) {
 
 // emission ring depth: as deep as fits a modest budget (several walker CTAs share an SM)
 bool pick_stages(int W, int NW, int fused_Lp, int* stages) {
-    const char* es = getenv("CTCB_WALK_STAGES");
     const size_t budget = 40 * 1024, hard = 200 * 1024;
-    for (int s = es ? atoi(es) : ctcb::kMaxStages; s >= 2; --s) {
+    for (int s = opt(OPT_WALK_STAGES) > 0 ? opt(OPT_WALK_STAGES) : ctcb::kMaxStages; s >= 2; --s) {
         if (s > ctcb::kMaxStages) continue;
         const size_t need = ctcb::walk_smem_bytes(W, NW, s, fused_Lp);
         if (need <= budget || (s <= 3 && need <= hard)) { *stages = s; return true; }
@@ -123,8 +143,7 @@ bool pick_stages(int W, int NW, int fused_Lp, int* stages) {
 // vocabularies: the gradient kernel wants every SM's bandwidth, so the walkers reserve nothing and the
 // gradient CTAs share their SMs (measured at cfg3: 238 -> 216 us; with the reservation it was no gain)
 bool overlap_allowed(int B, bool fused) {
-    const char* e = getenv("CTCB_OVERLAP");
-    if (e) return atoi(e) != 0;
+    if (opt(OPT_OVERLAP) >= 0) return opt(OPT_OVERLAP) != 0;
     (void)fused;
     return B <= 296;
 }
@@ -149,34 +168,18 @@ cudaError_t ensure_dynamic_smem(const void* fn, size_t bytes) {
     return rc;
 }
 
-// CUDA loads a kernel lazily at its first launch, and that load can wait for the device to drain.  A
-// kernel that running kernels WAIT FOR (k_emit, launched after the walkers that consume its blocks) must
-// therefore be resident before those are launched: cudaFuncGetAttributes forces the load.  Once per
-// device and kernel.
-cudaError_t ensure_loaded(const void* fn) {
-    static std::mutex mu;
-    static std::vector<std::pair<int, const void*>> seen;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    std::lock_guard<std::mutex> lk(mu);
-    for (auto& e : seen) if (e.first == dev && e.second == fn) return cudaSuccess;
-    cudaFuncAttributes fa{};
-    const cudaError_t rc = cudaFuncGetAttributes(&fa, fn);
-    if (rc == cudaSuccess) seen.push_back({dev, fn});
-    return rc;
-}
-
 struct Layout {
-    size_t off_Tb, off_Lb, off_flags, off_lab, off_rank, off_dl, off_nd, off_fr, off_E, off_hA, off_hB, off_oA, off_oB, off_gprog, off_eprog, total;
+    size_t off_Tb, off_Lb, off_flags, off_lab, off_rank, off_dl, off_nd, off_fr, off_E, off_hA, off_hB, off_oA, off_oB, off_gprog, total;
     int Lp, W, NB, dense, fused, P, NW;
+    int stamp;               // nonzero hash of everything the workspace layout depends on (Workspace::stamp)
     const WalkEntry* walk;
 };
 
 // small dense vocabularies: the walkers' own producer warps turn logits rows into emission
 // blocks (no k_emit launch, no emission table in HBM)
 inline bool fused_emit(int V, int Lmax) {
-    const char* e = getenv("CTCB_FUSED");
-    if (e && atoi(e) == 0) return false;
+    (void)Lmax;
+    if (opt(OPT_FUSED) == 0) return false;
     return V <= 64;
 }
 
@@ -204,7 +207,6 @@ Layout make_layout(int T, int B, int V, int Lmax, int need_grad) {
     l.off_dl = take(sizeof(int2) * (size_t)B * (l.Lp + 1));
     l.off_nd = take(sizeof(int) * B);
     l.off_gprog = take(sizeof(int) * 4 * (size_t)B);
-    l.off_eprog = take(l.fused ? 0 : sizeof(int) * (size_t)B * l.NB);
     l.off_fr = take(sizeof(float2) * (size_t)B * T);
     l.off_E = take(l.fused ? 0 : sizeof(double) * (size_t)B * l.NB * l.W * ctcb::kEC);
     if (need_grad) {
@@ -214,6 +216,9 @@ Layout make_layout(int T, int B, int V, int Lmax, int need_grad) {
         l.off_oB = take(sizeof(int2) * (size_t)B * l.NB * pairs);
     }
     l.total = o;
+    unsigned h = 2166136261u;
+    for (int v : {T, B, V, Lmax, l.Lp, l.W, l.NB, l.dense, l.fused, l.P, l.NW, need_grad ? 1 : 0}) { h ^= (unsigned)v; h *= 16777619u; }
+    l.stamp = (int)(h | 1u);
     return l;
 }
 
@@ -234,10 +239,9 @@ ctcb::Workspace carve(const Layout& l, void* ws) {
     w.oA = reinterpret_cast<int2*>(base + l.off_oA);
     w.oB = reinterpret_cast<int2*>(base + l.off_oB);
     w.gprog = reinterpret_cast<int*>(base + l.off_gprog);
-    w.eprog = reinterpret_cast<int*>(base + l.off_eprog);
-    w.ew = 0;
     w.Lp = l.Lp; w.W = l.W; w.NB = l.NB; w.dense = l.dense; w.P = l.P; w.NW = l.NW;
     w.fused = l.fused;
+    w.stamp = l.stamp;
     return w;
 }
 
@@ -299,6 +303,19 @@ int ctcb_last_walk_config(int32_t* p, int32_t* nw) {
     return CTCB_OK;
 }
 
+int ctcb_set_option(const char* name, int32_t value) {
+    if (!name) return fail(CTCB_INVALID_VALUE, "option name is NULL");
+    for (int i = 0; i < OPT_COUNT; ++i)
+        if (strcmp(name, kOptNames[i]) == 0) { options().v[i] = value; return CTCB_OK; }
+    return fail(CTCB_INVALID_VALUE, "unknown option '%s'", name);
+}
+int ctcb_get_option(const char* name, int32_t* value) {
+    if (!name || !value) return fail(CTCB_INVALID_VALUE, "NULL argument");
+    for (int i = 0; i < OPT_COUNT; ++i)
+        if (strcmp(name, kOptNames[i]) == 0) { *value = options().v[i]; return CTCB_OK; }
+    return fail(CTCB_INVALID_VALUE, "unknown option '%s'", name);
+}
+
 int ctcb_workspace_bytes(int32_t T, int32_t B, int32_t V, int32_t Lmax, int32_t need_grad, size_t* out) {
     if (!out) return fail(CTCB_INVALID_VALUE, "out_bytes is NULL");
     if (T <= 0 || B <= 0 || V <= 1 || Lmax < 0) return fail(CTCB_INVALID_VALUE, "bad shape T=%d B=%d V=%d Lmax=%d", T, B, V, Lmax);
@@ -333,6 +350,8 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
     ctcb::Workspace w = carve(lay, workspace);
 
     if (phases & PH_FORWARD) {
+        // status words: zeroed here, OR-ed into by the kernels (several CTAs of an utterance report bits)
+        if (p->status) CUDA_TRY(cudaMemsetAsync(p->status, 0, sizeof(int32_t) * (size_t)p->B, stream));
         const WalkEntry* we = lay.walk;
         if (!we) return fail(CTCB_UNSUPPORTED, "no walker configuration for Lmax=%d", p->Lmax);
         g_walk_p = we->P; g_walk_nw = we->NW;
@@ -349,9 +368,8 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
             int dev = 0, nsm = 148;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-            const char* eps = getenv("CTCB_WALK_PER_SM");
             int per_sm = (2 * p->B + nsm - 1) / nsm;
-            if (eps && atoi(eps) > per_sm) per_sm = atoi(eps);
+            if (opt(OPT_WALK_PER_SM) > per_sm) per_sm = opt(OPT_WALK_PER_SM);
             const size_t share = (size_t)233472 / per_sm;
             size_t want = share > 2048 ? (share - 1024) / 128 * 128 : 0;
             cudaFuncAttributes fa{};
@@ -366,33 +384,18 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
         const int units = (p->V / vec + 31) / 32;
         int nq = units <= 1 ? 1 : units <= 2 ? 2 : units <= 4 ? 4 : units <= 8 ? 8 : units <= 16 ? 16 : 0;
         // wide vocabularies with 16-byte aligned rows: the frame block's rows staged in shared memory by bulk copies
-        const char* est = getenv("CTCB_EMIT_STAGED");
         const bool staged = !lay.fused && vec == 4 && (nq == 0 || nq >= 8) && ctcb::emit_smem_bytes(lay.Lp, p->V) <= 75 * 1024 &&
-                            !(est && atoi(est) == 0);
+                            opt(OPT_EMIT_STAGED) != 0;
         if (staged) nq = -1;
-        // ... and then k_emit runs CONCURRENTLY with the walkers: k_walk is launched first, k_emit as its
-        // programmatic dependent, publishing every emission block (Workspace::eprog) in the order the two
-        // walkers consume them.  One walker CTA per SM at most, so that the emission CTAs keep their room.
-        const char* eew = getenv("CTCB_EW_OVERLAP");
-        // Measured at cfg3 and NOT faster (forward 114 -> 143 us, whole step 216 -> 213 us: the walkers' history
-        // stores stall behind the emission kernel's traffic), so it is opt-in: CTCB_EW_OVERLAP=1.
-        const bool ew = staged && !g_prof_events && 2 * p->B <= 148 && overlap_allowed(p->B, false) && eew && atoi(eew) != 0;
-        w.ew = ew ? 1 : 0;
         auto launch_emit = [&]() -> int {
             const int bpc = ctcb::emit_blocks_per_cta(nq);
             const int nblk = (lay.NB + bpc - 1) / bpc + 1;          // + the metadata CTA of each utterance
-            const dim3 egrid = ew ? dim3(p->B, nblk) : dim3(nblk, p->B);
+            const dim3 egrid(nblk, p->B);
             const size_t esm = ctcb::emit_smem_bytes(lay.Lp, staged ? p->V : 0);
             if (staged) {
                 auto efn = ctcb::k_emit<4, -1>;
                 if (esm > 48 * 1024) CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(efn), esm));
-                cudaLaunchConfig_t cfg{};
-                cfg.gridDim = egrid; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = esm; cfg.stream = stream;
-                cudaLaunchAttribute attr[1];
-                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-                attr[0].val.programmaticStreamSerializationAllowed = 1;
-                cfg.attrs = attr; cfg.numAttrs = ew ? 1 : 0;
-                CUDA_TRY(cudaLaunchKernelEx(&cfg, efn, dp, w));
+                efn<<<egrid, 256, esm, stream>>>(dp, w);
             } else {
 #define EMIT_LAUNCH(V_, Q_) ctcb::k_emit<V_, Q_><<<egrid, 128, esm, stream>>>(dp, w)
 #define EMIT_NQ(V_) switch (nq) { case 1: EMIT_LAUNCH(V_, 1); break; case 2: EMIT_LAUNCH(V_, 2); break; \
@@ -427,17 +430,8 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
             mark(stream);
             return CTCB_OK;
         };
-        if (ew) {
-            // the walkers spin on what k_emit publishes: k_emit must be loaded and configured before they start
-            const void* efn = reinterpret_cast<const void*>(ctcb::k_emit<4, -1>);
-            CUDA_TRY(ensure_loaded(efn));
-            CUDA_TRY(ensure_dynamic_smem(efn, ctcb::emit_smem_bytes(lay.Lp, p->V)));
-            if (int rc = launch_walk(false)) return rc;
-            if (int rc = launch_emit()) return rc;
-        } else {
-            if (!lay.fused) { if (int rc = launch_emit()) return rc; }
-            if (int rc = launch_walk(xchg && lay.fused != 0)) return rc;
-        }
+        if (!lay.fused) { if (int rc = launch_emit()) return rc; }
+        if (int rc = launch_walk(xchg && lay.fused != 0)) return rc;
     }
     if (phases & PH_BACKWARD) {
         ctcb::GradArgs ga{dp, w};
@@ -471,8 +465,7 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
         }
         // wide vocabularies with 16-byte aligned rows: the frame block's rows staged in shared memory by bulk copies
         const size_t gsm_staged = ctcb::grad_smem_bytes(lay.Lp, 32 * gch, p->V);
-        const char* est = getenv("CTCB_GRAD_STAGED");
-        if (xq == 0 && vec == 4 && gsm_staged <= 75 * 1024 && !(est && atoi(est) == 0)) {
+        if (xq == 0 && vec == 4 && gsm_staged <= 75 * 1024 && opt(OPT_GRAD_STAGED) != 0) {
             gfn = ch == 1 ? ctcb::k_grad<4, 1, -1> : ch == 2 ? ctcb::k_grad<4, 2, -1> : ch == 4 ? ctcb::k_grad<4, 4, -1> :
                   ch == 8 ? ctcb::k_grad<4, 8, -1> : ch == 16 ? ctcb::k_grad<4, 16, -1> : ctcb::k_grad<4, 0, -1>;
             gsm = gsm_staged;
@@ -541,8 +534,7 @@ int ctcb_backward(const ctcb_problem_t* p, void* workspace, size_t workspace_byt
 namespace {
 struct HostScratch {
     void* ptr = nullptr; size_t bytes = 0;
-    cudaStream_t stream = nullptr, stream2 = nullptr;          // second stream: the other half of a pipelined batch
-    cudaEvent_t ev_small = nullptr, ev_copy0 = nullptr, ev_done1 = nullptr;
+    cudaStream_t stream = nullptr;
 };
 std::mutex g_hs_mu;
 HostScratch g_hs[64];
@@ -581,17 +573,8 @@ int loss_grad_host_impl(const ctcb_problem_t* hp, int device, float** dev_grad) 
     if (Lmax > 0 && !((hp->label_stride_b == Lmax && hp->label_stride_l == 1) || (hp->label_stride_b == 1 && hp->label_stride_l == B)))
         return fail(CTCB_INVALID_VALUE, "host entry needs compact NT or TN labels");
 
-    // Two halves of the batch on two streams: the second half's logits cross PCIe while the first
-    // half's kernels run (the kernels are bound by the T-step recursion, not by the batch size).
-    // Needs utterance-major buffers (NTC logits, NT labels) so that a half is one contiguous copy.
-    const bool nt = Lmax == 0 || (hp->label_stride_b == Lmax && hp->label_stride_l == 1);
-    // (measured at cfg2: no faster than one copy + one launch -- two launches of latency-bound kernels cost
-    // what the overlap gains -- so it is opt-in: CTCB_HOST_CHUNKS=2)
-    int nchunk = 1;
-    if (const char* ec = getenv("CTCB_HOST_CHUNKS")) { if (atoi(ec) >= 2 && ntc && nt && B >= 16) nchunk = 2; }
-    const int Bc[2] = {nchunk == 2 ? (B + 1) / 2 : B, nchunk == 2 ? B - (B + 1) / 2 : 0};
-    size_t ws_bytes[2] = {0, 0};
-    for (int c = 0; c < nchunk; ++c) ctcb_workspace_bytes(T, Bc[c], V, Lmax, need_grad, &ws_bytes[c]);
+    size_t ws_bytes = 0;
+    ctcb_workspace_bytes(T, B, V, Lmax, need_grad, &ws_bytes);
     const size_t n_log = sizeof(float) * (size_t)T * B * V;
     const size_t n_lab = dt_size(hp->label_dtype) * (size_t)B * (Lmax > 0 ? Lmax : 1);
     const size_t n_dl = hp->data_lengths ? dt_size(hp->data_lengths_dtype) * (size_t)B : 0;
@@ -599,19 +582,15 @@ int loss_grad_host_impl(const ctcb_problem_t* hp, int device, float** dev_grad) 
     const size_t n_head = hp->head_grad ? sizeof(float) * (size_t)B : 0;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
-    const size_t o_ws[2] = {take(ws_bytes[0]), take(ws_bytes[1])};
+    const size_t o_ws = take(ws_bytes);
     const size_t o_log = take(n_log), o_grad = take(need_grad ? n_log : 0), o_lab = take(n_lab),
                  o_dl = take(n_dl), o_ll = take(n_ll), o_head = take(n_head), o_loss = take(sizeof(float) * B),
                  o_sum = take(sizeof(double)), o_stat = take(sizeof(int) * B);
     std::lock_guard<std::mutex> lk(g_hs_mu);
     HostScratch& hs = g_hs[device];
     if (!hs.stream) {
-        if (cudaStreamCreateWithFlags(&hs.stream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaStreamCreateWithFlags(&hs.stream2, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&hs.ev_small, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&hs.ev_copy0, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&hs.ev_done1, cudaEventDisableTiming) != cudaSuccess)
-            return fail(CTCB_MEMOPS_FAILED, "stream / event creation failed");
+        if (cudaStreamCreateWithFlags(&hs.stream, cudaStreamNonBlocking) != cudaSuccess)
+            return fail(CTCB_MEMOPS_FAILED, "stream creation failed");
     }
     if (hs.bytes < o) {
         if (hs.ptr) cudaFree(hs.ptr);
@@ -623,37 +602,25 @@ int loss_grad_host_impl(const ctcb_problem_t* hp, int device, float** dev_grad) 
     cudaStream_t s = hs.stream;
     if (dev_grad) *dev_grad = reinterpret_cast<float*>(base + o_grad);
 #define COPY_TRY(expr) do { if ((expr) != cudaSuccess) return fail(CTCB_MEMOPS_FAILED, "%s: %s", #expr, cudaGetErrorString(cudaGetLastError())); } while (0)
-    // small inputs of the whole batch first, then the logits half by half
     if (Lmax > 0) COPY_TRY(cudaMemcpyAsync(base + o_lab, hp->labels, n_lab, cudaMemcpyHostToDevice, s));
     if (n_dl) COPY_TRY(cudaMemcpyAsync(base + o_dl, hp->data_lengths, n_dl, cudaMemcpyHostToDevice, s));
     if (n_ll) COPY_TRY(cudaMemcpyAsync(base + o_ll, hp->label_lengths, n_ll, cudaMemcpyHostToDevice, s));
     if (n_head) COPY_TRY(cudaMemcpyAsync(base + o_head, hp->head_grad, n_head, cudaMemcpyHostToDevice, s));
     if (hp->loss_sum) COPY_TRY(cudaMemcpyAsync(base + o_sum, hp->loss_sum, sizeof(double), cudaMemcpyHostToDevice, s));
-    if (nchunk == 2) COPY_TRY(cudaEventRecord(hs.ev_small, s));
-    int b0 = 0;
-    for (int c = 0; c < nchunk; ++c) {
-        cudaStream_t sc = c == 0 ? s : hs.stream2;
-        const size_t row = (size_t)T * V;                                    // floats per utterance (NTC halves)
-        const size_t log_off = nchunk == 2 ? sizeof(float) * row * b0 : 0, log_n = nchunk == 2 ? sizeof(float) * row * Bc[c] : n_log;
-        if (c == 1) { COPY_TRY(cudaStreamWaitEvent(sc, hs.ev_small, 0)); COPY_TRY(cudaStreamWaitEvent(sc, hs.ev_copy0, 0)); }
-        COPY_TRY(cudaMemcpyAsync(base + o_log + log_off, reinterpret_cast<const char*>(hp->logits) + log_off, log_n, cudaMemcpyHostToDevice, sc));
-        if (nchunk == 2 && c == 0) COPY_TRY(cudaEventRecord(hs.ev_copy0, sc));
+    COPY_TRY(cudaMemcpyAsync(base + o_log, hp->logits, n_log, cudaMemcpyHostToDevice, s));
+    {
         ctcb_problem_t d = *hp;
-        d.B = Bc[c];
-        d.logits = reinterpret_cast<float*>(base + o_log + log_off);
-        d.grad = need_grad ? reinterpret_cast<float*>(base + o_grad + log_off) : nullptr;
+        d.logits = reinterpret_cast<float*>(base + o_log);
+        d.grad = need_grad ? reinterpret_cast<float*>(base + o_grad) : nullptr;
         if (dev_grad) { d.grad_stride_t = hp->logits_stride_t; d.grad_stride_b = hp->logits_stride_b; }
-        if (nchunk == 2) { d.logits_stride_b = (long long)row; if (need_grad) d.grad_stride_b = (long long)row; }
-        d.labels = base + o_lab + dt_size(hp->label_dtype) * (size_t)b0 * (nchunk == 2 ? Lmax : 0);
-        d.data_lengths = hp->data_lengths ? base + o_dl + dt_size(hp->data_lengths_dtype) * (size_t)b0 : nullptr;
-        d.label_lengths = hp->label_lengths ? base + o_ll + dt_size(hp->label_lengths_dtype) * (size_t)b0 : nullptr;
-        d.head_grad = hp->head_grad ? reinterpret_cast<float*>(base + o_head) + b0 : nullptr;
-        d.loss = reinterpret_cast<float*>(base + o_loss) + b0;
+        d.labels = base + o_lab;
+        d.data_lengths = hp->data_lengths ? base + o_dl : nullptr;
+        d.label_lengths = hp->label_lengths ? base + o_ll : nullptr;
+        d.head_grad = hp->head_grad ? reinterpret_cast<float*>(base + o_head) : nullptr;
+        d.loss = reinterpret_cast<float*>(base + o_loss);
         d.loss_sum = hp->loss_sum ? reinterpret_cast<double*>(base + o_sum) : nullptr;
-        d.status = hp->status ? reinterpret_cast<int32_t*>(base + o_stat) + b0 : nullptr;
-        if (int rc = ctcb_loss_grad(&d, base + o_ws[c], ws_bytes[c], sc)) return rc;
-        if (c == 1) { COPY_TRY(cudaEventRecord(hs.ev_done1, sc)); COPY_TRY(cudaStreamWaitEvent(s, hs.ev_done1, 0)); }
-        b0 += Bc[c];
+        d.status = hp->status ? reinterpret_cast<int32_t*>(base + o_stat) : nullptr;
+        if (int rc = ctcb_loss_grad(&d, base + o_ws, ws_bytes, s)) return rc;
     }
     COPY_TRY(cudaMemcpyAsync(hp->loss, base + o_loss, sizeof(float) * B, cudaMemcpyDeviceToHost, s));
     if (need_grad && !dev_grad) COPY_TRY(cudaMemcpyAsync(hp->grad, base + o_grad, n_log, cudaMemcpyDeviceToHost, s));
@@ -686,10 +653,33 @@ struct ctcb_pipe {
     std::vector<Slot> slots;
     int64_t next = 0;
     int64_t last_h2d = 0;                           // bytes the last submit moved host -> device
-    int last_pulled = 0;                            // ... with the logits pulled by k_pull_valid (valid frames only)
+    uintptr_t arena_lo = 0, arena_hi = 0;           // a host allocation already verified to hold a whole batch
 };
 
 namespace {
+// [lo, hi) lies inside ONE allocation known to the driver (page-locked host memory in the unified address
+// space): only then may separately described arrays be moved with a single copy over the span between them
+// -- the gaps of two unrelated allocations that merely happen to be neighbours could be unmapped or pageable.
+bool same_allocation(uintptr_t lo, uintptr_t hi, uintptr_t* range_lo, uintptr_t* range_hi) {
+    typedef int (*attr_fn)(void*, int, unsigned long long);
+    static attr_fn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuPointerGetAttribute", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<attr_fn>(f);
+        cudaGetLastError();
+    });
+    if (!fn) return false;
+    unsigned long long start = 0; size_t size = 0;
+    const int kRangeStart = 11, kRangeSize = 12;      // CU_POINTER_ATTRIBUTE_RANGE_START_ADDR / _RANGE_SIZE
+    if (fn(&start, kRangeStart, (unsigned long long)lo) != 0 || fn(&size, kRangeSize, (unsigned long long)lo) != 0) return false;
+    if (hi > start + size) return false;
+    *range_lo = (uintptr_t)start; *range_hi = (uintptr_t)(start + size);
+    return true;
+}
+
 int pipe_grow(char** ptr, size_t* have, size_t need, cudaStream_t drain) {
     if (*have >= need) return CTCB_OK;
     if (drain) cudaStreamSynchronize(drain);
@@ -781,7 +771,9 @@ int ctcb_pipe_submit(ctcb_pipe_t* p, const ctcb_problem_t* hp, int64_t* ticket) 
             lo = b < lo ? b : lo; hi = b + a.n > hi ? b + a.n : hi;
             sum += a.n;
         }
-    const bool one_copy = hi - lo <= sum + 5 * 4096;
+    // one copy over the whole span only when the span is one allocation (checked with the driver once per arena)
+    bool one_copy = hi - lo <= sum + 5 * 4096;
+    if (one_copy && !(lo >= p->arena_lo && hi <= p->arena_hi)) one_copy = same_allocation(lo, hi, &p->arena_lo, &p->arena_hi);
     size_t in_need = 0;
     const size_t skew = lo % 256;            // device addresses congruent to the host's mod 256 (vector loads)
     if (one_copy) {
@@ -801,56 +793,15 @@ int ctcb_pipe_submit(ctcb_pipe_t* p, const ctcb_problem_t* hp, int64_t* ticket) 
     if (int rc = pipe_grow(&sl.out, &sl.out_bytes, o, nullptr)) return rc;
     if (int rc = pipe_grow(reinterpret_cast<char**>(&p->ws), &p->ws_bytes, ws_need, p->s_comp)) return rc;
 #define COPY_TRY(expr) do { if ((expr) != cudaSuccess) return fail(CTCB_MEMOPS_FAILED, "%s: %s", #expr, cudaGetErrorString(cudaGetLastError())); } while (0)
-    // Utterance-major logits in page-locked memory with explicit lengths: the GPU pulls the valid frames itself
-    // (k_pull_valid) and the padded ones stay where they are; everything else -- and every other case -- is copied.
-    void* pull_src = nullptr;
-    {
-        const char* ep = getenv("CTCB_PIPE_PULL");
-        // measured at cfg2 and NOT faster: 2.37 MB pulled in 102 us (23 GB/s of SM loads over PCIe) against 2.96 MB
-        // copied in 68.7 us (43 GB/s by the copy engine) -- so it is opt-in: CTCB_PIPE_PULL=1
-        if (ntc && hp->data_lengths && ep && atoi(ep) != 0) {
-            if (cudaHostGetDevicePointer(&pull_src, const_cast<float*>(hp->logits), 0) != cudaSuccess) { cudaGetLastError(); pull_src = nullptr; }
-        }
-    }
     int64_t moved = 0;
-    if (one_copy && !pull_src) {
+    if (one_copy) {
         COPY_TRY(cudaMemcpyAsync(sl.in + skew, reinterpret_cast<const void*>(lo), hi - lo, cudaMemcpyHostToDevice, p->s_copy));
         moved += (int64_t)(hi - lo);
-    } else if (one_copy) {
-        uintptr_t lo2 = UINTPTR_MAX, hi2 = 0;
-        for (int k = 1; k < 5; ++k)
-            if (in[k].n) {
-                const uintptr_t b = reinterpret_cast<uintptr_t>(in[k].h);
-                lo2 = b < lo2 ? b : lo2; hi2 = b + in[k].n > hi2 ? b + in[k].n : hi2;
-            }
-        if (hi2 > lo2) {
-            COPY_TRY(cudaMemcpyAsync(sl.in + skew + (lo2 - lo), reinterpret_cast<const void*>(lo2), hi2 - lo2, cudaMemcpyHostToDevice, p->s_copy));
-            moved += (int64_t)(hi2 - lo2);
-        }
     } else {
-        for (int k = pull_src ? 1 : 0; k < 5; ++k)
+        for (int k = 0; k < 5; ++k)
             if (in[k].n) { COPY_TRY(cudaMemcpyAsync(sl.in + in[k].off, in[k].h, in[k].n, cudaMemcpyHostToDevice, p->s_copy)); moved += (int64_t)in[k].n; }
     }
-    if (pull_src) {
-        long long frames = 0;                                         // bytes pulled: counted from the host's own lengths
-        for (int b = 0; b < B; ++b) {
-            long long t = 0;
-            switch (hp->data_lengths_dtype) {
-                case CTCB_I32: t = static_cast<const int32_t*>(hp->data_lengths)[b]; break;
-                case CTCB_I64: t = static_cast<const int64_t*>(hp->data_lengths)[b]; break;
-                case CTCB_F32: t = (long long)static_cast<const float*>(hp->data_lengths)[b]; break;
-                default: t = (long long)static_cast<const double*>(hp->data_lengths)[b]; break;
-            }
-            frames += t < 0 ? 0 : (t > T ? T : t);
-        }
-        moved += frames * V * (int64_t)sizeof(float);
-        const int chunks = (int)((((size_t)T * V / 4) + 256 * 16 - 1) / (256 * 16));   // ~16 vector loads per thread
-        ctcb::k_pull_valid<<<dim3(chunks < 1 ? 1 : (chunks > 64 ? 64 : chunks), B), 256, 0, p->s_copy>>>(
-            static_cast<const float*>(pull_src), reinterpret_cast<float*>(sl.in + in[0].off), sl.in + in[2].off,
-            hp->data_lengths_dtype, T, V, hp->logits_stride_b);
-        COPY_TRY(cudaGetLastError());
-    }
-    p->last_h2d = moved; p->last_pulled = pull_src ? 1 : 0;
+    p->last_h2d = moved;
     if (hp->loss_sum) COPY_TRY(cudaMemcpyAsync(sl.out + o_sum, hp->loss_sum, sizeof(double), cudaMemcpyHostToDevice, p->s_copy));
     COPY_TRY(cudaEventRecord(sl.ev_in, p->s_copy));
     COPY_TRY(cudaStreamWaitEvent(p->s_comp, sl.ev_in, 0));
@@ -881,7 +832,7 @@ int ctcb_pipe_submit(ctcb_pipe_t* p, const ctcb_problem_t* hp, int64_t* ticket) 
 int ctcb_pipe_last_h2d_bytes(ctcb_pipe_t* p, int64_t* bytes, int32_t* pulled) {
     if (!p) return fail(CTCB_INVALID_VALUE, "pipe is NULL");
     if (bytes) *bytes = p->last_h2d;
-    if (pulled) *pulled = p->last_pulled;
+    if (pulled) *pulled = 0;        // kept in the signature: the library always copies (host entries)
     return CTCB_OK;
 }
 
@@ -915,15 +866,23 @@ int ctcb_scale_rows(float* grad, int64_t stride_t, int64_t stride_b, int32_t T, 
 int ctcb_greedy_decode(const float* logits, int64_t stride_t, int64_t stride_b, const void* data_lengths,
                        int32_t data_lengths_dtype, int32_t T, int32_t B, int32_t V, int32_t blank,
                        int32_t* out_tokens, int32_t* out_lengths, void* stream) {
+    return ctcb_greedy_decode_unk(logits, stride_t, stride_b, data_lengths, data_lengths_dtype, T, B, V, blank, -1,
+                                  out_tokens, out_lengths, stream);
+}
+
+int ctcb_greedy_decode_unk(const float* logits, int64_t stride_t, int64_t stride_b, const void* data_lengths,
+                           int32_t data_lengths_dtype, int32_t T, int32_t B, int32_t V, int32_t blank, int32_t unk,
+                           int32_t* out_tokens, int32_t* out_lengths, void* stream) {
     if (!logits || !out_tokens || !out_lengths) return fail(CTCB_INVALID_VALUE, "NULL argument");
     if (T <= 0 || B <= 0 || V <= 0) return fail(CTCB_INVALID_VALUE, "bad shape");
+    if (unk >= V) return fail(CTCB_INVALID_VALUE, "unk %d outside the vocabulary (V=%d; -1 = no <unk> rule)", unk, V);
     if (!is_device_ptr(logits) || !is_device_ptr(out_tokens)) return fail(CTCB_INVALID_VALUE, "buffers must be CUDA device memory");
-    const size_t smem = sizeof(int) * (size_t)T;
+    const size_t smem = 2 * sizeof(int) * (size_t)T;
     if (smem > 200 * 1024) return fail(CTCB_UNSUPPORTED, "T=%d too long for the decode kernel", T);
     if (smem > 48 * 1024)
         CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(ctcb::k_greedy_decode), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ctcb::k_greedy_decode<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(logits, stride_t, stride_b, data_lengths,
-                                                                                data_lengths_dtype, T, B, V, blank,
+                                                                                data_lengths_dtype, T, B, V, blank, unk < 0 ? -1 : unk,
                                                                                 out_tokens, out_lengths);
     CUDA_TRY(cudaGetLastError());
     return CTCB_OK;

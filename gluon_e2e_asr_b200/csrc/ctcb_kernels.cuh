@@ -42,7 +42,8 @@ constexpr double kLn2 = 0.6931471805599453094;
 constexpr float kMinLog2 = -100.0f;    // clamp of one frame's log2-probability (7.9e-31)
 constexpr int kMaxStages = 16;         // emission ring depth (blocks of kG frames), at most
 
-enum : int { UTT_INFEASIBLE = 1, UTT_BAD_LABEL = 2, UTT_LEN_CLAMPED = 4 };
+enum : int { UTT_INFEASIBLE = 1, UTT_BAD_LABEL = 2, UTT_LEN_CLAMPED = 4, UTT_WIDE_LOGITS = 8 };
+constexpr long long kSpinLimit = 4000000000LL;   // clocks (~2 s) a gradient CTA waits for the recursion kernel before giving up
 enum : int { DT_I32 = 0, DT_I64 = 1, DT_F32 = 2, DT_F64 = 3 };
 
 struct Problem {          // device view of ctcb_problem_t
@@ -72,12 +73,12 @@ struct Workspace {        // carved out of the caller's workspace by the host (c
     int2* oA;                         // (B, NB, NW*PW) exponent offsets {blank, label} valid for frame block n
     int2* oB;
     int* gprog;                       // (B, 4) {frame blocks whose history is complete: alpha walker, beta walker;
-                                      //   metadata ready (Tb, Lb, flags, rank, dl, nd), twice: one word per reader
-                                      //   class}: published with release/gpu scope, polled by the gradient CTAs
-                                      //   (and, when k_emit runs concurrently, by the walkers)
-    int* eprog;                       // (B, NB) emission block written (k_emit concurrent with the walkers only)
-    int ew;                           // k_emit runs concurrently with (and is launched after) k_walk
+                                      //   metadata ready (Tb, Lb, flags, rank, dl, nd)}: published with release/gpu
+                                      //   scope, polled by the gradient CTAs
     int Lp, W, NB, dense, P, NW;      // PW = 32*P pairs per walker warp
+    int stamp;                        // nonzero hash of the call's shape and layout choices: the value of the
+                                      //   "metadata ready" progress word, checked by the gradient CTAs (a workspace
+                                      //   that no matching forward call filled is an error, not a hang)
     int fused;                        // emissions made by the walkers' producer warps (no k_emit, no E)
 };
 
@@ -178,14 +179,8 @@ __global__ void __launch_bounds__(NQ < 0 ? 256 : 128) k_emit(Problem p, Workspac
     __shared__ int s_L, s_rep, s_flags;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr bool STAGED = NQ < 0;
-    // Concurrent with the walkers (launched after them as a programmatic dependent): CTAs are dispatched
-    // utterance-fastest, the metadata CTAs first, then the frame blocks of every utterance from both ends
-    // towards the middle -- the order in which the alpha and the beta walker consume them; each block is
-    // published in Workspace::eprog.
-    const bool ew = STAGED && w.ew != 0;
-    if (STAGED) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    const int b = ew ? blockIdx.x : blockIdx.y;
-    const int xi = ew ? (int)blockIdx.y - 1 : (int)blockIdx.x;
+    const int b = blockIdx.y;
+    const int xi = (int)blockIdx.x;
     constexpr int NT = STAGED ? 256 : 128;        // staged rows: 8 warps, one row each
     float* srow = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(slab) + emit_slab_bytes(w.Lp));   // kG rows of V floats
     uint64_t* rbar = reinterpret_cast<uint64_t*>(srow + (size_t)kG * p.V);
@@ -211,12 +206,8 @@ __global__ void __launch_bounds__(NQ < 0 ? 256 : 128) k_emit(Problem p, Workspac
         __syncthreads();
         L = s_L;
     }
-    const bool meta_cta = ew ? xi < 0 : blockIdx.x == gridDim.x - 1;       // one extra CTA per utterance: metadata only
-    int sblk = xi;
-    if (ew && !meta_cta) {
-        const int NQb = (Tb + kG - 1) / kG;
-        sblk = xi < NQb ? ((xi & 1) ? NQb - 1 - (xi >> 1) : (xi >> 1)) : w.NB;
-    }
+    const bool meta_cta = blockIdx.x == gridDim.x - 1;       // one extra CTA per utterance: metadata only
+    const int sblk = xi;
     if (STAGED && !meta_cta && lane == 0 && sblk * kG < Tb) {
         // this warp's row: requested before anything else, consumed below
         const int t = sblk * kG + warp;
@@ -281,20 +272,21 @@ __global__ void __launch_bounds__(NQ < 0 ? 256 : 128) k_emit(Problem p, Workspac
             const int ncol = w.dense ? p.V : L + 1;
             const int nval = min(kG, Tb - t0);
             double* eblk = w.E + ((size_t)b * w.NB + blk) * w.W * kEC;
+            bool floored = false;
             for (int col = tid; col < ncol; col += NT) {
                 const int v = w.dense ? col : (col == 0 ? p.blank : slab[col - 1]);
                 double y[kG];
 #pragma unroll
-                for (int j = 0; j < kG; ++j)
-                    y[j] = j < nval ? (double)fast_ex2(fmaxf((srow[(size_t)j * p.V + v] - s_mx[j]) * kLog2e, kMinLog2)) : 0.0;
+                for (int j = 0; j < kG; ++j) {
+                    const float l2 = (srow[(size_t)j * p.V + v] - s_mx[j]) * kLog2e;
+                    floored |= j < nval && l2 < kMinLog2;
+                    y[j] = j < nval ? (double)fast_ex2(fmaxf(l2, kMinLog2)) : 0.0;
+                }
                 double2* dst = reinterpret_cast<double2*>(eblk + (size_t)col * kEC);
 #pragma unroll
                 for (int j = 0; j < kG; j += 2) dst[j / 2] = make_double2(y[j], y[j + 1]);
             }
-            if (ew) {
-                __syncthreads();
-                if (tid == 0) { __threadfence(); st_release_gpu(w.eprog + (size_t)b * w.NB + blk, 1); }
-            }
+            if (floored && p.status) atomicOr(p.status + b, UTT_WIDE_LOGITS);
         } else if (NQ > 0) {
             constexpr int NQ1 = NQ > 0 ? NQ : 1;
             constexpr int F = NQ1 >= 16 ? 1 : (NQ1 >= 8 ? 2 : (NQ1 >= 4 ? 4 : 8));
@@ -357,6 +349,7 @@ __global__ void __launch_bounds__(NQ < 0 ? 256 : 128) k_emit(Problem p, Workspac
                         for (int f = 0; f < F; ++f) {
                             const bool valid = t0 + jf + f < Tb;
                             const float xv = valid ? __ldg(rows + (jf + f) * p.st_t + v) : 0.0f;
+                            if (valid && (xv - mx[f]) * kLog2e < kMinLog2 && p.status) atomicOr(p.status + b, UTT_WIDE_LOGITS);
                             eblk[(size_t)col * kEC + jf + f] = valid ? (double)fast_ex2(fmaxf((xv - mx[f]) * kLog2e, kMinLog2)) : 0.0;
                         }
                     }
@@ -402,6 +395,9 @@ __global__ void __launch_bounds__(NQ < 0 ? 256 : 128) k_emit(Problem p, Workspac
             for (int j = 0; j < kG; j += 2) {
                 const double y0 = t0 + j < Tb ? (double)fast_ex2(fmaxf((xv[j] - mxs[j]) * kLog2e, kMinLog2)) : 0.0;
                 const double y1 = t0 + j + 1 < Tb ? (double)fast_ex2(fmaxf((xv[j + 1] - mxs[j + 1]) * kLog2e, kMinLog2)) : 0.0;
+                if (p.status && ((t0 + j < Tb && (xv[j] - mxs[j]) * kLog2e < kMinLog2) ||
+                                 (t0 + j + 1 < Tb && (xv[j + 1] - mxs[j + 1]) * kLog2e < kMinLog2)))
+                    atomicOr(p.status + b, UTT_WIDE_LOGITS);
                 dst[j / 2] = make_double2(y0, y1);
             }
         }
@@ -447,17 +443,9 @@ __global__ void __launch_bounds__(NQ < 0 ? 256 : 128) k_emit(Problem p, Workspac
         if (Tb <= 0 || L + s_rep > Tb) flags |= UTT_INFEASIBLE;
         w.Tb[b] = Tb; w.Lb[b] = L; w.flags[b] = flags;
         w.nd[b] = s_nd; dl[s_nd] = make_int2(-1, L);
-        if (p.status) p.status[b] = flags;
+        if (p.status && flags) atomicOr(p.status + b, flags);   // zeroed by the host before the call; frame CTAs OR their bits in
         if (flags & UTT_INFEASIBLE) p.loss[b] = 0.0f;   // defined behaviour, SURVEY 7.3-6
-        if (ew) {      // the walkers reset the progress words before this grid could exist, and wait for these
-            __threadfence();
-            st_release_gpu(w.gprog + 4 * b + 2, 1);
-            st_release_gpu(w.gprog + 4 * b + 3, 1);
-            // the stream's next kernel must see what the walkers write last: this grid stays open until they are done
-            if (b == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
-        } else {
-            w.gprog[4 * b] = 0; w.gprog[4 * b + 1] = 0; w.gprog[4 * b + 2] = 1;
-        }
+        w.gprog[4 * b] = 0; w.gprog[4 * b + 1] = 0; w.gprog[4 * b + 2] = w.stamp;
     }
 }
 
@@ -663,6 +651,7 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
         };
         float cur[CPL], nxt[CPL];
         double ls = 0.0;
+        bool floored = false;
         int n = q;
         if (n < NQ) load_blk(n, cur);
 #pragma unroll 1
@@ -680,6 +669,8 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
             for (int i = 0; i < CPL; ++i) {                            // rows past T_b are all -inf: keep NaN out
                 e[i] = valid ? fast_ex2((cur[i] - mx) * kLog2e) : 0.0f;
                 sm += e[i];
+                // an emission below the floor (any symbol of a valid frame): reported, UTT_WIDE_LOGITS
+                if (DIR == 0) floored |= valid && i < cpl && col0 + i < V && e[i] < kMinProb;
             }
             sm += __shfl_xor_sync(FULL, sm, 1);
             sm += __shfl_xor_sync(FULL, sm, 2);
@@ -700,6 +691,7 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
 #pragma unroll
             for (int i = 0; i < CPL; ++i) cur[i] = nxt[i];
         }
+        if (DIR == 0 && p.status && __any_sync(FULL, floored) && lane == 0) atomicOr(p.status + b, UTT_WIDE_LOGITS);
         return;
     }
     if (FUSED && warp == NW + kFusedProducers) {
@@ -735,7 +727,7 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
                 w.nd[b] = nd; w.Tb[b] = Tb; w.Lb[b] = Lb; w.flags[b] = uflags;
             }
             __syncwarp();
-            if (lane == 0) st_release_gpu(w.gprog + 4 * b + 2, 1);
+            if (lane == 0) st_release_gpu(w.gprog + 4 * b + 2, w.stamp);
         }
         if (HIST && lane == 0) {
             // the last walker warp's group count (shared memory) -> global progress for the gradient CTAs
@@ -760,39 +752,6 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
             tma_load_1d(smem_raw + (size_t)st * stage_bytes, Eb + (size_t)blk * W * kEC, stage_bytes, &full[st]);
         };
         const int npro = min(NS, NQ);
-        if (w.ew) {
-            // k_emit runs concurrently: a block is requested once its flag is up; the alpha CTA's lanes add the
-            // block's log2(softmax denominator) terms as they go (lane = t mod 32, increasing t: the order of the
-            // serial schedule below, so the loss carries the same bits)
-            const int* ep = w.eprog + (size_t)b * w.NB;
-            double s = 0.0;
-            auto acquire = [&](int n) {
-                const int blk = DIR ? NQ - 1 - n : n;
-                while (ld_acquire_gpu(ep + blk) == 0) __nanosleep(100);
-                if (DIR == 0) {
-                    const int j = (lane - blk * kG) & 31, t = blk * kG + j;
-                    if (j < kG && t < Tb) s += (double)__ldcg(&w.fr[(size_t)b * a.T + t].y);
-                }
-                if (lane == 0) asm volatile("fence.proxy.async;" ::: "memory");
-            };
-            for (int n = 0; n < npro; ++n) { acquire(n); if (lane == 0) issue(n, n); }
-            int* gp = HIST ? w.gprog + 4 * b + DIR : nullptr;
-            int st = 0; uint32_t par = 0;
-            for (int n = 0; n < NQ; ++n) {
-                mbar_wait_relaxed(&empty[st], par);                   // group n is complete, its stage is free
-                const int sn = st + 1 == NS ? 0 : st + 1; const uint32_t pn = st + 1 == NS ? par ^ 1 : par;
-                if (HIST && lane == 0 && (n + 1 == NQ || !mbar_test(&empty[sn], pn))) st_release_gpu(gp, n + 1);
-                if (n + NS < NQ) { acquire(n + NS); if (lane == 0) issue(n + NS, st); }
-                st = sn; par = pn;
-            }
-            if (DIR == 0) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1)
-                    s += __hiloint2double(__shfl_xor_sync(FULL, __double2hiint(s), o), __shfl_xor_sync(FULL, __double2loint(s), o));
-                if (lane == 0) { sts_f64(lsum, s); sts_release(lsum + 8, 1); }
-            }
-            return;
-        }
         if (lane == 0) for (int n = 0; n < npro; ++n) issue(n, n);
         if (DIR == 0) {                         // sum_t log2(softmax denominator), fixed order
             double s = 0.0;
@@ -1111,22 +1070,7 @@ __global__ void __launch_bounds__((NW + (FUSED ? kFusedProducers + 1 : 1)) * 32)
     if (!FUSED) {
         // the gradient kernel may start as soon as every walker CTA is resident: its CTAs wait per
         // frame block on the progress this kernel publishes (Workspace::gprog)
-        if (a.w.ew) {
-            // this grid is the first of the call: the progress words start at 0 before k_emit (the dependent
-            // launched next) or k_grad (launched after it) can exist; then wait for k_emit's metadata CTA
-            if (blockIdx.y == 0) for (int j = threadIdx.x; j < a.w.NB; j += blockDim.x) a.w.eprog[(size_t)b * a.w.NB + j] = 0;
-            if (threadIdx.x == 0) {
-                a.w.gprog[4 * b + blockIdx.y] = 0;
-                a.w.gprog[4 * b + 2 + blockIdx.y] = 0;
-            }
-            __threadfence();
-            __syncthreads();
-        }
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-        if (a.w.ew) {
-            if (threadIdx.x == 0) { while (ld_acquire_gpu(a.w.gprog + 4 * b + 2 + blockIdx.y) == 0) __nanosleep(200); }
-            __syncthreads();
-        }
         const int flags = __ldcg(a.w.flags + b), Tb = __ldcg(a.w.Tb + b), Lb = __ldcg(a.w.Lb + b);
         if (flags & UTT_INFEASIBLE) return;
         if (blockIdx.y == 0) walk_dir<P, NW, 0, HIST, false>(a, smem_raw, Tb, Lb, flags);
@@ -1199,7 +1143,7 @@ __global__ void __launch_bounds__((NW + (FUSED ? kFusedProducers + 1 : 1)) * 32)
         if (flags & UTT_INFEASIBLE) {
             p.loss[b] = 0.0f;                        // defined behaviour, SURVEY 7.3-6
             w.Tb[b] = Tb; w.Lb[b] = L; w.flags[b] = flags; w.nd[b] = 0;
-            st_release_gpu(w.gprog + 4 * b + 2, 1);
+            st_release_gpu(w.gprog + 4 * b + 2, w.stamp);
         } else if (!HIST) {
             w.Tb[b] = Tb; w.Lb[b] = L; w.flags[b] = flags;
         }
@@ -1364,8 +1308,26 @@ __global__ void __launch_bounds__(XQ < 0 ? 256 : 128, XQ < 0 ? (CH == 16 ? 2 : 3
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // the utterance's metadata is written by k_emit (complete before this grid exists) or, in the
     // fused path, by the concurrently running alpha walker CTA
-    if (tid == 0) { while (ld_acquire_gpu(w.gprog + 4 * b + 2) == 0) __nanosleep(256); }
+    // Both waits are bounded: a workspace that no matching forward call filled (another shape, other layout
+    // switches, a forward that failed) makes this CTA write NaN into its rows and leave instead of hanging the GPU.
+    __shared__ int s_ok;
+    if (tid == 0) {
+        const long long t0 = clock64();
+        int v;
+        while ((v = ld_acquire_gpu(w.gprog + 4 * b + 2)) == 0 && clock64() - t0 < kSpinLimit) __nanosleep(256);
+        s_ok = v == w.stamp;
+    }
     __syncthreads();
+    if (!s_ok) {
+        for (int j = warp; j < kG; j += (XQ < 0 ? 8 : 4)) {
+            const int t = blockIdx.y * kG + j;
+            if (t < p.T) {
+                float* grow = p.grad + b * p.gst_b + (long long)t * p.gst_t;
+                for (int v = lane; v < p.V; v += 32) grow[v] = __int_as_float(0x7fc00000);
+            }
+        }
+        return;
+    }
     const int Tb = __ldcg(w.Tb + b), Lb = __ldcg(w.Lb + b);
     const bool infeasible = (__ldcg(w.flags + b) & UTT_INFEASIBLE) != 0;
     // CTAs are dispatched utterance-fastest, and per utterance in the order the walkers complete
@@ -1407,11 +1369,27 @@ __global__ void __launch_bounds__(XQ < 0 ? 256 : 128, XQ < 0 ? (CH == 16 ? 2 : 3
         if (tid == 0) {
             // block n is frame block n of the alpha walker and block NQ-1-n of the beta walker
             const int* gp = w.gprog + 4 * b;
-            while (ld_acquire_gpu(gp) < blk + 1) __nanosleep(256);
-            while (ld_acquire_gpu(gp + 1) < NQ - blk) __nanosleep(256);
+            const long long t0 = clock64();
+            while (ld_acquire_gpu(gp) < blk + 1 && clock64() - t0 < kSpinLimit) __nanosleep(256);
+            while (ld_acquire_gpu(gp + 1) < NQ - blk && clock64() - t0 < kSpinLimit) __nanosleep(256);
+            if (clock64() - t0 >= kSpinLimit) s_ok = 0;
         }
     }
     __syncthreads();
+    if (!s_ok) {                                   // the recursion kernel never got there: NaN rows, no hang
+        if (STAGED && lane == 0) {
+#pragma unroll
+            for (int f = 0; f < FPW; ++f) if (t_first + warp * FPW + f < Tb) mbar_wait(rbar + warp * FPW + f, 0);   // rows in flight land first
+        }
+        for (int j = warp; j < kG; j += NT / 32) {
+            const int t = t_first + j;
+            if (t < p.T) {
+                float* grow = p.grad + b * p.gst_b + (long long)t * p.gst_t;
+                for (int v = lane; v < p.V; v += 32) grow[v] = __int_as_float(0x7fc00000);
+            }
+        }
+        return;
+    }
 
     const int pairs = 32 * w.P * w.NW;
     const size_t blkoff = (size_t)b * w.NB + blk;
@@ -1631,38 +1609,6 @@ __global__ void __launch_bounds__(XQ < 0 ? 256 : 128, XQ < 0 ? (CH == 16 ? 2 : 3
 }
 
 // ---------------------------------------------------------------------------------------
-// k_pull_valid: the host->device step of the prefetching host entry for utterance-major (NTC) logits in
-// page-locked host memory.  The GPU reads the host buffer itself (zero-copy loads over PCIe) and takes only
-// the VALID frames of every utterance -- rows t < T_b, one contiguous run per utterance -- so the padded
-// frames of a length-bucketed batch (a fifth of cfg2's bytes) never cross the bus.  grid (chunks, B), 256
-// threads, 16-byte loads, four in flight per thread; lengths come from the device copy made just before.
-// ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_pull_valid(const float* __restrict__ src, float* __restrict__ dst, const void* data_len,
-                                                    int data_len_dtype, int T, int V, long long st_b) {
-    const int b = blockIdx.y;
-    long long t64 = load_as_int(data_len, data_len_dtype, b);
-    t64 = t64 < 0 ? 0 : (t64 > T ? T : t64);
-    const long long n = t64 * V;                                     // valid floats of this utterance
-    const float* s = src + (long long)b * st_b;
-    float* d = dst + (long long)b * st_b;
-    const long long stride = (long long)gridDim.x * blockDim.x, i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if ((((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
-        const long long n4 = n >> 2;
-        const float4* s4 = reinterpret_cast<const float4*>(s);
-        float4* d4 = reinterpret_cast<float4*>(d);
-        long long i = i0;
-        for (; i + 3 * stride < n4; i += 4 * stride) {
-            const float4 a0 = s4[i], a1 = s4[i + stride], a2 = s4[i + 2 * stride], a3 = s4[i + 3 * stride];
-            d4[i] = a0; d4[i + stride] = a1; d4[i + 2 * stride] = a2; d4[i + 3 * stride] = a3;
-        }
-        for (; i < n4; i += stride) d4[i] = s4[i];
-        for (long long j = (n4 << 2) + i0; j < n; j += stride) d[j] = s[j];
-    } else {
-        for (long long j = i0; j < n; j += stride) d[j] = s[j];
-    }
-}
-
-// ---------------------------------------------------------------------------------------
 // k_scale_rows: grad[b,t,:] *= head[b] in place.  Row a8 (the operator's Backward: the
 // gradient stored by Forward times the head gradient) for callers that ran the fused
 // forward+gradient with head = 1.  grid (ceil(T*ceil(V/128)... ) flat over (b, t) rows.
@@ -1679,38 +1625,47 @@ __global__ void __launch_bounds__(256) k_scale_rows(float* grad, long long gst_t
 }
 
 // ---------------------------------------------------------------------------------------
-// k_greedy_decode: grid B, block 256.  train_ctc_ce.py:149-160 (next-row scope).
+// k_greedy_decode: grid B, block 256.  train_ctc_ce.py:149-160 and, with unk >= 0, decode_ctc.py:123-143
+// (next-row scope): per frame the best symbol (ties: lowest index) and -- for the <unk> rule -- the second
+// best; the symbol of frame j is the best one, or the second best when the best is `unk`; it is kept when
+// it differs from the RAW best symbol of frame j-1 (the reference compares against trans[j-1], not against
+// the substituted symbol) and is not the blank.
 // ---------------------------------------------------------------------------------------
+struct Top2 { float v1; int i1; float v2; int i2; };
+__device__ __forceinline__ bool better(float va, int ia, float vb, int ib) { return va > vb || (va == vb && ia < ib); }
+__device__ __forceinline__ void top2_push(Top2& t, float v, int i) {
+    if (better(v, i, t.v1, t.i1)) { t.v2 = t.v1; t.i2 = t.i1; t.v1 = v; t.i1 = i; }
+    else if (better(v, i, t.v2, t.i2)) { t.v2 = v; t.i2 = i; }
+}
 __global__ void __launch_bounds__(256) k_greedy_decode(const float* logits, long long st_t, long long st_b,
                                                        const void* data_len, int dl_dtype, int T, int B, int V,
-                                                       int blank, int* out_tokens, int* out_len) {
-    extern __shared__ int path[];                 // T ints
+                                                       int blank, int unk, int* out_tokens, int* out_len) {
+    extern __shared__ int path[];                 // T ints: the raw best symbol; T more: the symbol after the <unk> rule
     __shared__ int s_scan[8];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     long long n64 = data_len ? load_as_int(data_len, dl_dtype, b) : T;
     const int n = (int)(n64 < 0 ? 0 : (n64 > T ? T : n64));
+    int* sym = path + T;
     for (int t = warp; t < n; t += 8) {
         const float* row = logits + b * st_b + t * st_t;
-        float best = -INFINITY; int bi = 0x7fffffff;
-        for (int v = lane; v < V; v += 32) {
-            const float x = __ldg(row + v);
-            if (x > best || (x == best && v < bi)) { best = x; bi = v; }
-        }
+        Top2 tp{-INFINITY, 0x7fffffff, -INFINITY, 0x7fffffff};
+        for (int v = lane; v < V; v += 32) top2_push(tp, __ldg(row + v), v);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            const float ov1 = __shfl_xor_sync(0xffffffffu, tp.v1, o), ov2 = __shfl_xor_sync(0xffffffffu, tp.v2, o);
+            const int oi1 = __shfl_xor_sync(0xffffffffu, tp.i1, o), oi2 = __shfl_xor_sync(0xffffffffu, tp.i2, o);
+            top2_push(tp, ov1, oi1);
+            top2_push(tp, ov2, oi2);
         }
-        if (lane == 0) path[t] = bi;
+        if (lane == 0) { path[t] = tp.i1; sym[t] = (unk >= 0 && tp.i1 == unk && tp.i2 != 0x7fffffff) ? tp.i2 : tp.i1; }
     }
     __syncthreads();
-    // keep[t] = path[t] != blank && (t == 0 || path[t] != path[t-1]); compact in order
+    // keep[t] = sym[t] != blank && (t == 0 || sym[t] != path[t-1]); compact in order
     const int chunk = (n + 255) / 256;
     const int lo = min(tid * chunk, n), hi = min(lo + chunk, n);
     int cnt = 0;
     for (int t = lo; t < hi; ++t) {
-        const int c = path[t];
+        const int c = sym[t];
         cnt += (c != blank && (t == 0 || c != path[t - 1]));
     }
     int incl = cnt;
@@ -1723,7 +1678,7 @@ __global__ void __launch_bounds__(256) k_greedy_decode(const float* logits, long
     int pos = base + incl - cnt;
     int* out = out_tokens + (size_t)b * T;
     for (int t = lo; t < hi; ++t) {
-        const int c = path[t];
+        const int c = sym[t];
         if (c != blank && (t == 0 || c != path[t - 1])) out[pos++] = c;
     }
     if (tid == 255) out_len[b] = base + incl;

@@ -298,9 +298,11 @@ def ctc_loss_and_grad(pred, label, pred_lengths=None, label_lengths=None, head_g
     return loss, grad
 
 
-def greedy_decode(pred, pred_lengths=None, blank=0, layout="NTC"):
+def greedy_decode(pred, pred_lengths=None, blank=0, layout="NTC", unk=None):
     """Greedy CTC decode of train_ctc_ce.py:149-160: argmax over V, collapse repeats, drop
-    blank.  Returns (tokens (B,T) int32 -- prefix valid, lengths (B,) int32) on pred's device."""
+    blank.  ``unk`` (the index of ``<unk>``): decode_ctc.py:120-140's rule -- a frame whose best symbol
+    is ``unk`` takes its second best; the repeat test still compares with the raw best symbol of the
+    previous frame.  Returns (tokens (B,T) int32 -- prefix valid, lengths (B,) int32) on pred's device."""
     pred = _check_data(pred)
     ta, ba = (1, 0) if layout == "NTC" else (0, 1)
     T, B, V = pred.shape[ta], pred.shape[ba], pred.shape[2]
@@ -311,11 +313,12 @@ def greedy_decode(pred, pred_lengths=None, blank=0, layout="NTC"):
     lens = torch.empty((B,), dtype=torch.int32, device=pred.device)
     lib = _lib.load()
     with _on_device(pred.device):
-        rc = lib.ctcb_greedy_decode(pred.data_ptr(), pred.stride(ta), pred.stride(ba),
-                                    pl.data_ptr() if pl is not None else None,
-                                    _DT[pl.dtype] if pl is not None else 0, T, B, V, blank,
-                                    toks.data_ptr(), lens.data_ptr(),
-                                    _stream_ptr(pred.device))
+        rc = lib.ctcb_greedy_decode_unk(pred.data_ptr(), pred.stride(ta), pred.stride(ba),
+                                        pl.data_ptr() if pl is not None else None,
+                                        _DT[pl.dtype] if pl is not None else 0, T, B, V, blank,
+                                        -1 if unk is None else int(unk),
+                                        toks.data_ptr(), lens.data_ptr(),
+                                        _stream_ptr(pred.device))
     _lib.check(rc)
     return toks, lens
 

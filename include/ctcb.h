@@ -49,6 +49,12 @@ typedef enum { CTCB_I32 = 0, CTCB_I64 = 1, CTCB_F32 = 2, CTCB_F64 = 3 } ctcb_dty
 #define CTCB_UTT_INFEASIBLE   1  /* L + repeats > T (or T == 0): loss 0, grad 0 */
 #define CTCB_UTT_BAD_LABEL    2  /* a label was < 0, >= V or == blank: clamped / treated as is */
 #define CTCB_UTT_LEN_CLAMPED  4  /* data_length > T or label_length > Lmax: clamped */
+#define CTCB_UTT_WIDE_LOGITS  8  /* CONTRACT DIFFERENCE from mx.nd.contrib.ctc_loss: an emission of a valid frame lay
+                                  * more than 100 bits (69.3 nats) below the frame's largest softmax numerator and was
+                                  * FLOORED there (small vocabularies: any symbol of the frame; wide ones: a blank or
+                                  * label column of this utterance).  Loss and gradient are then those of the floored
+                                  * lattice (the reference's fp32 log-space operator has its own, lower floor: log y is
+                                  * -inf below e^-103).  Never raised for logit ranges below 69 nats per frame. */
 
 /* One CTC problem = one call of the reference operator (loss.py:134-139).
  * All pointers are DEVICE pointers for ctcb_loss_grad(), HOST pointers for
@@ -137,8 +143,10 @@ int ctcb_loss_grad_host_resident(const ctcb_problem_t* p, int device, float** de
  *                     this batch's kernels.  All pointers of `host_problem` are HOST pointers (page-
  *                     locked for the copies to be asynchronous); they must stay valid and untouched
  *                     until ctcb_pipe_wait(ticket) returns.  p->grad is ignored.  Inputs that lie in
- *                     one host arena (gaps < 4 KB) move in ONE copy.  Submitting when all slots hold
- *                     uncollected batches first waits for the oldest.
+ *                     ONE host allocation (checked with the driver: cuPointerGetAttribute range
+ *                     queries, once per arena) with gaps < 4 KB move in one copy; separately
+ *                     allocated arrays are copied one by one, whatever their addresses.  Submitting
+ *                     when all slots hold uncollected batches first waits for the oldest.
  *   ctcb_pipe_wait    blocks until the ticket's batch is complete: the loss is in host_problem->loss,
  *                     *dev_grad (optional) is the device address of its gradient, in the logits'
  *                     layout, valid until `depth` more batches have been submitted.
@@ -148,11 +156,9 @@ int ctcb_pipe_create(int device, int depth, ctcb_pipe_t** out);
 int ctcb_pipe_submit(ctcb_pipe_t* pipe, const ctcb_problem_t* host_problem, int64_t* ticket);
 int ctcb_pipe_wait(ctcb_pipe_t* pipe, int64_t ticket, float** dev_grad);
 int ctcb_pipe_destroy(ctcb_pipe_t* pipe);
-/* bytes the last ctcb_pipe_submit moved host -> device.  *pulled = 1 when the logits did not go through a
- * copy: for utterance-major (NTC) logits in page-locked memory with explicit data_lengths the GPU reads
- * the host buffer itself and takes only the valid frames (t < T_b) of every utterance, so the padded
- * frames of a length-bucketed batch never cross PCIe.  Opt-in (CTCB_PIPE_PULL=1): on B200 the SMs' loads
- * over PCIe reach about half the copy engine's rate, so moving a fifth fewer bytes this way is slower. */
+/* bytes the last ctcb_pipe_submit moved host -> device.  *pulled is always 0 (the library always copies:
+ * a kernel that pulled only the valid frames over PCIe was measured slower than the copy engine in
+ * round 1 and removed; the argument stays for ABI stability). */
 int ctcb_pipe_last_h2d_bytes(ctcb_pipe_t* pipe, int64_t* bytes, int32_t* pulled);
 
 /* The operator's Backward for a caller that ran ctcb_loss_grad with head_grad = NULL in its
@@ -168,6 +174,14 @@ int ctcb_greedy_decode(const float* logits, int64_t stride_t, int64_t stride_b,
                        const void* data_lengths, int32_t data_lengths_dtype,
                        int32_t T, int32_t B, int32_t V, int32_t blank,
                        int32_t* out_tokens, int32_t* out_lengths, void* stream);
+/* The same with decode_ctc.py:120-140's <unk> rule: when the best symbol of a frame is `unk` the frame's
+ * symbol is the SECOND best one (ties: lowest index); it is kept when it differs from the raw best symbol
+ * of the previous frame -- the reference compares with trans[j-1], not with the substituted symbol -- and
+ * is not the blank.  unk = -1: no rule (identical to ctcb_greedy_decode). */
+int ctcb_greedy_decode_unk(const float* logits, int64_t stride_t, int64_t stride_b,
+                           const void* data_lengths, int32_t data_lengths_dtype,
+                           int32_t T, int32_t B, int32_t V, int32_t blank, int32_t unk,
+                           int32_t* out_tokens, int32_t* out_lengths, void* stream);
 
 /* Edit distance of each (reference, hypothesis) token pair of a batch: scripts/swbd/wer.py:45-68
  * (`_edit_distance`; next-row scope).  ref (B, max_ref) / hyp (B, max_hyp)
@@ -226,6 +240,16 @@ int ctcb_mailbox_destroy(ctcb_mailbox_t* mailbox);
  * thread enqueued, and the walker configuration it chose. */
 int ctcb_last_launch_count(void);
 int ctcb_last_walk_config(int32_t* pairs_per_lane, int32_t* warps);
+
+/* Tuning / experiment switches (tests and A/B measurements; a training loop never needs them).  Each
+ * is read ONCE from the environment (CTCB_<NAME>, upper case) when the library is first used and can be
+ * changed here; -1 = automatic.  Names: "walk_p", "walk_nw" (state pairs per lane / walker warps),
+ * "walk_stages" (emission ring depth), "overlap" (gradient
+ * kernel concurrent with the recursion kernel: 0/1), "fused" (0: always the k_emit path), "walk_per_sm",
+ * "emit_staged", "grad_staged" (0: register variants for wide vocabularies).  walk_p / walk_nw / fused
+ * are part of the workspace layout: do not change them between ctcb_forward and ctcb_backward. */
+int ctcb_set_option(const char* name, int32_t value);
+int ctcb_get_option(const char* name, int32_t* value);
 
 #ifdef __cplusplus
 }

@@ -244,6 +244,31 @@ def greedy_decode(logits_btv, lengths, blank=0):
     return out
 
 
+def greedy_decode_unk(logits_btv, lengths, unk, blank=0):
+    """Greedy decode with the ``<unk>`` rule of scripts/swbd/decode_ctc.py:120-140, restated loop for
+    loop: ``trans``/``trans2`` are the best and second best symbol of every frame (descending argsort,
+    :125-127; ties here: lowest index first); ``prev = trans[j-1]`` is the RAW best symbol of the
+    previous frame (:133), ``curr = trans[j]`` or ``trans2[j]`` when ``trans[j] == unk`` (:134-136); the
+    symbol is emitted when ``j == 0 or curr != prev`` and it is not the blank (:138-140)."""
+    logits = np.asarray(logits_btv)
+    out = []
+    for b in range(logits.shape[0]):
+        n = int(np.asarray(lengths)[b])
+        order = np.argsort(-logits[b, :n], axis=1, kind="stable")
+        trans, trans2 = order[:, 0], order[:, 1] if logits.shape[2] > 1 else order[:, 0]
+        seq = []
+        for j in range(n):
+            prev = int(trans[j - 1])
+            curr = int(trans[j])
+            if curr == unk:
+                curr = int(trans2[j])
+            if j == 0 or curr != prev:
+                if curr != blank:
+                    seq.append(curr)
+        out.append(seq)
+    return out
+
+
 def split_and_load_slices(n, k):
     """Batch-axis slices of scripts/swbd/utils.py:25-33 (``split_and_load``): k-1 chunks of
     n//k, the remainder on the last device; if n < k everything goes to device 0."""

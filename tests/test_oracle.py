@@ -184,3 +184,18 @@ def test_c_fp64_matches_numpy_at_size():
         assert ok.all() and okc.all()
         np.testing.assert_allclose(lc, lo, rtol=1e-12, atol=1e-11)
         np.testing.assert_allclose(gc, go, rtol=1e-9, atol=1e-12)
+
+
+def test_greedy_decode_unk_rule():
+    """decode_ctc.py:120-140 restated: <unk> -> second best; `prev` stays the raw best of the previous frame."""
+    unk = 3
+    x = np.zeros((1, 7, 5))
+    #        best:  2    unk(2nd 2)  unk(2nd 1)  1    0(blank)  unk(2nd 0)  4
+    best = [2, unk, unk, 1, 0, unk, 4]
+    second = [1, 2, 1, 2, 1, 0, 2]
+    for j, (a, b) in enumerate(zip(best, second)):
+        x[0, j, a] = 5.0; x[0, j, b] = 4.0
+    # j=1: curr=2 vs prev=2 (raw) -> dropped; j=2: curr=1 vs prev=unk -> kept; j=3: curr=1 vs prev=unk -> kept (the
+    # reference compares with the RAW previous symbol, so the repeated 1 is NOT collapsed); j=5: curr=0 blank dropped
+    assert O.greedy_decode_unk(x, [7], unk) == [[2, 1, 1, 4]]
+    assert O.greedy_decode_unk(x, [7], -1) == O.greedy_decode(x, [7])

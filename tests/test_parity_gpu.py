@@ -291,24 +291,104 @@ def test_greedy_decode(dev):
         assert list(toks[b, :lens[b]]) == ref[b]
 
 
-def _env(**kw):
-    """Context manager: set libctcb's debugging switches (read with getenv at every call)."""
-    import contextlib
+def test_greedy_decode_unk_rule(dev):
+    """decode_ctc.py:120-140: <unk> frames take the second-best symbol, the repeat test compares with the
+    RAW best symbol of the previous frame.  Bit-exact against the oracle's loop-for-loop restatement, on
+    logits where <unk> wins a third of the frames (runs of <unk>, <unk> next to its substitute, ties)."""
+    from gluon_e2e_asr_b200 import greedy_decode
+    rng = np.random.default_rng(77)
+    B, T, V, unk = 7, 90, 12, 5
+    x = rng.standard_normal((B, T, V)).astype(np.float32)
+    win = rng.random((B, T)) < 0.35
+    x[win, unk] += 6.0                                       # <unk> is the best symbol on these frames
+    x[0, 10:20, 3] = 4.0; x[0, 10:20, unk] = 9.0             # a run of <unk> over a constant second best
+    x[1, 5, :] = 0.0                                         # an all-ties frame: best 0 (blank), second 1
+    x[2, 30:34, unk] = 7.0; x[2, 30:34, 0] = 6.0             # <unk> over blank: substituted symbol is the blank
+    lens = np.array([90, 77, 90, 1, 0, 33, 64], np.float32)
+    t = torch.tensor(x, device=dev)
+    for layout, xt in (("NTC", t), ("TNC", t.transpose(0, 1).contiguous())):
+        toks, n = greedy_decode(xt, torch.tensor(lens, device=dev), unk=unk, layout=layout)
+        ref = O.greedy_decode_unk(x, lens, unk)
+        toks, n = toks.cpu().numpy(), n.cpu().numpy()
+        for b in range(B):
+            assert list(toks[b, :n[b]]) == ref[b], (layout, b)
+    # unk=None is the plain decode
+    toks, n = greedy_decode(t, torch.tensor(lens, device=dev))
+    ref = O.greedy_decode(x, lens)
+    for b in range(B):
+        assert list(toks.cpu().numpy()[b, :n.cpu().numpy()[b]]) == ref[b]
 
-    @contextlib.contextmanager
-    def cm():
-        old = {k: os.environ.get(k) for k in kw}
-        try:
-            for k, v in kw.items():
-                os.environ[k] = str(v)
-            yield
-        finally:
-            for k, v in old.items():
-                if v is None:
-                    os.environ.pop(k, None)
-                else:
-                    os.environ[k] = v
-    return cm()
+
+def test_wide_logit_ranges_are_floored_and_reported(dev):
+    """Emissions are floored at 2^-100 (69.3 nats) below the frame's largest softmax numerator -- a documented
+    contract difference (include/ctcb.h CTCB_UTT_WIDE_LOGITS).  Inside that range: parity with the oracle and no
+    status bit, up to gaps of 65 nats.  Beyond it: the bit is raised, results stay finite, the loss is the floored
+    lattice's (never above the exact one), for the small-vocabulary and the wide-vocabulary path."""
+    from gluon_e2e_asr_b200 import _lib, ctc_loss_and_grad
+    for V in (46, 300):
+        B, T, L = 4, 40, 8
+        d = make_batch(B, T, V, L, seed=90 + V)
+        rng = np.random.default_rng(V)
+        # (a) gaps up to 65 nats: one confident symbol per frame, the rest 55..65 nats below
+        x = (rng.uniform(-65.0, -55.0, (B, T, V))).astype(np.float32)
+        hot = rng.integers(0, V, (B, T))
+        np.put_along_axis(x, hot[..., None], 0.0, axis=2)
+        d["pred"] = x
+        t = _to(dev, d)
+        st = torch.full((B,), -1, dtype=torch.int32, device=dev)
+        loss, grad = ctc_loss_and_grad(t["pred"], t["label"], t["pred_lengths"], t["label_lengths"], status=st)
+        lo, go, ok = _oracle(d)
+        _check(loss.cpu().numpy(), grad.cpu().numpy(), lo, go, "gaps <= 65 nats, V=%d" % V)
+        assert (st.cpu().numpy() & _lib.UTT_WIDE_LOGITS == 0).all()
+        # (b) a confident-wrong frame 90 nats above everything the utterance can emit
+        y = d["pred"].copy()
+        y[:, 7, :] = -90.0
+        y[:, 7, V - 1] = 0.0
+        for b in range(B):                                     # make sure V-1 is not one of utterance b's labels
+            lab = d["label"][b]; lab[lab == V - 1] = 1
+        d["pred"] = y
+        t = _to(dev, d)
+        st = torch.zeros((B,), dtype=torch.int32, device=dev)
+        loss, grad = ctc_loss_and_grad(t["pred"], t["label"], t["pred_lengths"], t["label_lengths"], status=st)
+        lo, go, ok = _oracle(d)
+        l = loss.cpu().numpy()
+        assert np.isfinite(l).all() and torch.isfinite(grad).all()
+        assert (st.cpu().numpy() & _lib.UTT_WIDE_LOGITS != 0).all()
+        assert (l <= lo + 1e-3).all() and (l >= lo - 25.0).all()          # 90 - 69.3 nats of one frame, at most
+        valid = np.arange(T)[None, :] < d["pred_lengths"][:, None]
+        rows = grad.cpu().numpy().sum(axis=2)
+        assert np.abs(rows[valid]).max() < 1e-4                            # still a gradient of a normalised model
+
+
+def test_backward_on_a_foreign_workspace_fails_instead_of_hanging(dev):
+    """ctcb_backward on a workspace that no matching ctcb_forward filled: the gradient kernel's waits are bounded
+    and stamped -- NaN rows come back, the GPU does not hang."""
+    import ctypes
+    from gluon_e2e_asr_b200 import _lib, ops
+    d = make_batch(3, 40, 46, 8, seed=95)
+    t = _to(dev, d)
+    call = ops._Call(t["pred"], t["label"], t["pred_lengths"], t["label_lengths"], False, True, False)
+    ws = torch.zeros((_lib.workspace_bytes(call.T, call.B, call.V, call.Lmax, True),), dtype=torch.uint8, device=dev)
+    loss = torch.zeros((3,), device=dev); grad = torch.zeros_like(t["pred"])
+    # a forward of ANOTHER shape into the same buffer, then the backward of this one
+    d2 = make_batch(3, 32, 46, 8, seed=96)
+    t2 = _to(dev, d2)
+    call2 = ops._Call(t2["pred"], t2["label"], t2["pred_lengths"], t2["label_lengths"], False, True, False)
+    call2.run(_lib.PHASE_FORWARD, ws, loss, keep=True, handoff="pointer")
+    call.run(_lib.PHASE_BACKWARD, ws, loss, grad=grad, handoff="pointer")
+    torch.cuda.synchronize()
+    assert torch.isnan(grad).all()
+    # the matching pair still works afterwards
+    call.run(_lib.PHASE_FORWARD, ws, loss, keep=True, handoff="pointer")
+    call.run(_lib.PHASE_BACKWARD, ws, loss, grad=grad, handoff="pointer")
+    lo, go, _ = _oracle(d)
+    _check(loss.cpu().numpy(), grad.cpu().numpy(), lo, go, "forward + backward")
+
+
+def _env(**kw):
+    """Context manager: set libctcb's tuning switches (ctcb_set_option; CTCB_OVERLAP=0 -> option "overlap")."""
+    from gluon_e2e_asr_b200 import _lib
+    return _lib.options(**{k[5:].lower() if k.startswith("CTCB_") else k: v for k, v in kw.items()})
 
 
 def test_overlapped_and_serial_schedules_agree(dev):
@@ -340,13 +420,11 @@ def test_overlapped_and_serial_schedules_agree(dev):
     assert torch.equal(ref[0], l2) and torch.equal(ref[1], g2)
 
 
-def test_wide_vocabulary_concurrent_schedule(dev):
-    """Wide vocabularies (rows staged by bulk copies).  Default schedule: k_emit, then k_walk with k_grad
-    as its programmatic dependent sharing the walkers' SMs.  Opt-in schedule (CTCB_EW_OVERLAP=1): k_walk
-    launched first, k_emit as its programmatic dependent publishing emission blocks from both ends
-    inwards, k_grad behind it -- three grids running concurrently.  Both against the same kernels
-    launched one after the other: same BITS (loss, gradient, status), run after run, for ragged batches
-    with an infeasible utterance; and inside the tolerance of the fp64 oracle."""
+def test_wide_vocabulary_schedules_agree(dev):
+    """Wide vocabularies (rows staged by bulk copies): k_emit, then k_walk with k_grad as its programmatic
+    dependent sharing the walkers' SMs, against the same kernels launched one after the other: same BITS
+    (loss, gradient, status), run after run, for ragged batches with an infeasible utterance; and inside
+    the tolerance of the fp64 oracle."""
     from gluon_e2e_asr_b200 import ctc_loss_and_grad, ops
     for (B, T, V, L, seed) in ((9, 75, 600, 14, 41), (5, 130, 2000, 40, 42), (64, 40, 1024, 9, 43)):
         d = make_batch(B, T, V, L, seed=seed)
@@ -354,7 +432,7 @@ def test_wide_vocabulary_concurrent_schedule(dev):
         t = _to(dev, d)
         args = (t["pred"], t["label"], t["pred_lengths"], t["label_lengths"])
         head = torch.linspace(0.5, 1.5, B, device=dev)
-        with _env(CTCB_OVERLAP=0, CTCB_EW_OVERLAP=0):
+        with _env(CTCB_OVERLAP=0):
             ops._ws_cache.clear()
             st0 = torch.zeros((B,), dtype=torch.int32, device=dev)
             l0, g0 = ctc_loss_and_grad(*args, head_grad=head, status=st0)
@@ -362,14 +440,14 @@ def test_wide_vocabulary_concurrent_schedule(dev):
             assert _lib_launches() == 3
         for rep in range(4):
             st1 = torch.zeros((B,), dtype=torch.int32, device=dev)
-            with _env(CTCB_EW_OVERLAP=rep % 2):            # opt-in: k_emit concurrent with the walkers too
+            with _env(CTCB_OVERLAP=1):
                 l1, g1 = ctc_loss_and_grad(*args, head_grad=head, status=st1, out_grad=torch.full_like(g0, float("nan")))
             assert _lib_launches() == 3
             assert torch.equal(l0, l1) and torch.equal(st0, st1), "loss/status differ (run %d)" % rep
             assert torch.equal(g0, g1), "gradient differs (run %d)" % rep
         lo, go, ok = O.CtcLossOracle("NTC", "NT")(d["pred"], d["label"], d["pred_lengths"], d["label_lengths"],
                                                  head_grad=head.cpu().numpy().astype(np.float64))
-        _check(l1.cpu().numpy(), g1.cpu().numpy(), lo, go, "wide concurrent B%d T%d V%d" % (B, T, V))
+        _check(l1.cpu().numpy(), g1.cpu().numpy(), lo, go, "wide overlapped B%d T%d V%d" % (B, T, V))
         assert (st1.cpu().numpy()[1] & 1) == 1 and not ok[1]
 
 
@@ -509,9 +587,9 @@ def test_host_entry_with_resident_gradient(dev):
     assert _lib.load().ctcb_loss_grad_host_resident(ctypes.byref(p), 0, None) == _lib.CTCB_INVALID_VALUE
 
 
-def test_host_entry_pipelines_two_halves(dev):
-    """CTCB_HOST_CHUNKS=2, B >= 16, utterance-major buffers: the host entry copies and computes the
-    batch in two halves on two streams; per-utterance results are the same bits as one device call."""
+def test_host_entry_full_outputs(dev):
+    """ctcb_loss_grad_host with every output (gradient, status, loss sum back on the host, head gradient,
+    an infeasible utterance): the same bits as one device call."""
     import ctypes
     from gluon_e2e_asr_b200 import _lib, ctc_loss_and_grad
     B, T, V, L = 19, 70, 46, 14
@@ -533,10 +611,9 @@ def test_host_entry_pipelines_two_halves(dev):
     p.data_lengths, p.data_lengths_dtype = d["pred_lengths"].ctypes.data, _lib.DT_F32
     p.label_lengths, p.label_lengths_dtype = d["label_lengths"].ctypes.data, _lib.DT_F32
     p.head_grad, p.loss, p.status, p.loss_sum = head.ctypes.data, l.ctypes.data, st.ctypes.data, ssum.ctypes.data
-    for chunks in (2, 1):
+    for rep in range(2):
         g[:] = np.nan; l[:] = np.nan; st[:] = 0; ssum[0] = 0.0
-        with _env(CTCB_HOST_CHUNKS=chunks):
-            _lib.check(_lib.load().ctcb_loss_grad_host(ctypes.byref(p), 0))
+        _lib.check(_lib.load().ctcb_loss_grad_host(ctypes.byref(p), 0))
         np.testing.assert_array_equal(l, loss.cpu().numpy())
         np.testing.assert_array_equal(g, grad.cpu().numpy())
         np.testing.assert_array_equal(st, st_dev.cpu().numpy())
@@ -576,8 +653,7 @@ def test_prefetching_pipe_matches_device_calls(dev):
         if depth < len(shapes):
             assert l.ctcb_pipe_wait(pipe._h, 0, None) == _lib.CTCB_INVALID_VALUE      # slot long reused
         pipe.close()
-    # pinned utterance-major logits with explicit lengths, opt-in CTCB_PIPE_PULL=1: the GPU pulls the valid frames itself;
-    # padded frames (NaN on the host) never reach the device and nothing reads them; same bits as the plain copy
+    # one-arena pinned batch whose padded frames are NaN on the host: ONE copy of the arena, and nothing reads the padding
     B, T, V, L = 8, 64, 46, 9
     d = make_batch(B, T, V, L, seed=320)
     d["pred_lengths"][:] = np.array([64, 40, 33, 64, 21, 50, 12, 64], np.float32)
@@ -587,21 +663,33 @@ def test_prefetching_pipe_matches_device_calls(dev):
     t = _to(dev, d)
     want = ctc_loss_and_grad(t["pred"], t["label"], t["pred_lengths"], t["label_lengths"])
     pb = PinnedBatch.from_arrays(d["pred"], d["label"], d["pred_lengths"], d["label_lengths"])
-    valid_bytes = int(d["pred_lengths"].sum()) * V * 4
-    for pull in (1, 0):
-        with _env(CTCB_PIPE_PULL=pull):
-            pipe = HostPipeline(0, depth=2)
-            lo = torch.full((B,), float("nan")).pin_memory()
-            g = pipe.wait(pipe.submit(pb, lo))
-            moved, pulled = pipe.last_h2d_bytes()
-            assert pulled == bool(pull)
-            if pull:
-                assert valid_bytes < moved < valid_bytes + 4096 and moved < pb.nbytes
-            else:
-                assert pb.nbytes - 256 < moved <= pb.nbytes          # one copy of the arena (its last field is not padded)
-            assert torch.equal(lo, want[0].cpu()) and torch.equal(g, want[1])
-            assert not torch.isnan(g).any()
-            pipe.close()
+    pipe = HostPipeline(0, depth=2)
+    lo = torch.full((B,), float("nan")).pin_memory()
+    g = pipe.wait(pipe.submit(pb, lo))
+    moved, pulled = pipe.last_h2d_bytes()
+    assert not pulled and pb.nbytes - 256 < moved <= pb.nbytes          # one copy of the arena (its last field is not padded)
+    assert torch.equal(lo, want[0].cpu()) and torch.equal(g, want[1])
+    assert not torch.isnan(g).any()
+    pipe.close()
+    # separately pinned arrays that are NOT one allocation are never merged into one copy, whatever their addresses
+    parts = [torch.tensor(d[k]).pin_memory() for k in ("pred", "label", "pred_lengths", "label_lengths")]
+    q = _lib.Problem()
+    q.T, q.B, q.V, q.Lmax, q.blank, q.label_pad = T, B, V, L, 0, 0
+    q.logits, q.logits_stride_t, q.logits_stride_b = parts[0].data_ptr(), V, T * V
+    q.labels, q.label_dtype, q.label_stride_b, q.label_stride_l = parts[1].data_ptr(), _lib.DT_F32, L, 1
+    q.data_lengths, q.data_lengths_dtype = parts[2].data_ptr(), _lib.DT_F32
+    q.label_lengths, q.label_lengths_dtype = parts[3].data_ptr(), _lib.DT_F32
+    lo2 = torch.full((B,), float("nan")).pin_memory()
+    q.loss = lo2.data_ptr()
+    h = ctypes.c_void_p(); tk = ctypes.c_int64(-1); hb = ctypes.c_int64(0)
+    l = _lib.load()
+    _lib.check(l.ctcb_pipe_create(0, 2, ctypes.byref(h)))
+    _lib.check(l.ctcb_pipe_submit(h, ctypes.byref(q), ctypes.byref(tk)))
+    _lib.check(l.ctcb_pipe_wait(h, tk, None))
+    _lib.check(l.ctcb_pipe_last_h2d_bytes(h, ctypes.byref(hb), None))
+    assert hb.value == sum(x.numel() * 4 for x in parts)               # the arrays' own bytes: no span copy
+    assert torch.equal(lo2, want[0].cpu())
+    assert l.ctcb_pipe_destroy(h) == _lib.CTCB_OK
     # separately allocated pageable arrays, head gradient, loss sum and status through the raw ABI
     B, T, V, L = 7, 44, 46, 10
     d = make_batch(B, T, V, L, seed=311)
