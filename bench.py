@@ -560,10 +560,23 @@ def run_cuda(args, rank, world, local_rank):
         loss_bufs = [torch.zeros((B,), dtype=torch.float32).pin_memory() for _ in hsets]
         sum_bufs = [torch.zeros((1,), dtype=torch.float64).pin_memory() for _ in hsets]
         loss_np = [b.numpy() for b in loss_bufs]
+        # the pipe's batches are PACKED on the host (PinnedBatch(packed=True), ctcb_problem_t.logits_row_offsets): the
+        # collation writes only the valid frames of every utterance, so the padded frames never cross PCIe
+        psets = []
+        for s_ in sets[:len(hsets)]:
+            d = s_["np"]
+            psets.append(PinnedBatch.from_arrays(np.ascontiguousarray(d["pred"]), np.ascontiguousarray(d["label"]),
+                                                 np.ascontiguousarray(d["pred_lengths"]), np.ascontiguousarray(d["label_lengths"]),
+                                                 packed=not args.dense_host))
         pprobs = []
-        for q0, lb, sb in zip(probs, loss_bufs, sum_bufs):
+        for q0, pk, lb, sb in zip(probs, psets, loss_bufs, sum_bufs):
             q = _lib.Problem()
             ctypes.memmove(ctypes.byref(q), ctypes.byref(q0), ctypes.sizeof(q))
+            q.logits = pk.pred.data_ptr()
+            q.labels = pk.label.data_ptr()
+            q.data_lengths, q.label_lengths = pk.pred_lengths.data_ptr(), pk.label_lengths.data_ptr()
+            if pk.packed:
+                q.logits_row_offsets = pk.row_offsets.data_ptr()
             q.loss = lb.data_ptr()
             if world > 1:
                 q.loss_sum = sb.data_ptr()              # the shard's float64 loss sum, for the all-reduce over the ranks
@@ -612,6 +625,10 @@ def run_cuda(args, rank, world, local_rank):
         e2e_pipe = {"value": pipe_frames / (pipe_ms * 1e-3), "unit": UNIT, "ms_per_step": pipe_ms / pipe_steps,
                     "h2d_bytes_per_step": h2d_rank * world, "d2h_bytes_per_step": (d2h + 8) * world, "steps": pipe_steps,
                     "in_flight": depth, "loss_checksum": acc,
+                    "h2d_bytes_per_step_dense": hsets[0].h2d_bytes * world,
+                    "host_layout": ("dense (B,T,V) arena" if args.dense_host else
+                                    "packed arena: the valid frames of every utterance back to back + int64 row offsets "
+                                    "(ctcb_problem_t.logits_row_offsets); the dense gradient is formed on the device"),
                     "api": "ctcb_pipe_submit / ctcb_pipe_wait (pinned HOST batches, one cudaMemcpyAsync of the batch's arena): "
                            "every step's inputs cross PCIe and its loss is read on the host inside the timed region; batch "
                            "i+1's transfer overlaps batch i's kernels (%d in flight); gradient left on the device; host wall "
@@ -785,6 +802,7 @@ def main():
                     help="default: cfg2 on one GPU (BASELINE configs[1]); cfg5 split by utterance on N > 1 (configs[4])")
     ap.add_argument("--pipe-depth", type=int, default=2, help="batches in flight in the prefetching host entry (e2e)")
     ap.add_argument("--no-others", action="store_true", help="skip the context measurements of the other configs")
+    ap.add_argument("--dense-host", action="store_true", help="e2e: dense (B,T,V) host batches instead of the packed arena")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="N>1: loss-sum exchange through the library's peer mailbox (default) or torch.distributed's NCCL all-reduce")
     ap.add_argument("--peer-lag", type=int, default=4, help="slack between the ranks of the peer mailbox exchange, in steps")

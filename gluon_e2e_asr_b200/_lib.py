@@ -48,7 +48,7 @@ class Problem(ctypes.Structure):
         ("data_lengths", ctypes.c_void_p), ("data_lengths_dtype", ctypes.c_int32),
         ("label_lengths", ctypes.c_void_p), ("label_lengths_dtype", ctypes.c_int32),
         ("head_grad", ctypes.c_void_p), ("loss", ctypes.c_void_p), ("loss_sum", ctypes.c_void_p),
-        ("status", ctypes.c_void_p),
+        ("status", ctypes.c_void_p), ("logits_row_offsets", ctypes.c_void_p),
     ]
 
 

@@ -34,10 +34,17 @@ class PinnedBatch:
 
     FIELDS = ("pred", "label", "pred_lengths", "label_lengths")
 
-    def __init__(self, B, T, V, Lmax, label_dtype=torch.float32, length_dtype=torch.float32, pin=True):
+    def __init__(self, B, T, V, Lmax, label_dtype=torch.float32, length_dtype=torch.float32, pin=True, packed_frames=None):
+        """``packed_frames`` (= sum of the valid frame counts): the logits field holds only the VALID frames of
+        every utterance, back to back, plus an int64 ``row_offsets`` field (``ctcb_problem_t.logits_row_offsets``):
+        the padded frames of a length-bucketed batch never cross PCIe.  For the C ABI's host entries
+        (``HostPipeline``); ``load()`` -- dense device views for the torch plugin -- needs the dense layout."""
         self.shape = (B, T, V, Lmax)
-        specs = (("pred", (B, T, V), torch.float32), ("label", (B, Lmax), label_dtype),
+        self.packed = packed_frames is not None
+        specs = (("pred", (packed_frames, V) if self.packed else (B, T, V), torch.float32), ("label", (B, Lmax), label_dtype),
                  ("pred_lengths", (B,), length_dtype), ("label_lengths", (B,), length_dtype))
+        if self.packed:
+            specs = specs + (("row_offsets", (B,), torch.int64),)
         self._layout, off = [], 0
         for name, shp, dt in specs:
             n = int(np.prod(shp)) * torch.empty((), dtype=dt).element_size()
@@ -58,25 +65,40 @@ class PinnedBatch:
         return {name: arena[off:off + n].view(dt).view(shp) for name, shp, dt, off, n in self._layout}
 
     def fill(self, pred, label, pred_lengths, label_lengths):
-        """Copy one collated batch (numpy arrays or tensors) into the arena; returns self."""
-        for name, src in zip(self.FIELDS, (pred, label, pred_lengths, label_lengths)):
+        """Copy one collated batch (numpy arrays or tensors; ``pred`` dense ``(B, T, V)``) into the arena; returns self."""
+        for name, src in zip(self.FIELDS[1:], (label, pred_lengths, label_lengths)):
             dst = self.host[name]
             dst.copy_(torch.as_tensor(src).to(dst.dtype).reshape(dst.shape))
+        if not self.packed:
+            self.host["pred"].copy_(torch.as_tensor(pred).to(torch.float32).reshape(self.host["pred"].shape))
+            return self
+        B, T, V, _ = self.shape
+        x = torch.as_tensor(pred)
+        n = np.clip(np.asarray(pred_lengths).astype(np.int64), 0, T)
+        off = np.concatenate([[0], np.cumsum(n)[:-1]])
+        if int(n.sum()) != self.host["pred"].shape[0]:
+            raise ValueError("packed arena holds %d frames, the batch has %d valid ones" % (self.host["pred"].shape[0], int(n.sum())))
+        for b in range(B):
+            self.host["pred"][off[b]:off[b] + n[b]].copy_(x[b, :n[b]])
+        self.host["row_offsets"].copy_(torch.as_tensor(off * V))
         return self
 
     @classmethod
-    def from_arrays(cls, pred, label, pred_lengths, label_lengths, pin=True):
+    def from_arrays(cls, pred, label, pred_lengths, label_lengths, pin=True, packed=False):
         pred = np.asarray(pred)
         label = np.asarray(label)
         B, T, V = pred.shape
+        frames = int(np.clip(np.asarray(pred_lengths).astype(np.int64), 0, T).sum()) if packed else None
         out = cls(B, T, V, label.shape[1], label_dtype=torch.as_tensor(label).dtype,
-                  length_dtype=torch.as_tensor(np.asarray(pred_lengths)).dtype, pin=pin)
+                  length_dtype=torch.as_tensor(np.asarray(pred_lengths)).dtype, pin=pin, packed_frames=frames)
         return out.fill(pred, label, pred_lengths, label_lengths)
 
     def load(self, device, non_blocking=True):
         """One host->device copy of the whole arena on the current stream of ``device``; returns the
         device views ``{pred, label, pred_lengths, label_lengths}`` (the same tensor objects on every
         call: the device arena is persistent, stream order protects it)."""
+        if self.packed:
+            raise RuntimeError("PinnedBatch.load needs the dense layout (packed batches go through HostPipeline)")
         device = torch.device(device)
         slot = self._dev.get(device)
         if slot is None:

@@ -268,6 +268,8 @@ int validate(const ctcb_problem_t* p) {
     if (p->Lmax + 1 > 2048)
         return fail(CTCB_UNSUPPORTED, "Lmax=%d exceeds the supported 2047 labels per utterance", p->Lmax);
     if ((long long)p->B > 65535) return fail(CTCB_UNSUPPORTED, "B=%d exceeds 65535 utterances per call", p->B);
+    if (p->logits_row_offsets && !p->data_lengths)
+        return fail(CTCB_INVALID_VALUE, "packed logits (logits_row_offsets) need data_lengths");
     return CTCB_OK;
 }
 
@@ -275,6 +277,7 @@ ctcb::Problem to_device_problem(const ctcb_problem_t* p) {
     ctcb::Problem d{};
     d.T = p->T; d.B = p->B; d.V = p->V; d.Lmax = p->Lmax; d.blank = p->blank; d.label_pad = p->label_pad;
     d.logits = p->logits; d.st_t = p->logits_stride_t; d.st_b = p->logits_stride_b;
+    d.row_off = reinterpret_cast<const long long*>(p->logits_row_offsets);
     d.grad = p->grad; d.gst_t = p->grad_stride_t; d.gst_b = p->grad_stride_b;
     d.labels = p->labels; d.label_dtype = p->label_dtype; d.lst_b = p->label_stride_b; d.lst_l = p->label_stride_l;
     d.data_len = p->data_lengths; d.data_len_dtype = p->data_lengths_dtype;
@@ -343,7 +346,7 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
         return fail(CTCB_WORKSPACE_TOO_SMALL, "workspace %zu < required %zu bytes", workspace_bytes, lay.total);
     if (reinterpret_cast<uintptr_t>(workspace) % 256) return fail(CTCB_INVALID_VALUE, "workspace must be 256-byte aligned");
     if (!is_device_ptr(p->logits) || !is_device_ptr(p->loss) || !is_device_ptr(workspace) || !is_device_ptr(p->grad) ||
-        !is_device_ptr(p->labels))
+        !is_device_ptr(p->labels) || !is_device_ptr(p->logits_row_offsets))
         return fail(CTCB_INVALID_VALUE, "logits/labels/loss/grad/workspace must be CUDA device memory (there is no CPU path)");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const ctcb::Problem dp = to_device_problem(p);
@@ -378,7 +381,7 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
             if (want > cap) want = cap;
             if (want > smem) smem = want;
         }
-        const int vec = pick_vec(p->logits, p->logits_stride_t, p->logits_stride_b, p->V);
+        const int vec = pick_vec(p->logits, p->logits_stride_t, p->logits_row_offsets ? 0 : p->logits_stride_b, p->V);
         CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(wfn), smem));
         // NQ: vector loads per lane that hold one logits row in registers (0 = two-pass)
         const int units = (p->V / vec + 31) / 32;
@@ -440,7 +443,7 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
         size_t gsm = ctcb::grad_smem_bytes(lay.Lp, 32 * gch);
         int gthreads = 128;
         if (gsm > 200 * 1024) return fail(CTCB_UNSUPPORTED, "Lmax=%d too long for the gradient kernel", p->Lmax);
-        int vec = pick_vec(p->logits, p->logits_stride_t, p->logits_stride_b, p->V);
+        int vec = pick_vec(p->logits, p->logits_stride_t, p->logits_row_offsets ? 0 : p->logits_stride_b, p->V);
         const int gvec = pick_vec(p->grad, p->grad_stride_t, p->grad_stride_b, p->V);
         if (gvec < vec) vec = gvec;
         const int ch = gch;
@@ -543,6 +546,30 @@ size_t dt_size(int d) { return (d == CTCB_I32 || d == CTCB_F32) ? 4 : 8; }
 
 namespace {
 int loss_grad_host_impl(const ctcb_problem_t* hp, int device, float** dev_grad);
+
+long long host_len(const void* p, int dtype, int b) {
+    switch (dtype) {
+        case CTCB_I32: return static_cast<const int32_t*>(p)[b];
+        case CTCB_I64: return static_cast<const int64_t*>(p)[b];
+        case CTCB_F32: return (long long)static_cast<const float*>(p)[b];
+        default: return (long long)static_cast<const double*>(p)[b];
+    }
+}
+// Host entries, packed logits (ctcb_problem_t.logits_row_offsets, HOST arrays here): bytes of the buffer =
+// max_b (offset_b + T_b * V) floats.  Utterance-major rows only (logits_stride_t == V).
+int packed_logits_bytes(const ctcb_problem_t* hp, size_t* bytes) {
+    if (hp->logits_stride_t != hp->V) return fail(CTCB_INVALID_VALUE, "packed logits need logits_stride_t == V");
+    long long hi = 0;
+    for (int b = 0; b < hp->B; ++b) {
+        long long t = host_len(hp->data_lengths, hp->data_lengths_dtype, b);
+        t = t < 0 ? 0 : (t > hp->T ? hp->T : t);
+        const long long off = hp->logits_row_offsets[b];
+        if (off < 0) return fail(CTCB_INVALID_VALUE, "negative logits_row_offsets[%d]", b);
+        if (off + t * hp->V > hi) hi = off + t * hp->V;
+    }
+    *bytes = sizeof(float) * (size_t)hi;
+    return CTCB_OK;
+}
 }
 
 int ctcb_loss_grad_host(const ctcb_problem_t* hp, int device) { return loss_grad_host_impl(hp, device, nullptr); }
@@ -565,27 +592,32 @@ int loss_grad_host_impl(const ctcb_problem_t* hp, int device, float** dev_grad) 
     const int T = hp->T, B = hp->B, V = hp->V, Lmax = hp->Lmax;
     const bool need_grad = hp->grad != nullptr || dev_grad != nullptr;
     // the host entry takes compact buffers only: strides must describe TNC or NTC exactly
-    const bool tnc = hp->logits_stride_t == (long long)B * V && hp->logits_stride_b == V;
-    const bool ntc = hp->logits_stride_t == V && hp->logits_stride_b == (long long)T * V;
+    const bool packed = hp->logits_row_offsets != nullptr;
+    const bool tnc = !packed && hp->logits_stride_t == (long long)B * V && hp->logits_stride_b == V;
+    const bool ntc = packed || (hp->logits_stride_t == V && hp->logits_stride_b == (long long)T * V);
     if (!tnc && !ntc) return fail(CTCB_INVALID_VALUE, "host entry needs compact TNC or NTC logits");
-    if (need_grad && !dev_grad && (hp->grad_stride_t != hp->logits_stride_t || hp->grad_stride_b != hp->logits_stride_b))
-        return fail(CTCB_INVALID_VALUE, "host entry needs grad in the logits' layout");
+    const long long gst_t = tnc ? (long long)B * V : V, gst_b = tnc ? V : (long long)T * V;      // dense gradient, the logits' layout
+    if (need_grad && !dev_grad && (hp->grad_stride_t != gst_t || hp->grad_stride_b != gst_b))
+        return fail(CTCB_INVALID_VALUE, "host entry needs a dense grad in the logits' layout");
     if (Lmax > 0 && !((hp->label_stride_b == Lmax && hp->label_stride_l == 1) || (hp->label_stride_b == 1 && hp->label_stride_l == B)))
         return fail(CTCB_INVALID_VALUE, "host entry needs compact NT or TN labels");
 
     size_t ws_bytes = 0;
     ctcb_workspace_bytes(T, B, V, Lmax, need_grad, &ws_bytes);
-    const size_t n_log = sizeof(float) * (size_t)T * B * V;
+    const size_t n_dense = sizeof(float) * (size_t)T * B * V;
+    size_t n_log = n_dense;
+    if (packed) { if (int rc = packed_logits_bytes(hp, &n_log)) return rc; }
     const size_t n_lab = dt_size(hp->label_dtype) * (size_t)B * (Lmax > 0 ? Lmax : 1);
     const size_t n_dl = hp->data_lengths ? dt_size(hp->data_lengths_dtype) * (size_t)B : 0;
     const size_t n_ll = hp->label_lengths ? dt_size(hp->label_lengths_dtype) * (size_t)B : 0;
     const size_t n_head = hp->head_grad ? sizeof(float) * (size_t)B : 0;
+    const size_t n_off = packed ? sizeof(int64_t) * (size_t)B : 0;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
     const size_t o_ws = take(ws_bytes);
-    const size_t o_log = take(n_log), o_grad = take(need_grad ? n_log : 0), o_lab = take(n_lab),
+    const size_t o_log = take(n_log), o_grad = take(need_grad ? n_dense : 0), o_lab = take(n_lab),
                  o_dl = take(n_dl), o_ll = take(n_ll), o_head = take(n_head), o_loss = take(sizeof(float) * B),
-                 o_sum = take(sizeof(double)), o_stat = take(sizeof(int) * B);
+                 o_sum = take(sizeof(double)), o_stat = take(sizeof(int) * B), o_off = take(n_off);
     std::lock_guard<std::mutex> lk(g_hs_mu);
     HostScratch& hs = g_hs[device];
     if (!hs.stream) {
@@ -607,12 +639,14 @@ int loss_grad_host_impl(const ctcb_problem_t* hp, int device, float** dev_grad) 
     if (n_ll) COPY_TRY(cudaMemcpyAsync(base + o_ll, hp->label_lengths, n_ll, cudaMemcpyHostToDevice, s));
     if (n_head) COPY_TRY(cudaMemcpyAsync(base + o_head, hp->head_grad, n_head, cudaMemcpyHostToDevice, s));
     if (hp->loss_sum) COPY_TRY(cudaMemcpyAsync(base + o_sum, hp->loss_sum, sizeof(double), cudaMemcpyHostToDevice, s));
+    if (n_off) COPY_TRY(cudaMemcpyAsync(base + o_off, hp->logits_row_offsets, n_off, cudaMemcpyHostToDevice, s));
     COPY_TRY(cudaMemcpyAsync(base + o_log, hp->logits, n_log, cudaMemcpyHostToDevice, s));
     {
         ctcb_problem_t d = *hp;
         d.logits = reinterpret_cast<float*>(base + o_log);
+        d.logits_row_offsets = packed ? reinterpret_cast<const int64_t*>(base + o_off) : nullptr;
         d.grad = need_grad ? reinterpret_cast<float*>(base + o_grad) : nullptr;
-        if (dev_grad) { d.grad_stride_t = hp->logits_stride_t; d.grad_stride_b = hp->logits_stride_b; }
+        if (dev_grad) { d.grad_stride_t = gst_t; d.grad_stride_b = gst_b; }
         d.labels = base + o_lab;
         d.data_lengths = hp->data_lengths ? base + o_dl : nullptr;
         d.label_lengths = hp->label_lengths ? base + o_ll : nullptr;
@@ -623,7 +657,7 @@ int loss_grad_host_impl(const ctcb_problem_t* hp, int device, float** dev_grad) 
         if (int rc = ctcb_loss_grad(&d, base + o_ws, ws_bytes, s)) return rc;
     }
     COPY_TRY(cudaMemcpyAsync(hp->loss, base + o_loss, sizeof(float) * B, cudaMemcpyDeviceToHost, s));
-    if (need_grad && !dev_grad) COPY_TRY(cudaMemcpyAsync(hp->grad, base + o_grad, n_log, cudaMemcpyDeviceToHost, s));
+    if (need_grad && !dev_grad) COPY_TRY(cudaMemcpyAsync(hp->grad, base + o_grad, n_dense, cudaMemcpyDeviceToHost, s));
     if (hp->loss_sum) COPY_TRY(cudaMemcpyAsync(hp->loss_sum, base + o_sum, sizeof(double), cudaMemcpyDeviceToHost, s));
     if (hp->status) COPY_TRY(cudaMemcpyAsync(hp->status, base + o_stat, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
 #undef COPY_TRY
@@ -742,11 +776,15 @@ int ctcb_pipe_submit(ctcb_pipe_t* p, const ctcb_problem_t* hp, int64_t* ticket) 
     if (!p || !ticket) return fail(CTCB_INVALID_VALUE, "pipe / ticket is NULL");
     if (int rc = validate(hp)) return rc;
     const int T = hp->T, B = hp->B, V = hp->V, Lmax = hp->Lmax;
-    const bool tnc = hp->logits_stride_t == (long long)B * V && hp->logits_stride_b == V;
-    const bool ntc = hp->logits_stride_t == V && hp->logits_stride_b == (long long)T * V;
+    const bool packed = hp->logits_row_offsets != nullptr;
+    const bool tnc = !packed && hp->logits_stride_t == (long long)B * V && hp->logits_stride_b == V;
+    const bool ntc = packed || (hp->logits_stride_t == V && hp->logits_stride_b == (long long)T * V);
     if (!tnc && !ntc) return fail(CTCB_INVALID_VALUE, "host entry needs compact TNC or NTC logits");
     if (Lmax > 0 && !((hp->label_stride_b == Lmax && hp->label_stride_l == 1) || (hp->label_stride_b == 1 && hp->label_stride_l == B)))
         return fail(CTCB_INVALID_VALUE, "host entry needs compact NT or TN labels");
+    const size_t n_dense = sizeof(float) * (size_t)T * B * V;
+    size_t n_log = n_dense;
+    if (packed) { if (int rc = packed_logits_bytes(hp, &n_log)) return rc; }
     CUDA_TRY(cudaSetDevice(p->device));
     ctcb_pipe::Slot& sl = p->slots[p->next % p->depth];
     if (sl.busy) {   // the caller did not collect this slot's previous batch: its results are overwritten
@@ -756,12 +794,14 @@ int ctcb_pipe_submit(ctcb_pipe_t* p, const ctcb_problem_t* hp, int64_t* ticket) 
     // inputs: {host pointer, bytes}; one copy when they lie in one host arena (batch.py PinnedBatch,
     // the reference's shared-memory collation batchify.py:51), one copy per array otherwise
     struct In { const void* h; size_t n; size_t off; };
-    In in[5] = {
-        {hp->logits, sizeof(float) * (size_t)T * B * V, 0},
+    constexpr int NIN = 6;
+    In in[NIN] = {
+        {hp->logits, n_log, 0},
         {Lmax > 0 ? hp->labels : nullptr, Lmax > 0 ? dt_size(hp->label_dtype) * (size_t)B * Lmax : 0, 0},
         {hp->data_lengths, hp->data_lengths ? dt_size(hp->data_lengths_dtype) * (size_t)B : 0, 0},
         {hp->label_lengths, hp->label_lengths ? dt_size(hp->label_lengths_dtype) * (size_t)B : 0, 0},
         {hp->head_grad, hp->head_grad ? sizeof(float) * (size_t)B : 0, 0},
+        {hp->logits_row_offsets, packed ? sizeof(int64_t) * (size_t)B : 0, 0},
     };
     uintptr_t lo = UINTPTR_MAX, hi = 0;
     size_t sum = 0;
@@ -772,7 +812,7 @@ int ctcb_pipe_submit(ctcb_pipe_t* p, const ctcb_problem_t* hp, int64_t* ticket) 
             sum += a.n;
         }
     // one copy over the whole span only when the span is one allocation (checked with the driver once per arena)
-    bool one_copy = hi - lo <= sum + 5 * 4096;
+    bool one_copy = hi - lo <= sum + NIN * 4096;
     if (one_copy && !(lo >= p->arena_lo && hi <= p->arena_hi)) one_copy = same_allocation(lo, hi, &p->arena_lo, &p->arena_hi);
     size_t in_need = 0;
     const size_t skew = lo % 256;            // device addresses congruent to the host's mod 256 (vector loads)
@@ -787,7 +827,7 @@ int ctcb_pipe_submit(ctcb_pipe_t* p, const ctcb_problem_t* hp, int64_t* ticket) 
     if (int rc = ctcb_workspace_bytes(T, B, V, Lmax, need_grad, &ws_need)) return rc;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
-    const size_t o_grad = take(in[0].n), o_loss = take(sizeof(float) * B), o_sum = take(sizeof(double)),
+    const size_t o_grad = take(n_dense), o_loss = take(sizeof(float) * B), o_sum = take(sizeof(double)),
                  o_stat = take(sizeof(int) * B);
     if (int rc = pipe_grow(&sl.in, &sl.in_bytes, in_need, nullptr)) return rc;
     if (int rc = pipe_grow(&sl.out, &sl.out_bytes, o, nullptr)) return rc;
@@ -798,7 +838,7 @@ int ctcb_pipe_submit(ctcb_pipe_t* p, const ctcb_problem_t* hp, int64_t* ticket) 
         COPY_TRY(cudaMemcpyAsync(sl.in + skew, reinterpret_cast<const void*>(lo), hi - lo, cudaMemcpyHostToDevice, p->s_copy));
         moved += (int64_t)(hi - lo);
     } else {
-        for (int k = 0; k < 5; ++k)
+        for (int k = 0; k < NIN; ++k)
             if (in[k].n) { COPY_TRY(cudaMemcpyAsync(sl.in + in[k].off, in[k].h, in[k].n, cudaMemcpyHostToDevice, p->s_copy)); moved += (int64_t)in[k].n; }
     }
     p->last_h2d = moved;
@@ -811,8 +851,9 @@ int ctcb_pipe_submit(ctcb_pipe_t* p, const ctcb_problem_t* hp, int64_t* ticket) 
     d.data_lengths = in[2].n ? sl.in + in[2].off : nullptr;
     d.label_lengths = in[3].n ? sl.in + in[3].off : nullptr;
     d.head_grad = in[4].n ? reinterpret_cast<const float*>(sl.in + in[4].off) : nullptr;
+    d.logits_row_offsets = in[5].n ? reinterpret_cast<const int64_t*>(sl.in + in[5].off) : nullptr;
     d.grad = reinterpret_cast<float*>(sl.out + o_grad);
-    d.grad_stride_t = hp->logits_stride_t; d.grad_stride_b = hp->logits_stride_b;
+    d.grad_stride_t = tnc ? (long long)B * V : V; d.grad_stride_b = tnc ? V : (long long)T * V;      // dense, the logits' layout
     d.loss = reinterpret_cast<float*>(sl.out + o_loss);
     d.loss_sum = hp->loss_sum ? reinterpret_cast<double*>(sl.out + o_sum) : nullptr;
     d.status = hp->status ? reinterpret_cast<int32_t*>(sl.out + o_stat) : nullptr;

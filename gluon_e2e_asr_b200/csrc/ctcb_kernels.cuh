@@ -49,6 +49,7 @@ enum : int { DT_I32 = 0, DT_I64 = 1, DT_F32 = 2, DT_F64 = 3 };
 struct Problem {          // device view of ctcb_problem_t
     int T, B, V, Lmax, blank, label_pad;
     const float* logits; long long st_t, st_b;
+    const long long* row_off;        // optional: element offset of utterance b's frame 0 (packed, ragged logits); replaces b*st_b
     float* grad; long long gst_t, gst_b;
     const void* labels; int label_dtype; long long lst_b, lst_l;
     const void* data_len; int data_len_dtype;
@@ -89,6 +90,11 @@ __device__ __forceinline__ long long load_as_int(const void* p, int dtype, long 
         case DT_F32: return static_cast<long long>(static_cast<const float*>(p)[i]);
         default:     return static_cast<long long>(static_cast<const double*>(p)[i]);
     }
+}
+
+// frame 0 of utterance b: strided (any T/B strides), or packed -- utterance b's valid frames stored back to back
+__device__ __forceinline__ const float* utt_logits(const Problem& p, int b) {
+    return p.logits + (p.row_off ? __ldg(p.row_off + b) : b * p.st_b);
 }
 
 __device__ __forceinline__ float fast_ex2(float x) {
@@ -215,7 +221,7 @@ __global__ void __launch_bounds__(NQ < 0 ? 256 : 128) k_emit(Problem p, Workspac
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (t < Tb) {
             mbar_expect_tx(rbar + warp, (uint32_t)p.V * 4);
-            tma_load_1d(srow + (size_t)warp * p.V, p.logits + b * p.st_b + (long long)t * p.st_t, (uint32_t)p.V * 4, rbar + warp);
+            tma_load_1d(srow + (size_t)warp * p.V, utt_logits(p, b) + (long long)t * p.st_t, (uint32_t)p.V * 4, rbar + warp);
         }
     }
     __syncwarp();
@@ -239,7 +245,7 @@ __global__ void __launch_bounds__(NQ < 0 ? 256 : 128) k_emit(Problem p, Workspac
     const int jbeg = BPC == 4 ? 0 : warp * FPW;
     if (!meta_cta && t0 < Tb) {
         float mxs[kG];
-        const float* rows = p.logits + b * p.st_b + (long long)t0 * p.st_t;
+        const float* rows = utt_logits(p, b) + (long long)t0 * p.st_t;
         if (STAGED) {
             __shared__ float s_mx[kG];
             if (t0 + warp < Tb) {
@@ -640,7 +646,7 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
         const int q = warp - NW, V = p.V;
         const int fj = lane >> 2, qk = lane & 3;                       // frame of the block, quarter of the row
         const int cpl = (V + 3) >> 2, col0 = qk * cpl;                 // this lane's columns [col0, col0 + cpl) below V
-        const float* base = p.logits + b * p.st_b;
+        const float* base = utt_logits(p, b);
         const float kMinProb = 7.888609052210118e-31f;                 // 2^kMinLog2
         auto load_blk = [&](int n, float (&x)[CPL]) {
             const int t = (DIR ? NQ - 1 - n : n) * kG + fj;
@@ -1354,7 +1360,7 @@ __global__ void __launch_bounds__(XQ < 0 ? 256 : 128, XQ < 0 ? (CH == 16 ? 2 : 3
             const int j = warp * FPW + f, t = t_first + j;
             if (t < Tb) {
                 mbar_expect_tx(rbar + j, (uint32_t)p.V * 4);
-                tma_load_1d(srow + (size_t)j * p.V, p.logits + b * p.st_b + (long long)t * p.st_t, (uint32_t)p.V * 4, rbar + j);
+                tma_load_1d(srow + (size_t)j * p.V, utt_logits(p, b) + (long long)t * p.st_t, (uint32_t)p.V * 4, rbar + j);
             }
         }
     }
@@ -1429,7 +1435,7 @@ __global__ void __launch_bounds__(XQ < 0 ? 256 : 128, XQ < 0 ? (CH == 16 ? 2 : 3
             fr[f] = make_float2(0.0f, 0.0f);
             if (live[f]) {
                 fr[f] = __ldcg(w.fr + (size_t)b * p.T + tt[f]);
-                const float* xrow = p.logits + b * p.st_b + (long long)tt[f] * p.st_t;
+                const float* xrow = utt_logits(p, b) + (long long)tt[f] * p.st_t;
                 if (XQ > 0) {
                     const V_t* xv = reinterpret_cast<const V_t*>(xrow);
 #pragma unroll
@@ -1454,7 +1460,7 @@ __global__ void __launch_bounds__(XQ < 0 ? 256 : 128, XQ < 0 ? (CH == 16 ? 2 : 3
             if (t >= p.T) continue;
             float* grow = p.grad + b * p.gst_b + (long long)t * p.gst_t;
             if (!live[f]) { zero_row<VEC>(grow, p.V, lane); continue; }
-            const float* xrow = p.logits + b * p.st_b + (long long)t * p.st_t;
+            const float* xrow = utt_logits(p, b) + (long long)t * p.st_t;
             float* gbuf = gbuf0 + (size_t)(r * F + f) * GW;
             float zb = 0.0f, zl = 0.0f;
             if (CH > 0) {

@@ -59,6 +59,8 @@ class HostPipeline:
         q.T, q.B, q.V, q.Lmax = T, B, V, Lmax
         q.blank, q.label_pad = (V - 1, -1) if last else (0, 0)
         q.logits, q.logits_stride_t, q.logits_stride_b = batch.pred.data_ptr(), V, T * V
+        if getattr(batch, "packed", False):          # valid frames only, back to back: ctcb_problem_t.logits_row_offsets
+            q.logits_row_offsets = batch.row_offsets.data_ptr()
         q.labels, q.label_dtype = batch.label.data_ptr(), _DT[batch.label.dtype]
         q.label_stride_b, q.label_stride_l = Lmax, 1
         q.data_lengths, q.data_lengths_dtype = batch.pred_lengths.data_ptr(), _DT[batch.pred_lengths.dtype]

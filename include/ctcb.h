@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CTCB_VERSION 100 /* 0.1.0 */
+#define CTCB_VERSION 101 /* 0.1.1: ctcb_problem_t.logits_row_offsets, ctcb_set_option, ctcb_greedy_decode_unk */
 
 typedef enum {
     CTCB_OK = 0,
@@ -83,6 +83,13 @@ typedef struct ctcb_problem {
     double* loss_sum;               /* optional device scalar: += sum_b loss[b] (feeds the
                                        loss-sum allreduce, replaces train_ctc_ce.py:367-368) */
     int32_t* status;                /* optional (B,) CTCB_UTT_* bits */
+    const int64_t* logits_row_offsets; /* optional (B,): PACKED logits -- utterance b's frame 0 is at logits +
+                                       logits_row_offsets[b] (elements), its frames logits_stride_t apart, and only its
+                                       data_lengths[b] valid frames need to exist: a length-bucketed batch
+                                       (data/sampler.py:80-248) crosses PCIe without its padded frames
+                                       (batch.py PinnedBatch(packed=True)).  Replaces b * logits_stride_b, which is
+                                       then ignored.  Needs data_lengths.  The gradient stays dense (grad strides).
+                                       Device pointer for the device entries, host pointer for the host entries. */
 } ctcb_problem_t;
 
 /* library identity; replaces nothing (sanity check for the binding) */

@@ -40,7 +40,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 def test_version_and_error_string(lib):
     l = lib.load()
-    assert l.ctcb_version() == 100
+    assert l.ctcb_version() == 101
     assert isinstance(l.ctcb_last_error(), bytes)
 
 
@@ -48,9 +48,10 @@ def test_problem_struct_layout_matches_header(lib):
     """ctypes mirror of ctcb_problem_t: field order/size as the C compiler lays it out."""
     import subprocess
     import tempfile
-    src = '#include <stdio.h>\n#include <stddef.h>\n#include "ctcb.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n",' \
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "ctcb.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",' \
           'sizeof(ctcb_problem_t), offsetof(ctcb_problem_t, logits), offsetof(ctcb_problem_t, grad),' \
-          'offsetof(ctcb_problem_t, labels), offsetof(ctcb_problem_t, head_grad), offsetof(ctcb_problem_t, status));return 0;}'
+          'offsetof(ctcb_problem_t, labels), offsetof(ctcb_problem_t, head_grad), offsetof(ctcb_problem_t, status),' \
+          'offsetof(ctcb_problem_t, logits_row_offsets));return 0;}'
     with tempfile.TemporaryDirectory() as td:
         c = os.path.join(td, "l.c")
         with open(c, "w") as f:
@@ -60,7 +61,7 @@ def test_problem_struct_layout_matches_header(lib):
         got = [int(x) for x in subprocess.check_output([exe]).split()]
     P = lib.Problem
     assert got == [ctypes.sizeof(P), P.logits.offset, P.grad.offset, P.labels.offset, P.head_grad.offset,
-                   P.status.offset]
+                   P.status.offset, P.logits_row_offsets.offset]
 
 
 def test_workspace_bytes(lib):

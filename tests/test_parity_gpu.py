@@ -671,6 +671,23 @@ def test_prefetching_pipe_matches_device_calls(dev):
     assert torch.equal(lo, want[0].cpu()) and torch.equal(g, want[1])
     assert not torch.isnan(g).any()
     pipe.close()
+    # PACKED arena (ctcb_problem_t.logits_row_offsets): only the valid frames exist on the host and cross PCIe; same bits
+    pk = PinnedBatch.from_arrays(d["pred"], d["label"], d["pred_lengths"], d["label_lengths"], packed=True)
+    assert pk.packed and pk.pred.shape == (int(d["pred_lengths"].sum()), V) and not torch.isnan(pk.pred).any()
+    pipe = HostPipeline(0, depth=2)
+    for rep in range(3):
+        lo = torch.full((B,), float("nan")).pin_memory()
+        g = pipe.wait(pipe.submit(pk, lo))
+        moved, _ = pipe.last_h2d_bytes()
+        assert moved <= pk.nbytes and moved < 0.75 * pb.nbytes
+        assert torch.equal(lo, want[0].cpu()) and torch.equal(g, want[1])
+    pipe.close()
+    # the synchronous host entry takes the packed layout too
+    q = HostPipeline.problem(None, pk, lo)
+    dgp = ctypes.c_void_p()
+    lo.fill_(float("nan"))
+    _lib.check(_lib.load().ctcb_loss_grad_host_resident(ctypes.byref(q), 0, ctypes.byref(dgp)))
+    assert torch.equal(lo, want[0].cpu())
     # separately pinned arrays that are NOT one allocation are never merged into one copy, whatever their addresses
     parts = [torch.tensor(d[k]).pin_memory() for k in ("pred", "label", "pred_lengths", "label_lengths")]
     q = _lib.Problem()
