@@ -17,6 +17,7 @@
 #include "ctcb.h"
 #include "ctcb_dlpack.h"
 #include "ctcb_kernels.cuh"
+#include "ctcb_meet.cuh"
 
 struct ctcb_mailbox {
     int device = 0, rank = 0, world = 0;
@@ -56,9 +57,9 @@ thread_local int g_prof_count = 0;
 // Read from the environment ONCE (CTCB_<NAME>, at first use) and changeable through ctcb_set_option (tests, A/B
 // runs): nothing on the per-call host path calls getenv.  -1 = automatic.
 enum Opt { OPT_WALK_P, OPT_WALK_NW, OPT_WALK_STAGES, OPT_OVERLAP, OPT_FUSED, OPT_WALK_PER_SM, OPT_EMIT_STAGED,
-           OPT_GRAD_STAGED, OPT_COUNT };
+           OPT_GRAD_STAGED, OPT_MEET, OPT_COUNT };
 const char* const kOptNames[OPT_COUNT] = {"walk_p", "walk_nw", "walk_stages", "overlap", "fused", "walk_per_sm",
-                                          "emit_staged", "grad_staged"};
+                                          "emit_staged", "grad_staged", "meet"};
 struct Options {
     int v[OPT_COUNT];
     Options() {
@@ -146,6 +147,13 @@ bool overlap_allowed(int B, bool fused) {
     if (opt(OPT_OVERLAP) >= 0) return opt(OPT_OVERLAP) != 0;
     (void)fused;
     return B <= 296;
+}
+
+// the one-kernel path (k_meet): opt-in / opt-out through the "meet" option, automatic otherwise
+bool meet_wanted(int B) {
+    if (opt(OPT_MEET) >= 0) return opt(OPT_MEET) != 0;
+    (void)B;
+    return false;
 }
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) only when a launch needs more than any before it
@@ -352,6 +360,25 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
     const ctcb::Problem dp = to_device_problem(p);
     ctcb::Workspace w = carve(lay, workspace);
 
+    // ---- the one-kernel path (ctcb_meet.cuh): forward and gradient of small-vocabulary utterances in one CTA each ----
+    if (phases == (PH_FORWARD | PH_BACKWARD) && lay.fused && p->V <= 64 && p->Lmax + 1 <= 128 && meet_wanted(p->B)) {
+        const int mp = p->Lmax + 1 <= 32 ? 1 : p->Lmax + 1 <= 64 ? 2 : 4;
+        const size_t need = sizeof(int2) * (size_t)p->B * lay.NB * ctcb::kHR * 32 * mp;
+        if (lay.off_hA + need <= lay.total) {
+            if (p->status) CUDA_TRY(cudaMemsetAsync(p->status, 0, sizeof(int32_t) * (size_t)p->B, stream));
+            ctcb::MeetArgs ma{dp, w.hA, lay.NB};
+            using MeetFn = void (*)(ctcb::MeetArgs);
+            const MeetFn mfn = mp == 1 ? ctcb::k_meet<1> : mp == 2 ? ctcb::k_meet<2> : ctcb::k_meet<4>;
+            const size_t msm = ctcb::meet_smem_layout(mp, p->V, lay.Lp).total;
+            CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(mfn), msm));
+            g_walk_p = mp; g_walk_nw = 1;
+            mfn<<<p->B, 256, msm, stream>>>(ma);
+            mark(stream);
+            if (launch_pending_xchg(stream)) mark(stream);
+            CUDA_TRY(cudaGetLastError());
+            return CTCB_OK;
+        }
+    }
     if (phases & PH_FORWARD) {
         // status words: zeroed here, OR-ed into by the kernels (several CTAs of an utterance report bits)
         if (p->status) CUDA_TRY(cudaMemsetAsync(p->status, 0, sizeof(int32_t) * (size_t)p->B, stream));

@@ -837,3 +837,58 @@ def test_batch_size_regimes_vs_c_oracle(dev, B, T, V, L, seed):
     t = _to(dev, d)
     loss, grad = ctc_loss_and_grad(t["pred"], t["label"], t["pred_lengths"], t["label_lengths"])
     _check(loss.cpu().numpy(), grad.cpu().numpy(), lo, go, "B=%d" % B)
+
+
+# ---- the one-kernel path (ctcb_meet.cuh), opt-in through the "meet" option -----------------------------
+@pytest.mark.parametrize("B,T,V,L,seed,peaky", [
+    (2, 12, 5, 3, 1, False),        # one frame block more than the labels need
+    (3, 7, 46, 2, 3, False),        # a single (partial) frame block: the beta walker has no phase 1
+    (3, 9, 46, 4, 4, False),        # two frame blocks
+    (5, 100, 33, 40, 5, False),     # P = 2 state pairs per lane
+    (6, 64, 64, 31, 6, False),      # P = 1, the widest vocabulary of the path
+    (8, 200, 46, 50, 1, True),      # cfg1, peaky
+    (32, 500, 46, 120, 0, False),   # cfg2
+    (300, 120, 46, 120, 60, False), # more utterances than two per SM
+])
+def test_meet_in_the_middle_kernel_vs_c_oracle(dev, B, T, V, L, seed, peaky):
+    """k_meet (alpha and beta walkers of an utterance meet in the middle, occupancies normalised by P(l|x), one
+    launch): same tolerance against the fp64 C oracle as the two-kernel path, head gradients included, and the
+    same bits run after run."""
+    from gluon_e2e_asr_b200 import ctc_loss_and_grad, ops
+    d = make_batch(B, T, V, L, seed=seed, peaky=peaky)
+    head = np.linspace(0.5, 2.0, B)
+    lo, go, ok = _c_oracle(d, head=head)
+    t = _to(dev, d)
+    h = torch.tensor(head, device=dev, dtype=torch.float32)
+    with _env(meet=1):
+        ops._ws_cache.clear()
+        loss, grad = ctc_loss_and_grad(t["pred"], t["label"], t["pred_lengths"], t["label_lengths"], head_grad=h)
+        assert _lib_launches() == 1
+        l1, g1 = loss.clone(), grad.clone()
+        loss2, grad2 = ctc_loss_and_grad(t["pred"], t["label"], t["pred_lengths"], t["label_lengths"], head_grad=h,
+                                         out_grad=torch.full_like(grad, float("nan")))
+        assert torch.equal(l1, loss2) and torch.equal(g1, grad2)
+    ops._ws_cache.clear()
+    _check(l1.cpu().numpy(), g1.cpu().numpy(), lo, go, "k_meet B=%d" % B)
+
+
+def test_meet_kernel_edge_cases(dev):
+    """Infeasible utterances (loss 0, gradient 0, status bit), empty labels and a zero-length utterance through k_meet."""
+    from gluon_e2e_asr_b200 import ctc_loss_and_grad, ops
+    d = make_batch(6, 40, 11, 6, seed=9)
+    d["label"][1, :3] = 4; d["label_lengths"][1] = 3; d["pred_lengths"][1] = 4      # 3 repeats need 5 frames: infeasible
+    d["label_lengths"][2] = 0                                                         # empty label sequence
+    d["pred_lengths"][3] = 0                                                          # no frames at all
+    lo, go, ok = _c_oracle(d)
+    t = _to(dev, d)
+    status = torch.zeros((6,), dtype=torch.int32, device=dev)
+    with _env(meet=1):
+        ops._ws_cache.clear()
+        loss, grad = ctc_loss_and_grad(t["pred"], t["label"], t["pred_lengths"], t["label_lengths"], status=status)
+    ops._ws_cache.clear()
+    st = status.cpu().numpy()
+    assert st[1] & 1 and st[3] & 1 and not (st[0] & 1) and not (st[2] & 1)
+    l, g = loss.cpu().numpy(), grad.cpu().numpy()
+    assert l[1] == 0 and l[3] == 0 and not g[1].any() and not g[3].any()
+    feas = [0, 2, 4, 5]
+    _check(l[feas], g[feas], lo[feas], go[feas], "k_meet edge cases")
