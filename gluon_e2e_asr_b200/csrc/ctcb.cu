@@ -18,6 +18,7 @@
 #include "ctcb_dlpack.h"
 #include "ctcb_kernels.cuh"
 #include "ctcb_meet.cuh"
+#include "ctcb_grad2.cuh"
 
 struct ctcb_mailbox {
     int device = 0, rank = 0, world = 0;
@@ -57,9 +58,9 @@ thread_local int g_prof_count = 0;
 // Read from the environment ONCE (CTCB_<NAME>, at first use) and changeable through ctcb_set_option (tests, A/B
 // runs): nothing on the per-call host path calls getenv.  -1 = automatic.
 enum Opt { OPT_WALK_P, OPT_WALK_NW, OPT_WALK_STAGES, OPT_OVERLAP, OPT_FUSED, OPT_WALK_PER_SM, OPT_EMIT_STAGED,
-           OPT_GRAD_STAGED, OPT_MEET, OPT_COUNT };
+           OPT_GRAD_STAGED, OPT_MEET, OPT_GRAD2, OPT_GRAD2_BLOCKS, OPT_COUNT };
 const char* const kOptNames[OPT_COUNT] = {"walk_p", "walk_nw", "walk_stages", "overlap", "fused", "walk_per_sm",
-                                          "emit_staged", "grad_staged", "meet"};
+                                          "emit_staged", "grad_staged", "meet", "grad2", "grad2_blocks"};
 struct Options {
     int v[OPT_COUNT];
     Options() {
@@ -177,7 +178,7 @@ cudaError_t ensure_dynamic_smem(const void* fn, size_t bytes) {
 }
 
 struct Layout {
-    size_t off_Tb, off_Lb, off_flags, off_lab, off_rank, off_dl, off_nd, off_fr, off_E, off_hA, off_hB, off_oA, off_oB, off_gprog, total;
+    size_t off_Tb, off_Lb, off_flags, off_lab, off_rank, off_dl, off_nd, off_fr, off_E, off_hA, off_hB, off_oA, off_oB, off_gprog, off_runv, off_pinfo, total;
     int Lp, W, NB, dense, fused, P, NW;
     int stamp;               // nonzero hash of everything the workspace layout depends on (Workspace::stamp)
     const WalkEntry* walk;
@@ -215,6 +216,8 @@ Layout make_layout(int T, int B, int V, int Lmax, int need_grad) {
     l.off_dl = take(sizeof(int2) * (size_t)B * (l.Lp + 1));
     l.off_nd = take(sizeof(int) * B);
     l.off_gprog = take(sizeof(int) * 4 * (size_t)B);
+    l.off_runv = take(sizeof(int2) * 64 * (size_t)B);
+    l.off_pinfo = take(sizeof(int2) * (size_t)B);
     l.off_fr = take(sizeof(float2) * (size_t)B * T);
     l.off_E = take(l.fused ? 0 : sizeof(double) * (size_t)B * l.NB * l.W * ctcb::kEC);
     if (need_grad) {
@@ -247,6 +250,8 @@ ctcb::Workspace carve(const Layout& l, void* ws) {
     w.oA = reinterpret_cast<int2*>(base + l.off_oA);
     w.oB = reinterpret_cast<int2*>(base + l.off_oB);
     w.gprog = reinterpret_cast<int*>(base + l.off_gprog);
+    w.runv = reinterpret_cast<int2*>(base + l.off_runv);
+    w.pinfo = reinterpret_cast<int2*>(base + l.off_pinfo);
     w.Lp = l.Lp; w.W = l.W; w.NB = l.NB; w.dense = l.dense; w.P = l.P; w.NW = l.NW;
     w.fused = l.fused;
     w.stamp = l.stamp;
@@ -493,6 +498,21 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
 #undef GRADO_CH
 #undef GRADO_X
         }
+        bool grad2 = false;
+        // small vocabularies (fused path): the gradient kernel that normalises by P(l|x) (ctcb_grad2.cuh)
+        // (measured, scripts/grad2_blocks_sweep.py: from 48 utterances on it wins -- 13 % at B = 128 and 1024, 21 % at 256;
+        // below that the step is the walkers' chain plus the gradient kernel's tail, where k_grad is a little shorter)
+        const bool want_grad2 = opt(OPT_GRAD2) >= 0 ? opt(OPT_GRAD2) != 0 : (p->B >= 48 && ch <= 4);
+        if (lay.fused && p->V <= 64 && ch >= 1 && want_grad2) {
+            const bool occ = !((phases & PH_FORWARD) && !g_prof_events && overlap_allowed(p->B, true));
+#define GRAD2_O(V_, C_) (occ ? ctcb::k_grad2<V_, C_, 1> : ctcb::k_grad2<V_, C_, 0>)
+#define GRAD2_CH(V_) (ch == 1 ? GRAD2_O(V_, 1) : ch == 2 ? GRAD2_O(V_, 2) : ch == 4 ? GRAD2_O(V_, 4) : ch == 8 ? GRAD2_O(V_, 8) : GRAD2_O(V_, 16))
+            gfn = vec == 4 ? GRAD2_CH(4) : vec == 2 ? GRAD2_CH(2) : GRAD2_CH(1);
+#undef GRAD2_CH
+#undef GRAD2_O
+            gsm = ctcb::grad2_smem_bytes(ch);
+            grad2 = true;
+        }
         // wide vocabularies with 16-byte aligned rows: the frame block's rows staged in shared memory by bulk copies
         const size_t gsm_staged = ctcb::grad_smem_bytes(lay.Lp, 32 * gch, p->V);
         if (xq == 0 && vec == 4 && gsm_staged <= 75 * 1024 && opt(OPT_GRAD_STAGED) != 0) {
@@ -509,6 +529,11 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
         const bool overlap = (phases & PH_FORWARD) && !g_prof_events && overlap_allowed(p->B, lay.fused != 0);
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = ggrid; cfg.blockDim = dim3(gthreads); cfg.dynamicSmemBytes = gsm; cfg.stream = stream;
+        if (grad2) {
+            // k_grad2: a CTA takes several consecutive frame blocks (metadata and P(l|x) once per CTA)
+            const int gb = opt(OPT_GRAD2_BLOCKS) > 0 ? opt(OPT_GRAD2_BLOCKS) : (p->B >= 96 ? 4 : 2);
+            cfg.gridDim = dim3(p->B, (lay.NB + gb - 1) / gb);
+        }
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;

@@ -73,9 +73,13 @@ struct Workspace {        // carved out of the caller's workspace by the host (c
     int2* hB;                         // same for beta'_t in the reversed walker's pair coordinates, relative to oB
     int2* oA;                         // (B, NB, NW*PW) exponent offsets {blank, label} valid for frame block n
     int2* oB;
+    int2* runv;                       // (B, 64) small vocabularies (fused path): the run [start, end) of every symbol's label
+                                      //   positions in rank order (empty for symbols the utterance does not use)
+    int2* pinfo;                      // (B,) {exponent of P(l|x), bits of the float 1 / mantissa}: written by the gradient
+                                      //   kernel's middle frame block (k_grad2), read by the utterance's other blocks
     int* gprog;                       // (B, 4) {frame blocks whose history is complete: alpha walker, beta walker;
-                                      //   metadata ready (Tb, Lb, flags, rank, dl, nd)}: published with release/gpu
-                                      //   scope, polled by the gradient CTAs
+                                      //   metadata ready (Tb, Lb, flags, rank, dl, nd); pinfo ready}: published with
+                                      //   release/gpu scope, polled by the gradient CTAs
     int Lp, W, NB, dense, P, NW;      // PW = 32*P pairs per walker warp
     int stamp;                        // nonzero hash of the call's shape and layout choices: the value of the
                                       //   "metadata ready" progress word, checked by the gradient CTAs (a workspace
@@ -723,6 +727,8 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
             const int nd = __popc(m0) + __popc(m1);
             if (c0 > 0) dl[__popc(m0 & below)] = make_int2(lane, r0);
             if (c1 > 0) dl[__popc(m0) + __popc(m1 & below)] = make_int2(lane + 32, r1);
+            w.runv[(size_t)b * 64 + lane] = make_int2(r0, r0 + c0);
+            w.runv[(size_t)b * 64 + lane + 32] = make_int2(r1, r1 + c1);
             for (int j = 0; j < Lb; ++j) {
                 const int v = slab[j];
                 if (v == lane) rank[j] = r0++;
@@ -1092,7 +1098,7 @@ __global__ void __launch_bounds__((NW + (FUSED ? kFusedProducers + 1 : 1)) * 32)
     if (tid == 0) {
         // the progress words of this call start at 0 BEFORE any gradient CTA can exist
         w.gprog[4 * b + blockIdx.y] = 0;
-        if (blockIdx.y == 0) w.gprog[4 * b + 2] = 0;
+        if (blockIdx.y == 0) { w.gprog[4 * b + 2] = 0; w.gprog[4 * b + 3] = 0; }
         __threadfence();
         s_L = p.Lmax; s_rep = 0; s_flags = 0;
     }

@@ -641,8 +641,8 @@ __device__ __forceinline__ void meet_helper(const MeetCtx& c, const Problem& p, 
                     // leaves the normal range (gamma below 2^-1022 times the largest beta') is flushed to zero
                     int tb = a_.x != 0 ? (int)((unsigned)a_.x + (unsigned)dsb[q]) : 0, tl = a_.y != 0 ? (int)((unsigned)a_.y + (unsigned)dsl[q]) : 0;
                     tb = tb < (1 << 20) ? 0 : tb; tl = tl < (1 << 20) ? 0 : tl;
-                    zb[f] += (float)(__hiloint2double(tb, 0) * __hiloint2double(hbb[f][q], 0));
-                    const float gl = (float)(__hiloint2double(tl, 0) * __hiloint2double(hbl[f][q], 0));
+                    zb[f] += (float)(__hiloint2double(tb, 0) * __hiloint2double(tb ? hbb[f][q] : 0, 0));
+                    const float gl = (float)(__hiloint2double(tl, 0) * __hiloint2double(tl ? hbl[f][q] : 0, 0));
                     sts_f32(rowbuf + (uint32_t)(f * PW + rk[q]) * 4u, gl);
                 }
             }
@@ -663,7 +663,8 @@ __device__ __forceinline__ void meet_helper(const MeetCtx& c, const Problem& p, 
                     const float y0 = __shfl_up_sync(FULL, t0_, o), y1 = __shfl_up_sync(FULL, t1_, o);
                     if (lane >= o) { t0_ += y0; t1_ += y1; }
                 }
-                const float e0 = t0_ - sc[0][P - 1], e1 = t1_ - sc[1][P - 1];      // exclusive lane offsets
+                float e0 = __shfl_up_sync(FULL, t0_, 1), e1 = __shfl_up_sync(FULL, t1_, 1);      // exclusive lane offsets
+                if (lane == 0) { e0 = 0.0f; e1 = 0.0f; }
 #pragma unroll
                 for (int q = 0; q < P; ++q) {
                     sts_f32(sumbuf + (uint32_t)(lane * P + q) * 4u, sc[0][q] + e0);

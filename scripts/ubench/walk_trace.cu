@@ -21,7 +21,7 @@ int main(int argc, char** argv) {
     const int V = 46, W = 46, Lp = (L + 3) / 4 * 4, NB = (T + kG - 1) / kG, PAIRS = TNW * TP * 32;
     Workspace w{};
     cudaMalloc(&w.Tb, B * 4); cudaMalloc(&w.Lb, B * 4); cudaMalloc(&w.flags, B * 4); cudaMalloc(&w.nd, B * 4);
-    cudaMalloc(&w.rank, (size_t)B * Lp * 4); cudaMalloc(&w.dl, (size_t)B * (Lp + 1) * 8); cudaMalloc(&w.gprog, B * 16);
+    cudaMalloc(&w.rank, (size_t)B * Lp * 4); cudaMalloc(&w.dl, (size_t)B * (Lp + 1) * 8); cudaMalloc(&w.gprog, B * 16); cudaMalloc(&w.runv, (size_t)B * 64 * 8); cudaMalloc(&w.pinfo, (size_t)B * 8);
     cudaMalloc(&w.hA, (size_t)B * NB * kG * PAIRS * 8); cudaMalloc(&w.hB, (size_t)B * NB * kG * PAIRS * 8);
     cudaMalloc(&w.oA, (size_t)B * NB * PAIRS * 8); cudaMalloc(&w.oB, (size_t)B * NB * PAIRS * 8);
     cudaMalloc(&w.fr, (size_t)B * T * 8);

@@ -892,3 +892,60 @@ def test_meet_kernel_edge_cases(dev):
     assert l[1] == 0 and l[3] == 0 and not g[1].any() and not g[3].any()
     feas = [0, 2, 4, 5]
     _check(l[feas], g[feas], lo[feas], go[feas], "k_meet edge cases")
+
+
+# ---- k_grad2: the gradient kernel that normalises by P(l|x) (ctcb_grad2.cuh) ---------------------------
+@pytest.mark.parametrize("B,T,V,L,seed,peaky,blocks", [
+    (2, 12, 5, 3, 1, False, 1), (3, 7, 46, 2, 3, False, 4), (5, 100, 33, 40, 5, False, 2), (6, 64, 64, 31, 6, False, 4),
+    (8, 200, 46, 50, 1, True, 3), (32, 500, 46, 120, 0, False, 4), (8, 300, 46, 200, 7, False, 2),
+    (16, 2000, 46, 300, 0, False, 16), (300, 120, 46, 120, 60, False, 4),
+])
+def test_grad2_kernel_vs_c_oracle(dev, B, T, V, L, seed, peaky, blocks):
+    """k_grad2 forced on (it is the default only from 48 utterances on): every register-chunk variant (CH 1..16),
+    several frame blocks per CTA, overlapped and serial launches -- same tolerance against the fp64 C oracle, the same
+    loss bits as the k_grad path, the same gradient bits run after run and under both schedules."""
+    from gluon_e2e_asr_b200 import ctc_loss_and_grad, ops
+    d = make_batch(B, T, V, L, seed=seed, peaky=peaky)
+    head = np.linspace(0.5, 2.0, B)
+    lo, go, ok = _c_oracle(d, head=head)
+    t = _to(dev, d)
+    h = torch.tensor(head, device=dev, dtype=torch.float32)
+    args = (t["pred"], t["label"], t["pred_lengths"], t["label_lengths"])
+    with _env(grad2=0):
+        ops._ws_cache.clear()
+        l_old, _ = ctc_loss_and_grad(*args, head_grad=h)
+        l_old = l_old.clone()
+    with _env(grad2=1, grad2_blocks=blocks):
+        ops._ws_cache.clear()
+        loss, grad = ctc_loss_and_grad(*args, head_grad=h)
+        l1, g1 = loss.clone(), grad.clone()
+        loss2, grad2 = ctc_loss_and_grad(*args, head_grad=h, out_grad=torch.full_like(grad, float("nan")))
+        assert torch.equal(l1, loss2) and torch.equal(g1, grad2)
+        with _env(overlap=0):
+            loss3, grad3 = ctc_loss_and_grad(*args, head_grad=h, out_grad=torch.full_like(grad, float("nan")))
+        assert torch.equal(l1, loss3)
+        torch.testing.assert_close(grad3, g1, rtol=1e-6, atol=1e-7)
+    ops._ws_cache.clear()
+    assert torch.equal(l1, l_old)
+    _check(l1.cpu().numpy(), g1.cpu().numpy(), lo, go, "k_grad2 B=%d" % B)
+
+
+def test_grad2_forward_backward_split_and_edge_cases(dev):
+    """k_grad2 behind ctcb_forward(keep) / ctcb_backward (the autograd split) and on infeasible / empty utterances."""
+    from gluon_e2e_asr_b200 import CtcLoss, ops
+    d = make_batch(64, 120, 46, 30, seed=11)
+    d["label"][1, :3] = 4; d["label_lengths"][1] = 3; d["pred_lengths"][1] = 4      # infeasible
+    d["label_lengths"][2] = 0                                                         # empty label sequence
+    d["pred_lengths"][3] = 0                                                          # no frames
+    lo, go, ok = _c_oracle(d, head=np.full((64,), 1.0 / 64))
+    t = _to(dev, d)
+    with _env(grad2=1):
+        ops._ws_cache.clear()
+        pred = t["pred"].clone().requires_grad_(True)
+        loss = CtcLoss(layout="NTC", label_layout="NT")(pred, t["label"], t["pred_lengths"], t["label_lengths"])
+        loss.mean().backward()
+    ops._ws_cache.clear()
+    l, g = loss.detach().cpu().numpy(), pred.grad.cpu().numpy()
+    assert l[1] == 0 and l[3] == 0 and not g[1].any() and not g[3].any()
+    feas = [b for b in range(64) if b not in (1, 3)]
+    _check(l[feas], g[feas], lo[feas], go[feas], "k_grad2 split")
