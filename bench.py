@@ -657,7 +657,8 @@ def run_cuda(args, rank, world, local_rank):
                 alg += algorithmic_bytes(V, T, B, s["np"]["pred_lengths"], s["np"]["label_lengths"])
     kms = kms[:nk.value] / nrep
     alg /= nrep
-    knames = ["k_emit", "k_walk", "k_grad"] if nk.value == 3 else ["k_walk", "k_grad"]
+    gname = _lib.last_grad_kernel() or "k_grad"            # k_grad, or k_grad2 from 48 utterances per GPU on
+    knames = ["k_emit", "k_walk", gname] if nk.value == 3 else ["k_walk", gname]
     dom = int(np.argmax(kms))
     peak, peak_src = measured_peak()
     achieved = alg / (kms[dom] * 1e-3) / 1e9
@@ -668,7 +669,7 @@ def run_cuda(args, rank, world, local_rank):
             with open(tp) as f:
                 tj = json.load(f)
             tw = tj.get(name, {})
-            traffic = tw.get("whole_step", tw.get(knames[dom])) if world == 1 else None
+            traffic = tw.get("whole_step", tw.get(knames[dom].replace("k_grad2", "k_grad"))) if world == 1 else None
             traffic_src = tj.get("_source")
         except Exception:
             traffic = None

@@ -26,7 +26,7 @@ EXPORTS = (
     "ctcb_pipe_create", "ctcb_pipe_submit", "ctcb_pipe_wait", "ctcb_pipe_destroy", "ctcb_pipe_last_h2d_bytes",
     "ctcb_mailbox_create", "ctcb_mailbox_handle", "ctcb_mailbox_connect", "ctcb_mailbox_exchange",
     "ctcb_mailbox_flush", "ctcb_mailbox_destroy", "ctcb_mailbox_exchange_with_next",
-    "ctcb_set_option", "ctcb_get_option", "ctcb_greedy_decode_unk",
+    "ctcb_set_option", "ctcb_get_option", "ctcb_greedy_decode_unk", "ctcb_last_grad_kernel",
 )
 
 
@@ -157,6 +157,11 @@ def workspace_bytes(T, B, V, Lmax, need_grad=True):
 
 def last_launch_count():
     return int(load().ctcb_last_launch_count())
+
+
+def last_grad_kernel():
+    """Name of the gradient kernel the last call on this thread launched (ctcb_last_grad_kernel)."""
+    return {0: None, 1: "k_grad", 2: "k_grad2", 3: "k_meet"}[int(load().ctcb_last_grad_kernel())]
 
 
 def last_walk_config():

@@ -33,7 +33,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 thread_local int g_launches = 0;
-thread_local int g_walk_p = 0, g_walk_nw = 0;
+thread_local int g_walk_p = 0, g_walk_nw = 0, g_grad_kernel = 0;
 struct PendingXchg { struct ctcb_mailbox* mb = nullptr; double* values = nullptr; double* out = nullptr; int count = 0; };
 thread_local PendingXchg g_xchg;                      // ctcb_mailbox_exchange_with_next: consumed by the next gradient launch
 // enqueues the pending exchange (if any) on `stream`; true when a kernel was launched.  programmatic: as the
@@ -58,9 +58,9 @@ thread_local int g_prof_count = 0;
 // Read from the environment ONCE (CTCB_<NAME>, at first use) and changeable through ctcb_set_option (tests, A/B
 // runs): nothing on the per-call host path calls getenv.  -1 = automatic.
 enum Opt { OPT_WALK_P, OPT_WALK_NW, OPT_WALK_STAGES, OPT_OVERLAP, OPT_FUSED, OPT_WALK_PER_SM, OPT_EMIT_STAGED,
-           OPT_GRAD_STAGED, OPT_MEET, OPT_GRAD2, OPT_GRAD2_BLOCKS, OPT_COUNT };
+           OPT_GRAD_STAGED, OPT_MEET, OPT_GRAD2, OPT_GRAD2_BLOCKS, OPT_WALK_HW_WAIT, OPT_COUNT };
 const char* const kOptNames[OPT_COUNT] = {"walk_p", "walk_nw", "walk_stages", "overlap", "fused", "walk_per_sm",
-                                          "emit_staged", "grad_staged", "meet", "grad2", "grad2_blocks"};
+                                          "emit_staged", "grad_staged", "meet", "grad2", "grad2_blocks", "walk_hw_wait"};
 struct Options {
     int v[OPT_COUNT];
     Options() {
@@ -319,6 +319,8 @@ int ctcb_last_walk_config(int32_t* p, int32_t* nw) {
     return CTCB_OK;
 }
 
+int ctcb_last_grad_kernel(void) { return g_grad_kernel; }
+
 int ctcb_set_option(const char* name, int32_t value) {
     if (!name) return fail(CTCB_INVALID_VALUE, "option name is NULL");
     for (int i = 0; i < OPT_COUNT; ++i)
@@ -350,6 +352,7 @@ inline void mark(cudaStream_t stream) {
 }
 
 int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, void* stream_, int phases, bool keep_hist) {
+    g_grad_kernel = 0;
     if (int rc = validate(p)) return rc;
     const bool need_grad = keep_hist || (phases & PH_BACKWARD);
     if ((phases & PH_BACKWARD) && !p->grad) return fail(CTCB_INVALID_VALUE, "grad is NULL");
@@ -376,7 +379,7 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
             const MeetFn mfn = mp == 1 ? ctcb::k_meet<1> : mp == 2 ? ctcb::k_meet<2> : ctcb::k_meet<4>;
             const size_t msm = ctcb::meet_smem_layout(mp, p->V, lay.Lp).total;
             CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(mfn), msm));
-            g_walk_p = mp; g_walk_nw = 1;
+            g_walk_p = mp; g_walk_nw = 1; g_grad_kernel = 3;
             mfn<<<p->B, 256, msm, stream>>>(ma);
             mark(stream);
             if (launch_pending_xchg(stream)) mark(stream);
@@ -404,7 +407,11 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
             int per_sm = (2 * p->B + nsm - 1) / nsm;
-            if (opt(OPT_WALK_PER_SM) > per_sm) per_sm = opt(OPT_WALK_PER_SM);
+            // from ~80 utterances on the step is bound by the gradient kernel's throughput, not by the walkers' chain: the
+            // walkers are packed four to an SM and the gradient CTAs get the other SMs while the walkers run
+            // (scripts/regime_sweep.py: B = 96 89.8 -> 80.2 us, 128 113.5 -> 102.6, 148 126.4 -> 111.8)
+            if (p->B >= 80 && per_sm < 4) per_sm = 4;
+            if (opt(OPT_WALK_PER_SM) > 0) per_sm = opt(OPT_WALK_PER_SM) > (2 * p->B + nsm - 1) / nsm ? opt(OPT_WALK_PER_SM) : (2 * p->B + nsm - 1) / nsm;
             const size_t share = (size_t)233472 / per_sm;
             size_t want = share > 2048 ? (share - 1024) / 128 * 128 : 0;
             cudaFuncAttributes fa{};
@@ -453,7 +460,12 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
         const bool xchg = !(phases & PH_BACKWARD) && launch_pending_xchg(stream);
         if (xchg) mark(stream);
         auto launch_walk = [&](bool after_xchg) -> int {
-            ctcb::WalkArgs wa{dp, w, p->T, stages, p->blank, p->loss, p->loss_sum, nullptr};
+            ctcb::WalkArgs wa{dp, w, p->T, stages, p->blank, p->loss, p->loss_sum, nullptr, 0, 1};
+            // several walker CTAs per SM: the producers wait in hardware (no polling instructions)
+            wa.hw_wait = opt(OPT_WALK_HW_WAIT) >= 0 ? opt(OPT_WALK_HW_WAIT) : (2 * p->B > 148 ? 1 : 0);
+            // the per-group progress is for gradient CTAs that run concurrently with the walkers; a gradient kernel that
+            // runs afterwards polls the same words once, so the final count is enough
+            wa.publish = ((phases & PH_BACKWARD) && !g_prof_events && overlap_allowed(p->B, lay.fused != 0)) ? 1 : 2;
             const int wthreads = (we->NW + (lay.fused ? ctcb::kFusedProducers + 1 : 1)) * 32;
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3(p->B, need_grad ? 2 : 1); cfg.blockDim = dim3(wthreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
@@ -539,6 +551,7 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = overlap ? 1 : 0;
         CUDA_TRY(cudaLaunchKernelEx(&cfg, gfn, ga));
+        g_grad_kernel = grad2 ? 2 : 1;
         mark(stream);
         // ctcb_mailbox_exchange_with_next: behind the gradient kernel, as its programmatic dependent
         if (launch_pending_xchg(stream, true)) mark(stream);

@@ -493,7 +493,11 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
 }
 // wait of a warp that has slack (producers run many blocks ahead): it shares an SM sub-partition
 // with a walker warp whose dependent chain is the critical path, so it must not spin on the issue port
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, int hw_wait = 0) {
+    // hw_wait: mbarrier.try_wait suspends the warp in hardware -- no polling instructions at all, which is what
+    // counts when several walker CTAs share an SM and the kernel is bound by instruction issue (throughput
+    // regime: the nanosleep polls were a quarter of k_walk's executed instructions at B = 1024)
+    if (hw_wait) { mbar_wait(bar, parity); return; }
     while (!mbar_test(bar, parity)) __nanosleep(128);
 }
 __device__ __forceinline__ void st_release_gpu(int* p, int v) {
@@ -584,6 +588,9 @@ struct WalkArgs {
     Problem p;             // read by the fused variant only (parameter layer + logits)
     Workspace w; int T; int stages; int blank; float* loss; double* loss_sum;
     long long* trace;      // debug only (scripts/ubench/walk_trace.cu); nullptr in the product
+    int hw_wait;           // producers wait on mbarrier.try_wait (hardware suspend) instead of nanosleep polls
+    int publish;           // 1: the progress of every group is published promptly (gradient CTAs run concurrently);
+                           // 2: lazily (the gradient kernel runs after this one: only the final count matters)
 };
 
 #ifdef CTCB_TRACE
@@ -690,7 +697,7 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
                 w.fr[(size_t)b * a.T + t] = make_float2(mx, l2);
             }
             const int st = n % NS, use = n / NS;
-            if (use > 0) mbar_wait_relaxed(&empty[st], (uint32_t)((use - 1) & 1));
+            if (use > 0) mbar_wait_relaxed(&empty[st], (uint32_t)((use - 1) & 1), a.hw_wait);
             const uint32_t dst = ring + (uint32_t)st * stage_bytes + (uint32_t)col0 * (kEC * 8u) + (uint32_t)fj * 8u;
 #pragma unroll
             for (int i = 0; i < CPL; ++i)
@@ -741,7 +748,7 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
             __syncwarp();
             if (lane == 0) st_release_gpu(w.gprog + 4 * b + 2, w.stamp);
         }
-        if (HIST && lane == 0) {
+        if (HIST && lane == 0 && a.publish) {
             // the last walker warp's group count (shared memory) -> global progress for the gradient CTAs
             int* gp = w.gprog + 4 * b + DIR;
             const uint32_t last_prog = prog + (NW - 1) * 4;
@@ -749,7 +756,7 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
             while (seen < NQ) {
                 const int v = lds_acquire(last_prog);
                 if (v > seen) { st_release_gpu(gp, v); seen = v; }
-                else __nanosleep(128);
+                else __nanosleep(a.publish == 2 ? 4000 : 128);
             }
         }
         (void)p;
@@ -783,7 +790,7 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
             int* gp = HIST ? w.gprog + 4 * b + DIR : nullptr;
             int st = 0; uint32_t par = 0;
             for (int n = 0; n < NQ; ++n) {
-                mbar_wait_relaxed(&empty[st], par);
+                mbar_wait_relaxed(&empty[st], par, a.hw_wait);
                 if (n + NS < NQ) issue(n + NS, st);
                 if (++st == NS) { st = 0; par ^= 1; }
                 if (HIST && (n + 1 == NQ || !mbar_test(&empty[st], par))) st_release_gpu(gp, n + 1);

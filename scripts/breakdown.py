@@ -11,7 +11,8 @@ dev = torch.device("cuda:0")
 lib = _lib.load()
 names = sys.argv[1].split(",") if len(sys.argv) > 1 else ["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"]
 for name in names:
-    B, T, V, L = CONFIGS[name]
+    # a BASELINE config, or B:T:V:L
+    B, T, V, L = CONFIGS[name] if name in CONFIGS else tuple(int(x) for x in name.split(":"))
     d = make_batch(B, T, V, L, seed=0, full_lengths=(name == "cfg5"))
     t = {k: torch.tensor(v, device=dev) for k, v in d.items()}
     loss = torch.empty((B,), device=dev); grad = torch.empty_like(t["pred"])
@@ -30,7 +31,7 @@ for name in names:
     for i in range(20):
         _lib.check(lib.ctcb_loss_grad(ctypes.byref(p), ws.data_ptr(), ws.numel(), None))
     e1.record(); torch.cuda.synchronize()
-    print(name, "walk cfg", _lib.last_walk_config(), "kernel us", [round(float(x) * 1e3, 1) for x in acc[:nk.value]],
+    print(name, "walk cfg", _lib.last_walk_config(), _lib.last_grad_kernel(), "kernel us", [round(float(x) * 1e3, 1) for x in acc[:nk.value]],
           "back-to-back step us %.1f" % (e0.elapsed_time(e1) * 1e3 / 20), "ws MB %.0f" % (ws.numel() / 1e6), flush=True)
     del ws, grad, t
     torch.cuda.empty_cache()

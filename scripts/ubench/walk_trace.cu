@@ -46,7 +46,7 @@ int main(int argc, char** argv) {
     size_t smem = walk_smem_bytes(W, TNW, stages, Lp);
     auto fn = k_walk<TP, TNW, THIST, true>;
     cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    WalkArgs a{p, w, T, stages, 0, loss, nullptr, trace};
+    WalkArgs a{p, w, T, stages, 0, loss, nullptr, trace, 0, 1};
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int rep = 0; rep < 3; ++rep) {
         cudaMemset(trace, 0, tn * 8);
