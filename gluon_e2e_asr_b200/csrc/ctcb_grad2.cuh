@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(128, CH <= 4 ? (OCC ? 8 : 5) : (CH == 8 ? 4 : 
 #pragma unroll
         for (int r = 0; r < FPW / F; ++r) {
             int tt[F]; bool live[F];
-            int2 ha[F][CH <= 4 ? CH : 1]; int hbb[F][CH <= 4 ? CH : 1], hbl[F][CH <= 4 ? CH : 1];
+            int2 ha[F][CH <= 4 ? CH : 1], hb2[F][CH <= 4 ? CH : 1];
             V_t xr[F][NXQ]; float2 fr[F];
             // ---- every global load of the F frames ----
 #pragma unroll
@@ -202,8 +202,7 @@ __global__ void __launch_bounds__(128, CH <= 4 ? (OCC ? 8 : 5) : (CH == 8 ? 4 : 
 #pragma unroll
                         for (int c = 0; c < (CH <= 4 ? CH : 1); ++c) {
                             ha[f][c] = __ldcg(A + c * 32);
-                            hbb[f][c] = __ldcg(&Bh[ibb[c]].x);
-                            hbl[f][c] = __ldcg(&Bh[ibl[c]].y);
+                            hb2[f][c] = __ldcg(Bh + ibb[c]);       // {blank of slot L-g, label of slot L-g}: ONE 8-byte load
                         }
                     }
                 }
@@ -226,8 +225,14 @@ __global__ void __launch_bounds__(128, CH <= 4 ? (OCC ? 8 : 5) : (CH == 8 ? 4 : 
                     gbuf[rk[c]] = (float)(__hiloint2double(tl, 0) * __hiloint2double(tl ? hl : 0, 0));
                 };
                 if (CH <= 4) {
+                    // the label state of slot L-1-g is the label word the lane ABOVE loaded (its g is one higher; the
+                    // clamped indices agree: max(L-(g+1), 0) = max(L-1-g, 0)); lane 31 takes it from the next chunk's lane 0
 #pragma unroll
-                    for (int c = 0; c < (CH <= 4 ? CH : 1); ++c) occupancy(ha[f][c], hbb[f][c], hbl[f][c], c);
+                    for (int c = 0; c < (CH <= 4 ? CH : 1); ++c) {
+                        int hl = __shfl_down_sync(FULL, hb2[f][c].y, 1);
+                        if (c + 1 < (CH <= 4 ? CH : 1)) { const int nx = __shfl_sync(FULL, hb2[f][c + 1 < (CH <= 4 ? CH : 1) ? c + 1 : c].y, 0); if (lane == 31) hl = nx; }
+                        occupancy(ha[f][c], hb2[f][c].x, hl, c);
+                    }
                 } else {
                     const int2* A = hA0 + (size_t)(t - t_first) * pairs + lane;
                     const int2* Bh = hB0 + (size_t)(t - t_first) * pairs;
