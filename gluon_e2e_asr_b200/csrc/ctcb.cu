@@ -58,9 +58,9 @@ thread_local int g_prof_count = 0;
 // Read from the environment ONCE (CTCB_<NAME>, at first use) and changeable through ctcb_set_option (tests, A/B
 // runs): nothing on the per-call host path calls getenv.  -1 = automatic.
 enum Opt { OPT_WALK_P, OPT_WALK_NW, OPT_WALK_STAGES, OPT_OVERLAP, OPT_FUSED, OPT_WALK_PER_SM, OPT_EMIT_STAGED,
-           OPT_GRAD_STAGED, OPT_MEET, OPT_GRAD2, OPT_GRAD2_BLOCKS, OPT_WALK_HW_WAIT, OPT_COUNT };
+           OPT_GRAD_STAGED, OPT_MEET, OPT_GRAD2, OPT_GRAD2_BLOCKS, OPT_WALK_HW_WAIT, OPT_GRAD2_OCC, OPT_COUNT };
 const char* const kOptNames[OPT_COUNT] = {"walk_p", "walk_nw", "walk_stages", "overlap", "fused", "walk_per_sm",
-                                          "emit_staged", "grad_staged", "meet", "grad2", "grad2_blocks", "walk_hw_wait"};
+                                          "emit_staged", "grad_staged", "meet", "grad2", "grad2_blocks", "walk_hw_wait", "grad2_occ"};
 struct Options {
     int v[OPT_COUNT];
     Options() {
@@ -516,7 +516,10 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
         // below that the step is the walkers' chain plus the gradient kernel's tail, where k_grad is a little shorter)
         const bool want_grad2 = opt(OPT_GRAD2) >= 0 ? opt(OPT_GRAD2) != 0 : (p->B >= 48 && ch <= 4);
         if (lay.fused && p->V <= 64 && ch >= 1 && want_grad2) {
-            const bool occ = !((phases & PH_FORWARD) && !g_prof_events && overlap_allowed(p->B, true));
+            // two register budgets (profiles/r3e_*, r3f_*): 80 registers / 6 CTAs per SM while the walkers run beside the
+            // kernel, 72 registers / 7 CTAs per SM for batches whose gradient kernel runs after the walkers
+            bool occ = (phases & PH_FORWARD) && !g_prof_events && overlap_allowed(p->B, true);
+            if (opt(OPT_GRAD2_OCC) >= 0) occ = opt(OPT_GRAD2_OCC) != 0;
 #define GRAD2_O(V_, C_) (occ ? ctcb::k_grad2<V_, C_, 1> : ctcb::k_grad2<V_, C_, 0>)
 #define GRAD2_CH(V_) (ch == 1 ? GRAD2_O(V_, 1) : ch == 2 ? GRAD2_O(V_, 2) : ch == 4 ? GRAD2_O(V_, 4) : ch == 8 ? GRAD2_O(V_, 8) : GRAD2_O(V_, 16))
             gfn = vec == 4 ? GRAD2_CH(4) : vec == 2 ? GRAD2_CH(2) : GRAD2_CH(1);
@@ -543,7 +546,7 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
         cfg.gridDim = ggrid; cfg.blockDim = dim3(gthreads); cfg.dynamicSmemBytes = gsm; cfg.stream = stream;
         if (grad2) {
             // k_grad2: a CTA takes several consecutive frame blocks (metadata and P(l|x) once per CTA)
-            const int gb = opt(OPT_GRAD2_BLOCKS) > 0 ? opt(OPT_GRAD2_BLOCKS) : (p->B >= 96 ? 4 : 2);
+            const int gb = opt(OPT_GRAD2_BLOCKS) > 0 ? opt(OPT_GRAD2_BLOCKS) : 4;      // one whole frame block per warp
             cfg.gridDim = dim3(p->B, (lay.NB + gb - 1) / gb);
         }
         cudaLaunchAttribute attr[1];

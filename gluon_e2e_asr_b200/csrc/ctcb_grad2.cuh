@@ -22,8 +22,9 @@ namespace ctcb {
 
 __host__ __device__ inline size_t grad2_smem_bytes(int CH) { return (size_t)4 * 2 * 2 * 32 * CH * 4 + 64 * 8; }
 
+// OCC = 1: 6 CTAs per SM (80 registers); OCC = 0: 7 CTAs per SM (72 registers, a few spilled words)
 template <int VEC, int CH, int OCC>
-__global__ void __launch_bounds__(128, CH <= 4 ? (OCC ? 8 : 5) : (CH == 8 ? 4 : 2)) k_grad2(GradArgs a) {
+__global__ void __launch_bounds__(128, CH <= 4 ? (OCC ? 6 : 7) : (CH == 8 ? 4 : 2)) k_grad2(GradArgs a) {
     using V_t = typename VecT<VEC>::type;
     constexpr int FPW = kGradFramesPerWarp;               // 2 frames per warp, 4 warps: one frame block per trip
     constexpr int F = CH <= 4 ? FPW : 1;                  // frames in flight per warp
@@ -148,8 +149,10 @@ __global__ void __launch_bounds__(128, CH <= 4 ? (OCC ? 8 : 5) : (CH == 8 ? 4 : 
         }
 
     // ---- the CTA's frame blocks; no CTA barrier from here on: every warp waits for its blocks itself ----
+    // A warp takes WHOLE frame blocks (all kG frames, F at a time): the block's exponent shifts are formed once per
+    // kG frames, not once per two (ncu at cfg5: the per-block part was 130 of 490 instructions per frame)
 #pragma unroll 1
-    for (int i = 0; i < G; ++i) {
+    for (int i = warp; i < G; i += 4) {
         const int vi = blockIdx.y * G + i;
         if (vi >= w.NB) break;
         const int blk = block_of(vi);
@@ -163,7 +166,7 @@ __global__ void __launch_bounds__(128, CH <= 4 ? (OCC ? 8 : 5) : (CH == 8 ? 4 : 
         int dsb[CH], dsl[CH];
         if (blk_live) {
             if (!wait_block(blk)) {
-                for (int t = t_first + warp * FPW; t < t_first + warp * FPW + FPW && t < p.T; ++t) {
+                for (int t = t_first; t < t_first + kG && t < p.T; ++t) {
                     float* grow = p.grad + b * p.gst_b + (long long)t * p.gst_t;
                     for (int v = lane; v < p.V; v += 32) grow[v] = __int_as_float(0x7fc00000);
                 }
@@ -180,15 +183,15 @@ __global__ void __launch_bounds__(128, CH <= 4 ? (OCC ? 8 : 5) : (CH == 8 ? 4 : 
                 dsl[c] = g < Lb ? dl * (1 << 20) : INT_MIN;
             }
         }
-#pragma unroll
-        for (int r = 0; r < FPW / F; ++r) {
+#pragma unroll 1
+        for (int r = 0; r < kG / F; ++r) {
             int tt[F]; bool live[F];
             int2 ha[F][CH <= 4 ? CH : 1], hb2[F][CH <= 4 ? CH : 1];
             V_t xr[F][NXQ]; float2 fr[F];
             // ---- every global load of the F frames ----
 #pragma unroll
             for (int f = 0; f < F; ++f) {
-                tt[f] = t_first + warp * FPW + r * F + f;
+                tt[f] = t_first + r * F + f;
                 live[f] = blk_live && tt[f] < Tb;
                 fr[f] = make_float2(0.0f, 0.0f);
                 if (live[f]) {
@@ -213,8 +216,8 @@ __global__ void __launch_bounds__(128, CH <= 4 ? (OCC ? 8 : 5) : (CH == 8 ? 4 : 
                 if (t >= p.T) continue;
                 float* grow = p.grad + b * p.gst_b + (long long)t * p.gst_t;
                 if (!live[f]) { zero_row<VEC>(grow, p.V, lane); continue; }
-                float* gbuf = gbuf0 + (size_t)(r * F + f) * GW;             // gamma of the label states, rank order
-                float* sbuf = gbuf0 + (size_t)(FPW + r * F + f) * GW;       // inclusive prefix sums
+                float* gbuf = gbuf0 + (size_t)f * GW;                       // gamma of the label states, rank order
+                float* sbuf = gbuf0 + (size_t)(FPW + f) * GW;               // inclusive prefix sums
                 float zb = 0.0f;
                 auto occupancy = [&](int2 av, int hb, int hl, int c) {
                     // alpha's high word with the block's exponent shift applied: an exact zero stays zero, anything that leaves
