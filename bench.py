@@ -657,7 +657,7 @@ def run_cuda(args, rank, world, local_rank):
                 alg += algorithmic_bytes(V, T, B, s["np"]["pred_lengths"], s["np"]["label_lengths"])
     kms = kms[:nk.value] / nrep
     alg /= nrep
-    gname = _lib.last_grad_kernel() or "k_grad"            # k_grad, or k_grad2 from 48 utterances per GPU on
+    gname = _lib.last_grad_kernel() or "k_grad"            # k_grad, or k_grad2 from 64 utterances per GPU on
     knames = ["k_emit", "k_walk", gname] if nk.value == 3 else ["k_walk", gname]
     dom = int(np.argmax(kms))
     peak, peak_src = measured_peak()

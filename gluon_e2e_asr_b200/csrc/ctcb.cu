@@ -512,9 +512,9 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
         }
         bool grad2 = false;
         // small vocabularies (fused path): the gradient kernel that normalises by P(l|x) (ctcb_grad2.cuh)
-        // (measured, scripts/grad2_blocks_sweep.py: from 48 utterances on it wins -- 13 % at B = 128 and 1024, 21 % at 256;
+        // (measured, scripts/grad2_blocks_sweep.py: from 64 utterances on it wins -- 13 % at B = 128 and 1024, 21 % at 256;
         // below that the step is the walkers' chain plus the gradient kernel's tail, where k_grad is a little shorter)
-        const bool want_grad2 = opt(OPT_GRAD2) >= 0 ? opt(OPT_GRAD2) != 0 : (p->B >= 48 && ch <= 4);
+        const bool want_grad2 = opt(OPT_GRAD2) >= 0 ? opt(OPT_GRAD2) != 0 : (p->B >= 64 && ch <= 4);
         if (lay.fused && p->V <= 64 && ch >= 1 && want_grad2) {
             // two register budgets (profiles/r3e_*, r3f_*): 80 registers / 6 CTAs per SM while the walkers run beside the
             // kernel, 72 registers / 7 CTAs per SM for batches whose gradient kernel runs after the walkers

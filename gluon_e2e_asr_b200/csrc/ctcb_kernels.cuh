@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(NQ < 0 ? 256 : 128) k_emit(Problem p, Workspac
         w.nd[b] = s_nd; dl[s_nd] = make_int2(-1, L);
         if (p.status && flags) atomicOr(p.status + b, flags);   // zeroed by the host before the call; frame CTAs OR their bits in
         if (flags & UTT_INFEASIBLE) p.loss[b] = 0.0f;   // defined behaviour, SURVEY 7.3-6
-        w.gprog[4 * b] = 0; w.gprog[4 * b + 1] = 0; w.gprog[4 * b + 2] = w.stamp;
+        w.gprog[4 * b] = 0; w.gprog[4 * b + 1] = 0; w.gprog[4 * b + 3] = 0; w.gprog[4 * b + 2] = w.stamp;
     }
 }
 

@@ -248,7 +248,7 @@ int ctcb_mailbox_destroy(ctcb_mailbox_t* mailbox);
 int ctcb_last_launch_count(void);
 int ctcb_last_walk_config(int32_t* pairs_per_lane, int32_t* warps);
 /* Which gradient kernel the last call on this thread launched: 0 none, 1 k_grad (per-frame normalisation),
- * 2 k_grad2 (normalised by P(l|x); small vocabularies, from 48 utterances on), 3 k_meet (one-kernel path, opt-in). */
+ * 2 k_grad2 (normalised by P(l|x); small vocabularies, from 64 utterances on), 3 k_meet (one-kernel path, opt-in). */
 int ctcb_last_grad_kernel(void);
 
 /* Tuning / experiment switches (tests and A/B measurements; a training loop never needs them).  Each
@@ -257,7 +257,7 @@ int ctcb_last_grad_kernel(void);
  * "walk_stages" (emission ring depth), "overlap" (gradient
  * kernel concurrent with the recursion kernel: 0/1), "fused" (0: always the k_emit path), "walk_per_sm",
  * "emit_staged", "grad_staged" (0: register variants for wide vocabularies), "grad2" (0/1: the gradient kernel
- * that normalises by P(l|x); automatic = from 48 utterances on), "grad2_blocks" (frame blocks per CTA of that
+ * that normalises by P(l|x); automatic = from 64 utterances on), "grad2_blocks" (frame blocks per CTA of that
  * kernel), "meet" (1: the experimental one-kernel path of ctcb_meet.cuh).  walk_p / walk_nw / fused
  * are part of the workspace layout: do not change them between ctcb_forward and ctcb_backward. */
 int ctcb_set_option(const char* name, int32_t value);

@@ -901,7 +901,7 @@ def test_meet_kernel_edge_cases(dev):
     (16, 2000, 46, 300, 0, False, 16), (300, 120, 46, 120, 60, False, 4),
 ])
 def test_grad2_kernel_vs_c_oracle(dev, B, T, V, L, seed, peaky, blocks):
-    """k_grad2 forced on (it is the default only from 48 utterances on): every register-chunk variant (CH 1..16),
+    """k_grad2 forced on (it is the default only from 64 utterances on): every register-chunk variant (CH 1..16),
     several frame blocks per CTA, overlapped and serial launches -- same tolerance against the fp64 C oracle, the same
     loss bits as the k_grad path, the same gradient bits run after run and under both schedules."""
     from gluon_e2e_asr_b200 import ctc_loss_and_grad, ops
