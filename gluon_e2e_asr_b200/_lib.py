@@ -27,6 +27,7 @@ EXPORTS = (
     "ctcb_mailbox_create", "ctcb_mailbox_handle", "ctcb_mailbox_connect", "ctcb_mailbox_exchange",
     "ctcb_mailbox_flush", "ctcb_mailbox_destroy", "ctcb_mailbox_exchange_with_next",
     "ctcb_set_option", "ctcb_get_option", "ctcb_greedy_decode_unk", "ctcb_last_grad_kernel",
+    "ctcb_proj_forward", "ctcb_proj_loss_grad",
 )
 
 
@@ -49,6 +50,14 @@ class Problem(ctypes.Structure):
         ("label_lengths", ctypes.c_void_p), ("label_lengths_dtype", ctypes.c_int32),
         ("head_grad", ctypes.c_void_p), ("loss", ctypes.c_void_p), ("loss_sum", ctypes.c_void_p),
         ("status", ctypes.c_void_p), ("logits_row_offsets", ctypes.c_void_p),
+    ]
+
+
+class Proj(ctypes.Structure):
+    """ctcb_proj_t (include/ctcb.h): the output projection in front of the loss."""
+    _fields_ = [
+        ("hidden", ctypes.c_void_p), ("hidden_stride_t", ctypes.c_int64), ("hidden_stride_b", ctypes.c_int64),
+        ("K", ctypes.c_int32), ("weight", ctypes.c_void_p), ("bias", ctypes.c_void_p),
     ]
 
 
@@ -95,6 +104,8 @@ def load():
     lib.ctcb_loss_sum_allreduce.argtypes = [vp, vp, i32, vp]
     lib.ctcb_last_walk_config.argtypes = [ctypes.POINTER(i32), ctypes.POINTER(i32)]
     lib.ctcb_loss_grad_dlpack.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, sz, vp]
+    lib.ctcb_proj_forward.argtypes = [ctypes.POINTER(Proj), PP, i32, vp, sz, vp]
+    lib.ctcb_proj_loss_grad.argtypes = [ctypes.POINTER(Proj), PP, vp, sz, vp]
     lib.ctcb_set_option.argtypes = [ctypes.c_char_p, i32]
     lib.ctcb_get_option.argtypes = [ctypes.c_char_p, ctypes.POINTER(i32)]
     for name in EXPORTS:

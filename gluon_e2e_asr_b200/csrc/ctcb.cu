@@ -19,6 +19,7 @@
 #include "ctcb_kernels.cuh"
 #include "ctcb_meet.cuh"
 #include "ctcb_grad2.cuh"
+#include "ctcb_proj.cuh"
 
 struct ctcb_mailbox {
     int device = 0, rank = 0, world = 0;
@@ -51,6 +52,7 @@ bool launch_pending_xchg(cudaStream_t stream, bool programmatic = false) {
     g_xchg = PendingXchg{};
     return true;
 }
+thread_local const ctcb_proj_t* g_proj = nullptr;      // ctcb_proj_*: the projection whose epilogue replaces k_emit in this call
 thread_local cudaEvent_t* g_prof_events = nullptr;   // when set: one event recorded after every launch
 thread_local int g_prof_count = 0;
 
@@ -272,7 +274,7 @@ int validate(const ctcb_problem_t* p) {
     if (p->T <= 0 || p->B <= 0 || p->V <= 1 || p->Lmax < 0)
         return fail(CTCB_INVALID_VALUE, "bad shape T=%d B=%d V=%d Lmax=%d", p->T, p->B, p->V, p->Lmax);
     if (p->blank < 0 || p->blank >= p->V) return fail(CTCB_INVALID_VALUE, "blank %d outside [0,%d)", p->blank, p->V);
-    if (!p->logits || !p->loss) return fail(CTCB_INVALID_VALUE, "logits and loss must not be NULL");
+    if ((!p->logits && !g_proj) || !p->loss) return fail(CTCB_INVALID_VALUE, "logits and loss must not be NULL");
     if (p->Lmax > 0 && !p->labels) return fail(CTCB_INVALID_VALUE, "labels is NULL");
     auto dt_ok = [](int d) { return d >= CTCB_I32 && d <= CTCB_F64; };
     if (!dt_ok(p->label_dtype) || (p->data_lengths && !dt_ok(p->data_lengths_dtype)) ||
@@ -349,6 +351,73 @@ enum { PH_FORWARD = 1, PH_BACKWARD = 2 };
 inline void mark(cudaStream_t stream) {
     ++g_launches;
     if (g_prof_events && g_prof_count < 8) cudaEventRecord(g_prof_events[g_prof_count++], stream);
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point: libcuda is not linked
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q{};
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+
+// the projection kernel (ctcb_proj.cuh) in k_emit's place: {row max, normaliser} and the emission table from the
+// encoder output, then the metadata CTAs of k_emit (one per utterance)
+int launch_proj(const ctcb_proj_t* pj, const ctcb_problem_t* p, const ctcb::Problem& dp, const ctcb::Workspace& w,
+                const Layout& lay, cudaStream_t stream) {
+    if (!pj->hidden || !pj->weight || pj->K <= 0) return fail(CTCB_INVALID_VALUE, "projection: hidden / weight is NULL or K <= 0");
+    if (lay.fused || lay.dense)
+        return fail(CTCB_UNSUPPORTED, "projection fused with the loss needs V > 64 and V > Lmax + 1 (V=%d, Lmax=%d)", p->V, p->Lmax);
+    if (p->logits_row_offsets) return fail(CTCB_UNSUPPORTED, "projection: packed logits are not supported");
+    if (pj->K % 4 || pj->hidden_stride_t % 4 || pj->hidden_stride_b % 4 || reinterpret_cast<uintptr_t>(pj->hidden) % 16 ||
+        reinterpret_cast<uintptr_t>(pj->weight) % 16)
+        return fail(CTCB_INVALID_VALUE, "projection: K and the hidden strides must be multiples of 4 elements, bases 16-byte aligned");
+    if (!is_device_ptr(pj->hidden) || !is_device_ptr(pj->weight) || !is_device_ptr(pj->bias))
+        return fail(CTCB_INVALID_VALUE, "projection: hidden / weight / bias must be CUDA device memory");
+    const size_t smem = ctcb::proj_smem_bytes(p->Lmax, lay.Lp);
+    if (smem > 232448 - 256) return fail(CTCB_UNSUPPORTED, "projection: Lmax=%d label columns do not fit the kernel's shared memory", p->Lmax);
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return fail(CTCB_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
+    CUtensorMap tmA, tmB;
+    {
+        const cuuint64_t gdim[3] = {(cuuint64_t)pj->K, (cuuint64_t)p->T, (cuuint64_t)p->B};
+        const cuuint64_t gstr[2] = {(cuuint64_t)pj->hidden_stride_t * 4, (cuuint64_t)pj->hidden_stride_b * 4};
+        const cuuint32_t box[3] = {(cuuint32_t)ctcb::kPK, (cuuint32_t)ctcb::kPM, 1};
+        const cuuint32_t est[3] = {1, 1, 1};
+        const CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(pj->hidden), gdim, gstr, box, est,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(CTCB_INVALID_VALUE, "cuTensorMapEncodeTiled(hidden) failed: %d", (int)r);
+    }
+    {
+        const cuuint64_t gdim[2] = {(cuuint64_t)pj->K, (cuuint64_t)p->V};
+        const cuuint64_t gstr[1] = {(cuuint64_t)pj->K * 4};
+        const cuuint32_t box[2] = {(cuuint32_t)ctcb::kPK, (cuuint32_t)ctcb::kPN};
+        const cuuint32_t est[2] = {1, 1};
+        const CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(pj->weight), gdim, gstr, box, est,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(CTCB_INVALID_VALUE, "cuTensorMapEncodeTiled(weight) failed: %d", (int)r);
+    }
+    ctcb::ProjArgs pa{};
+    pa.p = dp; pa.w = w; pa.bias = pj->bias; pa.logits = const_cast<float*>(p->logits);
+    pa.K = pj->K; pa.NT = (p->V + ctcb::kPN - 1) / ctcb::kPN; pa.KB = (pj->K + ctcb::kPK - 1) / ctcb::kPK;
+    pa.vec4 = (p->V % 4 == 0 && reinterpret_cast<uintptr_t>(pj->bias) % 16 == 0 &&
+               (!p->logits || (p->logits_stride_t % 4 == 0 && p->logits_stride_b % 4 == 0 && reinterpret_cast<uintptr_t>(p->logits) % 16 == 0))) ? 1 : 0;
+    const dim3 pgrid((p->T + ctcb::kPM - 1) / ctcb::kPM, p->B);
+    CUDA_TRY(ctcb::launch_proj_emit(tmA, tmB, pa, pgrid, smem, stream));
+    mark(stream);
+    // per-utterance metadata: k_emit's extra CTA alone (grid.x = 1: every CTA is the metadata CTA)
+    ctcb::k_emit<1, 0><<<dim3(1, p->B), 128, ctcb::emit_smem_bytes(lay.Lp, 0), stream>>>(dp, w);
+    mark(stream);
+    return CTCB_OK;
 }
 
 int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, void* stream_, int phases, bool keep_hist) {
@@ -477,7 +546,9 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
             mark(stream);
             return CTCB_OK;
         };
-        if (!lay.fused) { if (int rc = launch_emit()) return rc; }
+        if (g_proj) {
+            if (int rc = launch_proj(g_proj, p, dp, w, lay, stream)) return rc;
+        } else if (!lay.fused) { if (int rc = launch_emit()) return rc; }
         if (int rc = launch_walk(xchg && lay.fused != 0)) return rc;
     }
     if (phases & PH_BACKWARD) {
@@ -599,6 +670,28 @@ int ctcb_forward(const ctcb_problem_t* p, int32_t keep_for_backward, void* works
 int ctcb_backward(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, void* stream) {
     g_launches = 0;
     return enqueue(p, workspace, workspace_bytes, stream, PH_BACKWARD, true);
+}
+
+int ctcb_proj_forward(const ctcb_proj_t* proj, const ctcb_problem_t* p, int32_t keep_for_backward, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+    if (!proj) return fail(CTCB_INVALID_VALUE, "proj is NULL");
+    if (keep_for_backward && p && !p->logits)
+        return fail(CTCB_INVALID_VALUE, "keep_for_backward needs p->logits (the gradient kernel reads the projection's output)");
+    g_launches = 0;
+    g_proj = proj;
+    const int rc = enqueue(p, workspace, workspace_bytes, stream, PH_FORWARD, keep_for_backward != 0);
+    g_proj = nullptr;
+    return rc;
+}
+
+int ctcb_proj_loss_grad(const ctcb_proj_t* proj, const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!proj) return fail(CTCB_INVALID_VALUE, "proj is NULL");
+    if (p && (!p->logits || !p->grad)) return fail(CTCB_INVALID_VALUE, "ctcb_proj_loss_grad needs p->logits and p->grad");
+    g_launches = 0;
+    g_proj = proj;
+    const int rc = enqueue(p, workspace, workspace_bytes, stream, PH_FORWARD | PH_BACKWARD, true);
+    g_proj = nullptr;
+    return rc;
 }
 
 // ---- host-buffer entry ------------------------------------------------------------------

@@ -1248,6 +1248,7 @@ __device__ __forceinline__ void mailbox_exchange_warp(const MailboxDev* md, doub
     }
 }
 
+#ifndef CTCB_NO_PLAIN_KERNELS   // non-template kernels: defined in ctcb.cu's translation unit only
 __global__ void __launch_bounds__(32) k_mailbox_exchange(const MailboxDev* m, double* values, int count, double* out, int flush) {
     // Riding on a step, either BEHIND its gradient kernel as that kernel's programmatic dependent (this grid starts when
     // the gradient kernel's last wave of CTAs has started, works beside it -- it shares nothing with the step -- and stays
@@ -1257,6 +1258,7 @@ __global__ void __launch_bounds__(32) k_mailbox_exchange(const MailboxDev* m, do
     mailbox_exchange_warp(m, values, count, out, flush, threadIdx.x);
     if (threadIdx.x == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+#endif
 
 // ---------------------------------------------------------------------------------------
 // k_grad<VEC,CH,XQ>: grid (NB, B), block 128: one frame block (kG = 8 frames) per CTA, two
@@ -1632,6 +1634,7 @@ __global__ void __launch_bounds__(XQ < 0 ? 256 : 128, XQ < 0 ? (CH == 16 ? 2 : 3
 // gradient stored by Forward times the head gradient) for callers that ran the fused
 // forward+gradient with head = 1.  grid (ceil(T*ceil(V/128)... ) flat over (b, t) rows.
 // ---------------------------------------------------------------------------------------
+#ifndef CTCB_NO_PLAIN_KERNELS   // non-template kernels: defined in ctcb.cu's translation unit only
 __global__ void __launch_bounds__(256) k_scale_rows(float* grad, long long gst_t, long long gst_b, int T, int B, int V,
                                                     const float* head) {
     const int rows_per_cta = 8, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1642,6 +1645,7 @@ __global__ void __launch_bounds__(256) k_scale_rows(float* grad, long long gst_t
     float* row = grad + b * gst_b + t * gst_t;
     for (int v = lane; v < V; v += 32) row[v] *= h;
 }
+#endif
 
 // ---------------------------------------------------------------------------------------
 // k_greedy_decode: grid B, block 256.  train_ctc_ce.py:149-160 and, with unk >= 0, decode_ctc.py:123-143
@@ -1656,6 +1660,7 @@ __device__ __forceinline__ void top2_push(Top2& t, float v, int i) {
     if (better(v, i, t.v1, t.i1)) { t.v2 = t.v1; t.i2 = t.i1; t.v1 = v; t.i1 = i; }
     else if (better(v, i, t.v2, t.i2)) { t.v2 = v; t.i2 = i; }
 }
+#ifndef CTCB_NO_PLAIN_KERNELS   // non-template kernels: defined in ctcb.cu's translation unit only
 __global__ void __launch_bounds__(256) k_greedy_decode(const float* logits, long long st_t, long long st_b,
                                                        const void* data_len, int dl_dtype, int T, int B, int V,
                                                        int blank, int unk, int* out_tokens, int* out_len) {
@@ -1702,6 +1707,7 @@ __global__ void __launch_bounds__(256) k_greedy_decode(const float* logits, long
     }
     if (tid == 255) out_len[b] = base + incl;
 }
+#endif
 
 // ---------------------------------------------------------------------------------------
 // k_edit_distance: grid B, block 128.  scripts/swbd/wer.py:45-68 (next-row scope): Levenshtein
@@ -1712,6 +1718,7 @@ __global__ void __launch_bounds__(256) k_greedy_decode(const float* logits, long
 // minima plus one hop through shared memory.  (The reference takes d[i-1][j-1] alone on a match;
 // neighbouring cells differ by at most one, so the three-way minimum gives the same number.)
 // ---------------------------------------------------------------------------------------
+#ifndef CTCB_NO_PLAIN_KERNELS   // non-template kernels: defined in ctcb.cu's translation unit only
 __global__ void __launch_bounds__(128) k_edit_distance(const int* ref, long long ref_stride, const int* ref_len,
                                                        const int* hyp, long long hyp_stride, const int* hyp_len,
                                                        int max_ref, int max_hyp, int* out_dist, long long* totals) {
@@ -1757,5 +1764,6 @@ __global__ void __launch_bounds__(128) k_edit_distance(const int* ref, long long
         }
     }
 }
+#endif
 
 }  // namespace ctcb

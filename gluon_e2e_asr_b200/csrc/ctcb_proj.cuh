@@ -1,0 +1,315 @@
+// ctcb_proj.cuh -- the output projection fused with the loss's emission stage.
+//
+// Reference: /root/reference/scripts/swbd/model.py:394-398 (`tgt_proj = nn.Dense(units=V, flatten=False)`) and
+// :424 (`return self.tgt_proj(net_out)`), whose output is the `pred` of CtcLoss (train_ctc_ce.py:363).  For the
+// BPE-sized vocabulary (V = 2000) the logits are 8 KB per frame against 2 KB of encoder output: the tensor that
+// dominates the step's HBM traffic is the one nobody needs -- the loss reads, per frame, the row maximum, the
+// softmax normaliser and the L+1 columns of the utterance's own labels.
+//
+// k_proj_emit computes  logits[b, t, :] = hidden[b, t, :] . W^T + bias  on the 5th-generation tensor cores and
+// reduces each 128-frame x 256-symbol accumulator tile to exactly those three things while it is still in tensor
+// memory:
+//   * one CTA per (utterance, 128-frame tile); the vocabulary is swept in tiles of 256 columns, the hidden units
+//     in blocks of 32 fp32 values (= one 128-byte swizzle row);
+//   * warp 0 (one lane): TMA producer -- `cp.async.bulk.tensor` of the A tile (3-D map over hidden (K, T, B): rows
+//     beyond T are zero-filled by the hardware and never read the next utterance) and the B tile (2-D map over W
+//     (K, V): rows beyond V zero-filled) into a 3-stage 128B-swizzled shared-memory ring, full/empty mbarriers;
+//   * warp 1 (one lane): `tcgen05.mma.cta_group::1.kind::tf32`, M = 128, N = 256, K = 8 per instruction, fp32
+//     accumulators in tensor memory, two accumulator stages (2 x 256 columns = the SM's whole TMEM) so that the
+//     tensor cores work on vocabulary tile n+1 while the epilogue drains tile n; `tcgen05.commit` hands shared-memory
+//     stages back to the producer and accumulator stages to the epilogue;
+//   * warps 2..5: epilogue, ONE FRAME PER THREAD (TMEM lane = accumulator row): `tcgen05.ld.32x32b.x32` brings 32
+//     columns of the thread's own row into registers; bias add, online row maximum / sum of exp2 (no shuffles: a
+//     thread owns its row), optional store of the logits row chunk for the gradient kernel (training) -- or no
+//     store at all (validation, train_ctc_ce.py:143: the logits never exist in HBM); the utterance's label columns
+//     that fall into the tile are fetched again from TMEM with single-column loads (the column index is uniform
+//     over the warp) and parked in shared memory until the row maximum is final;
+//   * after the sweep every thread writes its frame's {row max, log2 sum} to `fr` and its frame's slot of the
+//     emission table E (fp64 softmax numerators, frame-minor blocks of 8 frames) -- the two inputs of k_walk's
+//     unfused variant, bit-compatible with what k_emit writes from a logits tensor.
+// The tf32 data path reads the caller's fp32 tensors as they are (the tensor cores ignore the low 13 mantissa
+// bits): no conversion pass, no copy of hidden or W.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ctcb_kernels.cuh"
+
+namespace ctcb {
+
+constexpr int kPM = 128;                 // frames per CTA tile = UMMA M (TMEM lanes)
+constexpr int kPN = 256;                 // vocabulary columns per accumulator stage = UMMA N
+constexpr int kPK = 32;                  // fp32 values per K block: 128 bytes, one SWIZZLE_128B row
+constexpr int kPStages = 3;              // shared-memory ring depth
+constexpr int kPThreads = 192;           // warp 0 TMA, warp 1 MMA + TMEM allocation, warps 2..5 epilogue
+constexpr uint32_t kPBytesA = kPM * kPK * 4;     // 16 KB
+constexpr uint32_t kPBytesB = kPN * kPK * 4;     // 32 KB
+constexpr uint32_t kPTmemCols = 512;             // two accumulator stages of kPN columns
+
+struct ProjArgs {
+    Problem p; Workspace w;
+    const float* bias;       // (V,) or nullptr
+    float* logits;           // where the projection's output is kept for the gradient kernel (Problem::logits), or nullptr
+    int K, NT, KB;           // hidden units, vocabulary tiles, K blocks
+    int vec4;                // logits rows (and bias) allow 16-byte accesses
+};
+
+__host__ __device__ inline size_t proj_smem_bytes(int Lmax, int Lp) {
+    return 1024 + (size_t)kPStages * (kPBytesA + kPBytesB) + (size_t)(Lmax + 1) * kPM * sizeof(float) +
+           (size_t)Lp * sizeof(int) + 128;
+}
+
+// host-side launcher, defined in ctcb_proj.cu (its own translation unit: the kernel below is compiled there only)
+cudaError_t launch_proj_emit(const CUtensorMap& tmA, const CUtensorMap& tmB, const ProjArgs& a, dim3 grid, size_t smem, cudaStream_t stream);
+
+#ifdef CTCB_PROJ_IMPL
+// ---- tcgen05 / TMA wrappers -------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, tf32 inputs, fp32 accumulation; issued by ONE thread for the CTA
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives on the mbarrier when every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor of a K-major tile whose rows are 128 bytes (one SWIZZLE_128B row per row,
+// 8-row groups 1024 bytes apart) -- the layout TMA writes with CU_TENSOR_MAP_SWIZZLE_128B.  Bits: [0,14) start
+// address >> 4, [16,30) leading byte offset >> 4 (unused for swizzled K-major), [32,46) stride byte offset >> 4,
+// [46,48) descriptor version 1 (sm_100), [61,64) layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D fp32 (bit 4), A and B tf32 (format 2 at bits 7 and 10), both K-major, N >> 3 at
+// bit 17, M >> 4 at bit 24
+constexpr uint32_t kPIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kPN >> 3) << 17) | ((uint32_t)(kPM >> 4) << 24);
+
+__device__ __forceinline__ void bar_sync_epilogue() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kPThreads, 1)
+k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ProjArgs a) {
+    extern __shared__ unsigned char proj_raw[];
+    __shared__ int s_L;
+    const Problem& p = a.p;
+    const Workspace& w = a.w;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y, m0 = blockIdx.x * kPM;
+
+    // operator parameter layer, frame count: lengths truncated and clamped (as k_emit does)
+    int Tb = p.T;
+    if (p.data_len) {
+        long long t64 = load_as_int(p.data_len, p.data_len_dtype, b);
+        t64 = t64 < 0 ? 0 : (t64 > p.T ? p.T : t64);
+        Tb = (int)t64;
+    }
+    if (m0 >= Tb) return;                 // a tile of padded frames: nothing of it is ever read
+
+    const uint32_t raw = smem_u32(proj_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;          // SWIZZLE_128B tiles want 1024-byte alignment
+    unsigned char* gbase = proj_raw + (base - raw);
+    const uint32_t sA = base, sB = base + kPStages * kPBytesA;
+    float* stash = reinterpret_cast<float*>(gbase + (size_t)kPStages * (kPBytesA + kPBytesB));   // [Lmax+1][128] raw label logits
+    int* labs = reinterpret_cast<int*>(stash + (size_t)(p.Lmax + 1) * kPM);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(labs + w.Lp);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + kPStages;
+    uint64_t* tfull = bars + 2 * kPStages;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    if (tid == 0) {
+        for (int s = 0; s < kPStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_L = p.Lmax;
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kPTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int st = 0; uint32_t ph = 0;
+            for (int n = 0; n < a.NT; ++n)
+                for (int kb = 0; kb < a.KB; ++kb) {
+                    mbar_wait(empty + st, ph ^ 1u);
+                    mbar_expect_tx(full + st, kPBytesA + kPBytesB);
+                    tma_load_3d(sA + st * kPBytesA, &tmA, smem_u32(full + st), kb * kPK, m0, b);
+                    tma_load_2d(sB + st * kPBytesB, &tmB, smem_u32(full + st), kb * kPK, n * kPN);
+                    if (++st == kPStages) { st = 0; ph ^= 1u; }
+                }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int st = 0; uint32_t ph = 0;
+            for (int n = 0; n < a.NT; ++n) {
+                const int as = n & 1;
+                mbar_wait(tempty + as, (((uint32_t)n >> 1) & 1u) ^ 1u);       // the epilogue has drained this accumulator stage
+                tc_fence_after();
+                const uint32_t dcol = tmem + (uint32_t)as * kPN;
+                for (int kb = 0; kb < a.KB; ++kb) {
+                    mbar_wait(full + st, ph);
+                    tc_fence_after();
+                    const uint32_t a0 = sA + st * kPBytesA, b0 = sB + st * kPBytesB;
+#pragma unroll
+                    for (int k = 0; k < kPK / 8; ++k)                          // 8 tf32 values = 32 bytes per instruction
+                        umma_tf32(dcol, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), kPIdesc, (uint32_t)((kb | k) != 0));
+                    umma_commit(smem_u32(empty + st));                         // the stage is free once these MMAs have read it
+                    if (++st == kPStages) { st = 0; ph ^= 1u; }
+                }
+                umma_commit(smem_u32(tfull + as));                             // the accumulator tile is complete
+            }
+        }
+    } else {
+        // ===== epilogue: one frame per thread =====
+        const int etid = tid - 64;
+        const int q = warp & 3;                       // TMEM lane quadrant this warp may read
+        const int r = q * 32 + lane;                  // accumulator row = frame within the tile
+        const int t = m0 + r;
+        // labels (the rest of the parameter layer; bad labels are clamped here and reported by the metadata CTA)
+        int L;
+        if (p.label_len) {
+            long long l64 = load_as_int(p.label_len, p.label_len_dtype, b);
+            l64 = l64 < 0 ? 0 : (l64 > p.Lmax ? p.Lmax : l64);
+            L = (int)l64;
+        } else {
+            for (int j = etid; j < p.Lmax; j += 128)
+                if (load_as_int(p.labels, p.label_dtype, b * p.lst_b + j * p.lst_l) == p.label_pad) atomicMin(&s_L, j);
+            bar_sync_epilogue();
+            L = s_L;
+        }
+        for (int j = etid; j < L; j += 128) {
+            const long long v = load_as_int(p.labels, p.label_dtype, b * p.lst_b + j * p.lst_l);
+            labs[j] = (int)(v < 0 ? 0 : (v >= p.V ? p.V - 1 : v));
+        }
+        bar_sync_epilogue();
+
+        float* lrow = (a.logits && t < p.T) ? a.logits + (long long)b * p.st_b + (long long)t * p.st_t : nullptr;
+        float mx = -INFINITY, sum = 0.0f;
+        for (int n = 0; n < a.NT; ++n) {
+            const int as = n & 1;
+            mbar_wait(tfull + as, ((uint32_t)n >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)as * kPN;
+#pragma unroll 1
+            for (int c = 0; c < kPN / 32; ++c) {
+                const int col0 = n * kPN + c * 32;
+                if (col0 >= p.V) break;
+                uint32_t v[32];
+                tmem_ld32(trow + c * 32, v);
+                tmem_ld_wait();
+                float x[32];
+                if (a.vec4) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const bool in = col0 + i < p.V;                         // V % 4 == 0: whole groups
+                        const float4 bb = (in && a.bias) ? __ldg(reinterpret_cast<const float4*>(a.bias + col0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        x[i] = in ? __uint_as_float(v[i]) + bb.x : -INFINITY;
+                        x[i + 1] = in ? __uint_as_float(v[i + 1]) + bb.y : -INFINITY;
+                        x[i + 2] = in ? __uint_as_float(v[i + 2]) + bb.z : -INFINITY;
+                        x[i + 3] = in ? __uint_as_float(v[i + 3]) + bb.w : -INFINITY;
+                        if (lrow && in) *reinterpret_cast<float4*>(lrow + col0 + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const bool in = col0 + i < p.V;
+                        x[i] = in ? __uint_as_float(v[i]) + (a.bias ? __ldg(a.bias + col0 + i) : 0.0f) : -INFINITY;
+                        if (lrow && in) lrow[col0 + i] = x[i];
+                    }
+                }
+                float cm = x[0];
+#pragma unroll
+                for (int i = 1; i < 32; ++i) cm = fmaxf(cm, x[i]);
+                if (cm > mx) { sum *= fast_ex2((mx - cm) * kLog2e); mx = cm; }     // first chunk: mx = -inf -> sum (0) * 0
+                const float ms = mx * kLog2e;
+                float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    s0 += fast_ex2(fmaf(x[i], kLog2e, -ms));
+                    s1 += fast_ex2(fmaf(x[i + 1], kLog2e, -ms));
+                }
+                sum += s0 + s1;
+            }
+            // the utterance's own columns of this tile (blank, l_1..l_L): column index uniform over the warp
+            for (int j = 0; j <= L; ++j) {
+                const int vj = j == 0 ? p.blank : labs[j - 1];
+                if ((vj >> 8) != n) continue;
+                const uint32_t raw1 = tmem_ld1(trow + (uint32_t)(vj & (kPN - 1)));
+                tmem_ld_wait();
+                stash[j * kPM + r] = __uint_as_float(raw1) + (a.bias ? __ldg(a.bias + vj) : 0.0f);
+            }
+            tc_fence_before();
+            mbar_arrive(tempty + as);
+        }
+        // ---- the frame's outputs: {row max, log2 normaliser} and its slot of the emission table ----
+        if (t < Tb) w.fr[(size_t)b * p.T + t] = make_float2(mx, log2f(sum));
+        const int blk = t >> 3;
+        if (blk < w.NB && blk * kG < Tb) {
+            double* ecol = w.E + ((size_t)b * w.NB + blk) * w.W * kEC + (t & 7);
+            const bool valid = t < Tb;
+            bool floored = false;
+            for (int j = 0; j <= L; ++j) {
+                const float l2 = (stash[j * kPM + r] - mx) * kLog2e;
+                floored |= valid && l2 < kMinLog2;
+                ecol[(size_t)j * kEC] = valid ? (double)fast_ex2(fmaxf(l2, kMinLog2)) : 0.0;
+            }
+            if (floored && p.status) atomicOr(p.status + b, UTT_WIDE_LOGITS);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, kPTmemCols);
+}
+
+#endif  // CTCB_PROJ_IMPL
+
+}  // namespace ctcb

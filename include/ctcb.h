@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CTCB_VERSION 101 /* 0.1.1: ctcb_problem_t.logits_row_offsets, ctcb_set_option, ctcb_greedy_decode_unk */
+#define CTCB_VERSION 102 /* 0.1.2: ctcb_proj_forward, ctcb_proj_loss_grad */
 
 typedef enum {
     CTCB_OK = 0,
@@ -262,6 +262,35 @@ int ctcb_last_grad_kernel(void);
  * are part of the workspace layout: do not change them between ctcb_forward and ctcb_backward. */
 int ctcb_set_option(const char* name, int32_t value);
 int ctcb_get_option(const char* name, int32_t* value);
+
+/* ---- output projection fused with the loss ------------------------------------------------
+ * Replaces the pair  `self.tgt_proj(net_out)`  (scripts/swbd/model.py:394-398 `nn.Dense(units=V, flatten=False)`, called
+ * at model.py:424)  ->  `loss_function(out, ...)`  (train_ctc_ce.py:363 / :143) for vocabularies wider than 64 symbols:
+ * logits[b,t,:] = hidden[b,t,:] . weight^T + bias is formed on the tensor cores (tcgen05, tf32 inputs read straight
+ * from the fp32 tensors, fp32 accumulation in tensor memory) and reduced to what the lattice recursion reads -- row
+ * maximum, softmax normaliser, the utterance's own label columns -- before it leaves the SM (csrc/ctcb_proj.cuh).
+ * All pointers are device pointers.  hidden: (B, T, K) in any T/B strides (elements, multiples of 4), unit stride along
+ * K; weight: (V, K) row-major, gluon's Dense layout (units, in_units); K a multiple of 4; 16-byte aligned bases. */
+typedef struct ctcb_proj {
+    const float* hidden;
+    int64_t hidden_stride_t, hidden_stride_b;
+    int32_t K;
+    const float* weight;
+    const float* bias;              /* (V,) or NULL (Dense(use_bias=False)) */
+} ctcb_proj_t;
+
+/* Loss of one batch from the encoder output.  p->logits is an OUTPUT here: NULL = the logits are never stored (the
+ * validation pass, train_ctc_ce.py:143); otherwise the (T,B,V) buffer (p->logits_stride_*) the projection is written to,
+ * once, for the gradient kernel.  keep_for_backward as in ctcb_forward: with it (and p->logits) a following
+ * ctcb_backward(p, ...) writes d loss / d logits into p->grad, from which d hidden = G . weight, d weight = G^T . hidden
+ * and d bias = sum G are plain library GEMMs (gluon_e2e_asr_b200/proj.py).  p->logits_row_offsets is not supported.
+ * CTCB_UNSUPPORTED for V <= 64 or V <= Lmax + 1 (there the logits are a few per cent of the projection's traffic and the
+ * walkers' fused producers read them once anyway) and for label rows too long for the kernel's shared memory. */
+int ctcb_proj_forward(const ctcb_proj_t* proj, const ctcb_problem_t* p, int32_t keep_for_backward, void* workspace,
+                      size_t workspace_bytes, void* stream);
+/* ctcb_proj_forward(keep_for_backward=1) followed by ctcb_backward in one call: loss, p->logits and p->grad. */
+int ctcb_proj_loss_grad(const ctcb_proj_t* proj, const ctcb_problem_t* p, void* workspace, size_t workspace_bytes,
+                        void* stream);
 
 #ifdef __cplusplus
 }
