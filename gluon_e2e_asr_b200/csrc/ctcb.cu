@@ -383,6 +383,7 @@ int launch_proj(const ctcb_proj_t* pj, const ctcb_problem_t* p, const ctcb::Prob
         return fail(CTCB_INVALID_VALUE, "projection: hidden / weight / bias must be CUDA device memory");
     const size_t smem = ctcb::proj_smem_bytes(p->Lmax, lay.Lp);
     if (smem > 232448 - 256) return fail(CTCB_UNSUPPORTED, "projection: Lmax=%d label columns do not fit the kernel's shared memory", p->Lmax);
+    if ((p->V + 127) / 128 + 1 > ctcb::kPMaxHalfTiles) return fail(CTCB_UNSUPPORTED, "projection: V=%d is wider than the kernel's column index", p->V);
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return fail(CTCB_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
     CUtensorMap tmA, tmB;

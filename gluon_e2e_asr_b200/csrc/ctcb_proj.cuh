@@ -42,10 +42,12 @@ constexpr int kPM = 128;                 // frames per CTA tile = UMMA M (TMEM l
 constexpr int kPN = 256;                 // vocabulary columns per accumulator stage = UMMA N
 constexpr int kPK = 32;                  // fp32 values per K block: 128 bytes, one SWIZZLE_128B row
 constexpr int kPStages = 3;              // shared-memory ring depth
-constexpr int kPThreads = 192;           // warp 0 TMA, warp 1 MMA + TMEM allocation, warps 2..5 epilogue
+constexpr int kPEpiWarps = 8;             // two epilogue warps per TMEM lane quadrant: each takes half of a tile's columns
+constexpr int kPThreads = 64 + 32 * kPEpiWarps;   // warp 0 TMA, warp 1 MMA + TMEM allocation, warps 2.. epilogue
 constexpr uint32_t kPBytesA = kPM * kPK * 4;     // 16 KB
 constexpr uint32_t kPBytesB = kPN * kPK * 4;     // 32 KB
 constexpr uint32_t kPTmemCols = 512;             // two accumulator stages of kPN columns
+constexpr int kPMaxHalfTiles = 512;              // half tiles of 128 columns: vocabularies up to 65536 symbols
 
 struct ProjArgs {
     Problem p; Workspace w;
@@ -57,7 +59,7 @@ struct ProjArgs {
 
 __host__ __device__ inline size_t proj_smem_bytes(int Lmax, int Lp) {
     return 1024 + (size_t)kPStages * (kPBytesA + kPBytesB) + (size_t)(Lmax + 1) * kPM * sizeof(float) +
-           (size_t)Lp * sizeof(int) + 128;
+           (size_t)Lp * sizeof(int) + 128 + 2 * kPM * sizeof(float2) + (size_t)(Lp + 4) * sizeof(int) + kPMaxHalfTiles * sizeof(int);
 }
 
 // host-side launcher, defined in ctcb_proj.cu (its own translation unit: the kernel below is compiled there only)
@@ -126,7 +128,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // bit 17, M >> 4 at bit 24
 constexpr uint32_t kPIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kPN >> 3) << 17) | ((uint32_t)(kPM >> 4) << 24);
 
-__device__ __forceinline__ void bar_sync_epilogue() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_epilogue() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kPEpiWarps) : "memory"); }
 
 __global__ void __launch_bounds__(kPThreads, 1)
 k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ProjArgs a) {
@@ -158,10 +160,13 @@ k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint64_t* tfull = bars + 2 * kPStages;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float2* part = reinterpret_cast<float2*>(bars + 16);                 // [2][128] {row max, sum} of each column half
+    int* order = reinterpret_cast<int*>(part + 2 * kPM);                  // lattice columns 0..L sorted by half tile of their symbol
+    int* hstart = order + w.Lp + 4;                                       // [2 NT + 1] where each half tile's columns start in `order`
 
     if (tid == 0) {
         for (int s = 0; s < kPStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 128); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 32 * kPEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_L = p.Lmax;
         tma_prefetch_desc(&tmA);
@@ -209,9 +214,12 @@ k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
         }
     } else {
-        // ===== epilogue: one frame per thread =====
+        // ===== epilogue: one frame per thread pair (each thread takes half of a tile's columns) =====
+        constexpr int NE = 32 * kPEpiWarps;
+        constexpr int HC = kPN / 2;                   // columns per thread and tile
         const int etid = tid - 64;
         const int q = warp & 3;                       // TMEM lane quadrant this warp may read
+        const int hsel = (warp - 2) >> 2;             // which half of the tile's columns
         const int r = q * 32 + lane;                  // accumulator row = frame within the tile
         const int t = m0 + r;
         // labels (the rest of the parameter layer; bad labels are clamped here and reported by the metadata CTA)
@@ -221,14 +229,31 @@ k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             l64 = l64 < 0 ? 0 : (l64 > p.Lmax ? p.Lmax : l64);
             L = (int)l64;
         } else {
-            for (int j = etid; j < p.Lmax; j += 128)
+            for (int j = etid; j < p.Lmax; j += NE)
                 if (load_as_int(p.labels, p.label_dtype, b * p.lst_b + j * p.lst_l) == p.label_pad) atomicMin(&s_L, j);
             bar_sync_epilogue();
             L = s_L;
         }
-        for (int j = etid; j < L; j += 128) {
+        for (int j = etid; j < L; j += NE) {
             const long long v = load_as_int(p.labels, p.label_dtype, b * p.lst_b + j * p.lst_l);
             labs[j] = (int)(v < 0 ? 0 : (v >= p.V ? p.V - 1 : v));
+        }
+        bar_sync_epilogue();
+        // the lattice's columns (0 = blank, j = label j) bucketed by the half tile (128 symbols) their symbol lies in: each
+        // epilogue warp then visits exactly its own columns of a tile instead of scanning the label row
+        for (int h = etid; h <= 2 * a.NT; h += NE) {
+            int c = 0;
+            for (int j = 0; j <= L; ++j) c += ((j == 0 ? p.blank : labs[j - 1]) >> 7) < h;
+            hstart[h] = c;
+        }
+        for (int j = etid; j <= L; j += NE) {
+            const int hb = (j == 0 ? p.blank : labs[j - 1]) >> 7;
+            int pos = 0;
+            for (int k = 0; k <= L; ++k) {
+                const int hk = (k == 0 ? p.blank : labs[k - 1]) >> 7;
+                pos += (hk < hb) | ((hk == hb) & (k < j));
+            }
+            order[pos] = j;
         }
         bar_sync_epilogue();
 
@@ -238,66 +263,85 @@ k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int as = n & 1;
             mbar_wait(tfull + as, ((uint32_t)n >> 1) & 1u);
             tc_fence_after();
-            const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)as * kPN;
-#pragma unroll 1
-            for (int c = 0; c < kPN / 32; ++c) {
-                const int col0 = n * kPN + c * 32;
-                if (col0 >= p.V) break;
-                uint32_t v[32];
-                tmem_ld32(trow + c * 32, v);
-                tmem_ld_wait();
-                float x[32];
-                if (a.vec4) {
+            const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kPN + hsel * HC);
+            const int cbase = n * kPN + hsel * HC;
+            uint32_t v[2][32];
+            if (cbase < p.V) tmem_ld32(trow, v[0]);
+#pragma unroll
+            for (int c = 0; c < HC / 32; ++c) {
+                const int col0 = cbase + c * 32;
+                if (col0 < p.V) {                      // warp-uniform
+                    tmem_ld_wait();
+                    // the next chunk's accumulators travel while this one is reduced
+                    if (c + 1 < HC / 32 && col0 + 32 < p.V) tmem_ld32(trow + (c + 1) * 32, v[(c + 1) & 1]);
+                    float x[32];
+                    if (a.vec4) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            const bool in = col0 + i < p.V;                         // V % 4 == 0: whole groups
+                            const float4 bb = (in && a.bias) ? __ldg(reinterpret_cast<const float4*>(a.bias + col0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            x[i] = in ? __uint_as_float(v[c & 1][i]) + bb.x : -INFINITY;
+                            x[i + 1] = in ? __uint_as_float(v[c & 1][i + 1]) + bb.y : -INFINITY;
+                            x[i + 2] = in ? __uint_as_float(v[c & 1][i + 2]) + bb.z : -INFINITY;
+                            x[i + 3] = in ? __uint_as_float(v[c & 1][i + 3]) + bb.w : -INFINITY;
+                            if (lrow && in) *reinterpret_cast<float4*>(lrow + col0 + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const bool in = col0 + i < p.V;
+                            x[i] = in ? __uint_as_float(v[c & 1][i]) + (a.bias ? __ldg(a.bias + col0 + i) : 0.0f) : -INFINITY;
+                            if (lrow && in) lrow[col0 + i] = x[i];
+                        }
+                    }
+                    float cm[4] = {x[0], x[1], x[2], x[3]};
+#pragma unroll
+                    for (int i = 4; i < 32; i += 4) {
+                        cm[0] = fmaxf(cm[0], x[i]); cm[1] = fmaxf(cm[1], x[i + 1]);
+                        cm[2] = fmaxf(cm[2], x[i + 2]); cm[3] = fmaxf(cm[3], x[i + 3]);
+                    }
+                    const float cmx = fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3]));
+                    if (cmx > mx) { sum *= fast_ex2((mx - cmx) * kLog2e); mx = cmx; }     // first chunk: mx = -inf -> sum (0) * 0
+                    const float ms = mx * kLog2e;
+                    float sp[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
-                        const bool in = col0 + i < p.V;                         // V % 4 == 0: whole groups
-                        const float4 bb = (in && a.bias) ? __ldg(reinterpret_cast<const float4*>(a.bias + col0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        x[i] = in ? __uint_as_float(v[i]) + bb.x : -INFINITY;
-                        x[i + 1] = in ? __uint_as_float(v[i + 1]) + bb.y : -INFINITY;
-                        x[i + 2] = in ? __uint_as_float(v[i + 2]) + bb.z : -INFINITY;
-                        x[i + 3] = in ? __uint_as_float(v[i + 3]) + bb.w : -INFINITY;
-                        if (lrow && in) *reinterpret_cast<float4*>(lrow + col0 + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
+                        sp[0] += fast_ex2(fmaf(x[i], kLog2e, -ms));
+                        sp[1] += fast_ex2(fmaf(x[i + 1], kLog2e, -ms));
+                        sp[2] += fast_ex2(fmaf(x[i + 2], kLog2e, -ms));
+                        sp[3] += fast_ex2(fmaf(x[i + 3], kLog2e, -ms));
                     }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const bool in = col0 + i < p.V;
-                        x[i] = in ? __uint_as_float(v[i]) + (a.bias ? __ldg(a.bias + col0 + i) : 0.0f) : -INFINITY;
-                        if (lrow && in) lrow[col0 + i] = x[i];
-                    }
+                    sum += (sp[0] + sp[1]) + (sp[2] + sp[3]);
                 }
-                float cm = x[0];
-#pragma unroll
-                for (int i = 1; i < 32; ++i) cm = fmaxf(cm, x[i]);
-                if (cm > mx) { sum *= fast_ex2((mx - cm) * kLog2e); mx = cm; }     // first chunk: mx = -inf -> sum (0) * 0
-                const float ms = mx * kLog2e;
-                float s0 = 0.0f, s1 = 0.0f;
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    s0 += fast_ex2(fmaf(x[i], kLog2e, -ms));
-                    s1 += fast_ex2(fmaf(x[i + 1], kLog2e, -ms));
-                }
-                sum += s0 + s1;
             }
-            // the utterance's own columns of this tile (blank, l_1..l_L): column index uniform over the warp
-            for (int j = 0; j <= L; ++j) {
+            // the utterance's own columns in this half tile (blank, l_1..l_L): column index uniform over the warp
+            for (int k = hstart[2 * n + hsel]; k < hstart[2 * n + hsel + 1]; ++k) {
+                const int j = order[k];
                 const int vj = j == 0 ? p.blank : labs[j - 1];
-                if ((vj >> 8) != n) continue;
-                const uint32_t raw1 = tmem_ld1(trow + (uint32_t)(vj & (kPN - 1)));
+                const uint32_t raw1 = tmem_ld1(trow + (uint32_t)(vj & (HC - 1)));
                 tmem_ld_wait();
                 stash[j * kPM + r] = __uint_as_float(raw1) + (a.bias ? __ldg(a.bias + vj) : 0.0f);
             }
             tc_fence_before();
             mbar_arrive(tempty + as);
         }
+        // ---- the two column halves of a row meet: row max and normaliser ----
+        part[hsel * kPM + r] = make_float2(mx, sum);
+        bar_sync_epilogue();
+        {
+            const float2 o = part[(hsel ^ 1) * kPM + r];
+            const float m2 = fmaxf(mx, o.x);           // a half without columns holds {-inf, 0}: ex2(-inf) = 0
+            sum = sum * fast_ex2((mx - m2) * kLog2e) + o.y * fast_ex2((o.x - m2) * kLog2e);
+            mx = m2;
+        }
         // ---- the frame's outputs: {row max, log2 normaliser} and its slot of the emission table ----
-        if (t < Tb) w.fr[(size_t)b * p.T + t] = make_float2(mx, log2f(sum));
+        if (hsel == 0 && t < Tb) w.fr[(size_t)b * p.T + t] = make_float2(mx, log2f(sum));
         const int blk = t >> 3;
         if (blk < w.NB && blk * kG < Tb) {
             double* ecol = w.E + ((size_t)b * w.NB + blk) * w.W * kEC + (t & 7);
             const bool valid = t < Tb;
             bool floored = false;
-            for (int j = 0; j <= L; ++j) {
+            for (int j = hsel; j <= L; j += 2) {       // the pair shares the frame's columns
                 const float l2 = (stash[j * kPM + r] - mx) * kLog2e;
                 floored |= valid && l2 < kMinLog2;
                 ecol[(size_t)j * kEC] = valid ? (double)fast_ex2(fmaxf(l2, kMinLog2)) : 0.0;
