@@ -381,7 +381,7 @@ int launch_proj(const ctcb_proj_t* pj, const ctcb_problem_t* p, const ctcb::Prob
         return fail(CTCB_INVALID_VALUE, "projection: K and the hidden strides must be multiples of 4 elements, bases 16-byte aligned");
     if (!is_device_ptr(pj->hidden) || !is_device_ptr(pj->weight) || !is_device_ptr(pj->bias))
         return fail(CTCB_INVALID_VALUE, "projection: hidden / weight / bias must be CUDA device memory");
-    const size_t smem = ctcb::proj_smem_bytes(p->Lmax, lay.Lp);
+    const size_t smem = ctcb::proj_smem_bytes(p->Lmax, lay.Lp, p->logits != nullptr);
     if (smem > 232448 - 256) return fail(CTCB_UNSUPPORTED, "projection: Lmax=%d label columns do not fit the kernel's shared memory", p->Lmax);
     if ((p->V + 127) / 128 + 1 > ctcb::kPMaxHalfTiles) return fail(CTCB_UNSUPPORTED, "projection: V=%d is wider than the kernel's column index", p->V);
     EncodeTiledFn enc = encode_tiled();
@@ -410,10 +410,27 @@ int launch_proj(const ctcb_proj_t* pj, const ctcb_problem_t* p, const ctcb::Prob
     ctcb::ProjArgs pa{};
     pa.p = dp; pa.w = w; pa.bias = pj->bias; pa.logits = const_cast<float*>(p->logits);
     pa.K = pj->K; pa.NT = (p->V + ctcb::kPN - 1) / ctcb::kPN; pa.KB = (pj->K + ctcb::kPK - 1) / ctcb::kPK;
-    pa.vec4 = (p->V % 4 == 0 && reinterpret_cast<uintptr_t>(pj->bias) % 16 == 0 &&
-               (!p->logits || (p->logits_stride_t % 4 == 0 && p->logits_stride_b % 4 == 0 && reinterpret_cast<uintptr_t>(p->logits) % 16 == 0))) ? 1 : 0;
+    pa.vec4 = (p->V % 4 == 0 && reinterpret_cast<uintptr_t>(pj->bias) % 16 == 0) ? 1 : 0;
+    // the logits (kept for the gradient kernel) leave through TMA stores when their rows allow a tensor map
+    CUtensorMap tmC = tmA;
+    pa.store = 0;
+    pa.smem_stash = ctcb::proj_smem_stash(p->Lmax, p->logits != nullptr) ? 1 : 0;
+    if (p->logits) {
+        pa.store = 2;
+        if (p->logits_stride_t % 4 == 0 && p->logits_stride_b % 4 == 0 && reinterpret_cast<uintptr_t>(p->logits) % 16 == 0) {
+            const cuuint64_t gdim[3] = {(cuuint64_t)p->V, (cuuint64_t)p->T, (cuuint64_t)p->B};
+            const cuuint64_t gstr[2] = {(cuuint64_t)p->logits_stride_t * 4, (cuuint64_t)p->logits_stride_b * 4};
+            const cuuint32_t box[3] = {32, 32, 1};
+            const cuuint32_t est[3] = {1, 1, 1};
+            // a (T,B,V) buffer has the batch stride below the frame stride: the map's dimensions stay (V, T, B), strides say the rest
+            const CUresult r = enc(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p->logits), gdim, gstr, box, est,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r == CUDA_SUCCESS) pa.store = 1;
+        }
+    }
     const dim3 pgrid((p->T + ctcb::kPM - 1) / ctcb::kPM, p->B);
-    CUDA_TRY(ctcb::launch_proj_emit(tmA, tmB, pa, pgrid, smem, stream));
+    CUDA_TRY(ctcb::launch_proj_emit(tmA, tmB, tmC, pa, pgrid, smem, stream));
     mark(stream);
     // per-utterance metadata: k_emit's extra CTA alone (grid.x = 1: every CTA is the metadata CTA)
     ctcb::k_emit<1, 0><<<dim3(1, p->B), 128, ctcb::emit_smem_bytes(lay.Lp, 0), stream>>>(dp, w);

@@ -5,7 +5,8 @@
 
 namespace ctcb {
 
-cudaError_t launch_proj_emit(const CUtensorMap& tmA, const CUtensorMap& tmB, const ProjArgs& a, dim3 grid, size_t smem, cudaStream_t stream) {
+cudaError_t launch_proj_emit(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const ProjArgs& a, dim3 grid, size_t smem,
+                             cudaStream_t stream) {
     // the opt-in shared-memory size is a per-device function attribute: raised when a launch needs more than any before
     static thread_local int done_dev = -1;
     static thread_local size_t done_bytes = 0;
@@ -16,7 +17,7 @@ cudaError_t launch_proj_emit(const CUtensorMap& tmA, const CUtensorMap& tmB, con
         if (rc != cudaSuccess) return rc;
         done_dev = dev; done_bytes = smem;
     }
-    k_proj_emit<<<grid, kPThreads, smem, stream>>>(tmA, tmB, a);
+    k_proj_emit<<<grid, kPThreads, smem, stream>>>(tmA, tmB, tmC, a);
     return cudaGetLastError();
 }
 

@@ -21,12 +21,15 @@
 //   * warps 2..5: epilogue, ONE FRAME PER THREAD (TMEM lane = accumulator row): `tcgen05.ld.32x32b.x32` brings 32
 //     columns of the thread's own row into registers; bias add, online row maximum / sum of exp2 (no shuffles: a
 //     thread owns its row), optional store of the logits row chunk for the gradient kernel (training) -- or no
-//     store at all (validation, train_ctc_ce.py:143: the logits never exist in HBM); the utterance's label columns
-//     that fall into the tile are fetched again from TMEM with single-column loads (the column index is uniform
-//     over the warp) and parked in shared memory until the row maximum is final;
-//   * after the sweep every thread writes its frame's {row max, log2 sum} to `fr` and its frame's slot of the
-//     emission table E (fp64 softmax numerators, frame-minor blocks of 8 frames) -- the two inputs of k_walk's
-//     unfused variant, bit-compatible with what k_emit writes from a logits tensor.
+//     store at all (validation, train_ctc_ce.py:143: the logits never exist in HBM).  The store goes through a
+//     128B-swizzled 32 x 32 staging tile per warp and leaves with `cp.async.bulk.tensor` (TMA store, 3-D map over the
+//     logits: rows beyond T and columns beyond V are clipped by the hardware) -- a thread owns a ROW, so direct
+//     stores would write 16 bytes per row and instruction (measured: +90 us at V = 2000);
+//   * the utterance's label columns that fall into the tile are fetched again from TMEM with single-column loads
+//     (the column index is uniform over the warp) and parked, raw, in their slot of the emission table E;
+//   * after the sweep every thread writes its frame's {row max, log2 sum} to `fr` and turns its parked columns into
+//     the softmax numerators relative to the final row maximum (fp64, frame-minor blocks of 8 frames) -- `fr` and E
+//     are the two inputs of k_walk's unfused variant, bit-compatible with what k_emit writes from a logits tensor.
 // The tf32 data path reads the caller's fp32 tensors as they are (the tensor cores ignore the low 13 mantissa
 // bits): no conversion pass, no copy of hidden or W.
 #pragma once
@@ -54,16 +57,27 @@ struct ProjArgs {
     const float* bias;       // (V,) or nullptr
     float* logits;           // where the projection's output is kept for the gradient kernel (Problem::logits), or nullptr
     int K, NT, KB;           // hidden units, vocabulary tiles, K blocks
-    int vec4;                // logits rows (and bias) allow 16-byte accesses
+    int vec4;                // bias allows 16-byte loads
+    int store;               // 0: logits not stored; 1: TMA store through the staging tiles; 2: direct scalar stores
+    int smem_stash;          // the label columns are parked in shared memory (store == 0 and they fit), else in E
 };
 
-__host__ __device__ inline size_t proj_smem_bytes(int Lmax, int Lp) {
-    return 1024 + (size_t)kPStages * (kPBytesA + kPBytesB) + (size_t)(Lmax + 1) * kPM * sizeof(float) +
+constexpr uint32_t kPStageTile = 32 * 32 * 4;    // one warp's 32 frames x 32 columns on their way to the logits tensor
+// the region behind the ring: staging tiles of the logits store, or -- when the logits are not stored and the label
+// row fits -- the parked label columns [Lmax+1][128] (otherwise they are parked in the emission table itself)
+__host__ __device__ inline bool proj_smem_stash(int Lmax, bool store) { return !store && (size_t)(Lmax + 1) * kPM * sizeof(float) <= 80 * 1024; }
+__host__ __device__ inline size_t proj_side_bytes(int Lmax, bool store) {
+    if (store) return (size_t)kPEpiWarps * 2 * kPStageTile;
+    return proj_smem_stash(Lmax, store) ? (size_t)(Lmax + 1) * kPM * sizeof(float) : 0;
+}
+__host__ __device__ inline size_t proj_smem_bytes(int Lmax, int Lp, bool store) {
+    return 1024 + (size_t)kPStages * (kPBytesA + kPBytesB) + proj_side_bytes(Lmax, store) +
            (size_t)Lp * sizeof(int) + 128 + 2 * kPM * sizeof(float2) + (size_t)(Lp + 4) * sizeof(int) + kPMaxHalfTiles * sizeof(int);
 }
 
 // host-side launcher, defined in ctcb_proj.cu (its own translation unit: the kernel below is compiled there only)
-cudaError_t launch_proj_emit(const CUtensorMap& tmA, const CUtensorMap& tmB, const ProjArgs& a, dim3 grid, size_t smem, cudaStream_t stream);
+cudaError_t launch_proj_emit(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const ProjArgs& a, dim3 grid, size_t smem,
+                             cudaStream_t stream);
 
 #ifdef CTCB_PROJ_IMPL
 // ---- tcgen05 / TMA wrappers -------------------------------------------------------------------------------------
@@ -74,6 +88,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// shared -> global tile store (the staging tile was written with ordinary stores: the caller fences the proxy)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
@@ -131,7 +151,8 @@ constexpr uint32_t kPIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kP
 __device__ __forceinline__ void bar_sync_epilogue() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kPEpiWarps) : "memory"); }
 
 __global__ void __launch_bounds__(kPThreads, 1)
-k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ProjArgs a) {
+k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+            ProjArgs a) {
     extern __shared__ unsigned char proj_raw[];
     __shared__ int s_L;
     const Problem& p = a.p;
@@ -152,8 +173,9 @@ k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const uint32_t base = (raw + 1023u) & ~1023u;          // SWIZZLE_128B tiles want 1024-byte alignment
     unsigned char* gbase = proj_raw + (base - raw);
     const uint32_t sA = base, sB = base + kPStages * kPBytesA;
-    float* stash = reinterpret_cast<float*>(gbase + (size_t)kPStages * (kPBytesA + kPBytesB));   // [Lmax+1][128] raw label logits
-    int* labs = reinterpret_cast<int*>(stash + (size_t)(p.Lmax + 1) * kPM);
+    const uint32_t sC = base + kPStages * (kPBytesA + kPBytesB);          // [epilogue warp][2] staging tiles of the logits store
+    float* stash = reinterpret_cast<float*>(gbase + (size_t)kPStages * (kPBytesA + kPBytesB));   // [Lmax+1][128], a.smem_stash only
+    int* labs = reinterpret_cast<int*>(gbase + (size_t)kPStages * (kPBytesA + kPBytesB) + proj_side_bytes(p.Lmax, a.store != 0));
     uint64_t* bars = reinterpret_cast<uint64_t*>(labs + w.Lp);
     uint64_t* full = bars;
     uint64_t* empty = bars + kPStages;
@@ -171,6 +193,7 @@ k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         s_L = p.Lmax;
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if (a.store == 1) tma_prefetch_desc(&tmC);
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kPTmemCols);
     tc_fence_before();
@@ -239,25 +262,35 @@ k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             labs[j] = (int)(v < 0 ? 0 : (v >= p.V ? p.V - 1 : v));
         }
         bar_sync_epilogue();
-        // the lattice's columns (0 = blank, j = label j) bucketed by the half tile (128 symbols) their symbol lies in: each
-        // epilogue warp then visits exactly its own columns of a tile instead of scanning the label row
+        // the lattice's columns (0 = blank, j = label j) bucketed by the half tile (128 symbols) their symbol lies in, the
+        // buckets of the lower column halves first (key = half * NT + tile): an epilogue warp visits exactly its own
+        // columns of a tile, and all the columns a thread parks are one contiguous range of `order`
         for (int h = etid; h <= 2 * a.NT; h += NE) {
             int c = 0;
-            for (int j = 0; j <= L; ++j) c += ((j == 0 ? p.blank : labs[j - 1]) >> 7) < h;
+            for (int j = 0; j <= L; ++j) { const int hb = (j == 0 ? p.blank : labs[j - 1]) >> 7; c += ((hb & 1) * a.NT + (hb >> 1)) < h; }
             hstart[h] = c;
         }
         for (int j = etid; j <= L; j += NE) {
             const int hb = (j == 0 ? p.blank : labs[j - 1]) >> 7;
+            const int key = (hb & 1) * a.NT + (hb >> 1);
             int pos = 0;
             for (int k = 0; k <= L; ++k) {
                 const int hk = (k == 0 ? p.blank : labs[k - 1]) >> 7;
-                pos += (hk < hb) | ((hk == hb) & (k < j));
+                const int kk = (hk & 1) * a.NT + (hk >> 1);
+                pos += (kk < key) | ((kk == key) & (k < j));
             }
             order[pos] = j;
         }
         bar_sync_epilogue();
 
-        float* lrow = (a.logits && t < p.T) ? a.logits + (long long)b * p.st_b + (long long)t * p.st_t : nullptr;
+        float* lrow = (a.store == 2 && t < p.T) ? a.logits + (long long)b * p.st_b + (long long)t * p.st_t : nullptr;
+        // this frame's slots of the emission table (block of 8 frames, frame-minor): parked raw, finished below
+        const int blk = t >> 3;
+        const bool eblock = blk < w.NB && blk * kG < Tb;
+        const bool valid = t < Tb;
+        double* ecol = w.E + ((size_t)b * w.NB + (eblock ? blk : 0)) * w.W * kEC + (t & 7);
+        const uint32_t sbuf = sC + (uint32_t)(warp - 2) * 2 * kPStageTile;
+        int nstored = 0;
         float mx = -INFINITY, sum = 0.0f;
         for (int n = 0; n < a.NT; ++n) {
             const int as = n & 1;
@@ -284,15 +317,32 @@ k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             x[i + 1] = in ? __uint_as_float(v[c & 1][i + 1]) + bb.y : -INFINITY;
                             x[i + 2] = in ? __uint_as_float(v[c & 1][i + 2]) + bb.z : -INFINITY;
                             x[i + 3] = in ? __uint_as_float(v[c & 1][i + 3]) + bb.w : -INFINITY;
-                            if (lrow && in) *reinterpret_cast<float4*>(lrow + col0 + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
                         }
                     } else {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             const bool in = col0 + i < p.V;
                             x[i] = in ? __uint_as_float(v[c & 1][i]) + (a.bias ? __ldg(a.bias + col0 + i) : 0.0f) : -INFINITY;
-                            if (lrow && in) lrow[col0 + i] = x[i];
                         }
+                    }
+                    if (a.store == 1) {
+                        // 32 frames x 32 columns through a swizzled staging tile: row = lane, 16-byte chunk i at (i ^ row % 8)
+                        const uint32_t tile = sbuf + (uint32_t)(nstored & 1) * kPStageTile;
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that read this tile two chunks ago
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
+                                         ::"r"(tile + (uint32_t)lane * 128u + (uint32_t)((i ^ (lane & 7)) << 4)),
+                                           "f"(x[4 * i]), "f"(x[4 * i + 1]), "f"(x[4 * i + 2]), "f"(x[4 * i + 3]) : "memory");
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) tma_store_3d(&tmC, tile, col0, m0 + q * 32, b);
+                        ++nstored;
+                    } else if (lrow) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (col0 + i < p.V) lrow[col0 + i] = x[i];
                     }
                     float cm[4] = {x[0], x[1], x[2], x[3]};
 #pragma unroll
@@ -315,12 +365,14 @@ k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
             }
             // the utterance's own columns in this half tile (blank, l_1..l_L): column index uniform over the warp
-            for (int k = hstart[2 * n + hsel]; k < hstart[2 * n + hsel + 1]; ++k) {
+            for (int k = hstart[hsel * a.NT + n]; k < hstart[hsel * a.NT + n + 1]; ++k) {
                 const int j = order[k];
                 const int vj = j == 0 ? p.blank : labs[j - 1];
                 const uint32_t raw1 = tmem_ld1(trow + (uint32_t)(vj & (HC - 1)));
                 tmem_ld_wait();
-                stash[j * kPM + r] = __uint_as_float(raw1) + (a.bias ? __ldg(a.bias + vj) : 0.0f);
+                const float xv = __uint_as_float(raw1) + (a.bias ? __ldg(a.bias + vj) : 0.0f);
+                if (a.smem_stash) stash[j * kPM + r] = xv;
+                else if (eblock) ecol[(size_t)j * kEC] = valid ? (double)xv : 0.0;
             }
             tc_fence_before();
             mbar_arrive(tempty + as);
@@ -334,20 +386,39 @@ k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             sum = sum * fast_ex2((mx - m2) * kLog2e) + o.y * fast_ex2((o.x - m2) * kLog2e);
             mx = m2;
         }
-        // ---- the frame's outputs: {row max, log2 normaliser} and its slot of the emission table ----
-        if (hsel == 0 && t < Tb) w.fr[(size_t)b * p.T + t] = make_float2(mx, log2f(sum));
-        const int blk = t >> 3;
-        if (blk < w.NB && blk * kG < Tb) {
-            double* ecol = w.E + ((size_t)b * w.NB + blk) * w.W * kEC + (t & 7);
-            const bool valid = t < Tb;
+        // ---- the frame's outputs: {row max, log2 normaliser}; the parked columns (each thread finishes the ones it
+        // parked itself) become softmax numerators relative to the final row maximum ----
+        if (hsel == 0 && valid) w.fr[(size_t)b * p.T + t] = make_float2(mx, log2f(sum));
+        if (a.smem_stash) {
+            if (eblock) {
+                bool floored = false;
+                for (int k = hstart[hsel * a.NT]; k < hstart[(hsel + 1) * a.NT]; ++k) {
+                    const int j = order[k];
+                    const float l2 = (stash[j * kPM + r] - mx) * kLog2e;
+                    floored |= valid && l2 < kMinLog2;
+                    ecol[(size_t)j * kEC] = valid ? (double)fast_ex2(fmaxf(l2, kMinLog2)) : 0.0;
+                }
+                if (floored && p.status) atomicOr(p.status + b, UTT_WIDE_LOGITS);
+            }
+        } else if (eblock && valid) {
             bool floored = false;
-            for (int j = hsel; j <= L; j += 2) {       // the pair shares the frame's columns
-                const float l2 = (stash[j * kPM + r] - mx) * kLog2e;
-                floored |= valid && l2 < kMinLog2;
-                ecol[(size_t)j * kEC] = valid ? (double)fast_ex2(fmaxf(l2, kMinLog2)) : 0.0;
+            const int k1 = hstart[(hsel + 1) * a.NT];
+            for (int k0 = hstart[hsel * a.NT]; k0 < k1; k0 += 8) {          // eight independent round trips to L2 at a time
+                double raw[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (k0 + i < k1) raw[i] = ecol[(size_t)order[k0 + i] * kEC];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (k0 + i < k1) {
+                        const float l2 = ((float)raw[i] - mx) * kLog2e;
+                        floored |= l2 < kMinLog2;
+                        ecol[(size_t)order[k0 + i] * kEC] = (double)fast_ex2(fmaxf(l2, kMinLog2));
+                    }
             }
             if (floored && p.status) atomicOr(p.status + b, UTT_WIDE_LOGITS);
         }
+        if (a.store == 1 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tiles are read before the CTA exits
     }
     tc_fence_before();
     __syncthreads();

@@ -86,9 +86,28 @@ def main():
         from gluon_e2e_asr_b200 import CtcLoss
         CtcLoss()(logits, s["lab"], s["pl"], s["ll"]).mean().backward()
 
+    def fused_fwd_keep(i):
+        s = sets[i % a.sets]
+        h = s["h"].requires_grad_(True)
+        return proj_ctc_loss(h, s["w"], s["bias"], s["lab"], s["pl"], s["ll"])
+
+    def unfused_fwd_keep(i):
+        s = sets[i % a.sets]
+        from gluon_e2e_asr_b200 import CtcLoss
+        logits = torch.addmm(s["bias"], s["h"].view(-1, a.H), s["w"].t()).view(a.B, a.T, a.V).requires_grad_(True)
+        return CtcLoss()(logits, s["lab"], s["pl"], s["ll"])
+
+    def backward_gemms(i):
+        s = sets[i % a.sets]
+        G2 = gbuf.view(-1, a.V)
+        return (G2 @ s["w"]), (G2.t() @ s["h"].view(-1, a.H)), G2.sum(0)
+
+    gbuf = torch.randn((a.B, a.T, a.V), device=dev)
     lf, lu = fused_fwd(0), unfused_fwd(0)
     res["max_rel_loss_difference_fused_vs_unfused"] = float(((lf - lu).abs() / lu.abs().clamp_min(1)).max())
     for name, fn in (("gemm_only_tf32_cublas", gemm_only), ("fused_forward", fused_fwd), ("unfused_forward", unfused_fwd),
+                     ("fused_forward_keep_logits", fused_fwd_keep), ("unfused_forward_keep", unfused_fwd_keep),
+                     ("backward_gemms_tf32_cublas", backward_gemms),
                      ("fused_step", fused_step), ("unfused_step", unfused_step)):
         res[name + "_us"] = round(timed(fn, a.iters), 1)
     flops = 2.0 * a.B * a.T * a.H * a.V
