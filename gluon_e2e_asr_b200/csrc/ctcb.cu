@@ -60,9 +60,9 @@ thread_local int g_prof_count = 0;
 // Read from the environment ONCE (CTCB_<NAME>, at first use) and changeable through ctcb_set_option (tests, A/B
 // runs): nothing on the per-call host path calls getenv.  -1 = automatic.
 enum Opt { OPT_WALK_P, OPT_WALK_NW, OPT_WALK_STAGES, OPT_OVERLAP, OPT_FUSED, OPT_WALK_PER_SM, OPT_EMIT_STAGED,
-           OPT_GRAD_STAGED, OPT_MEET, OPT_GRAD2, OPT_GRAD2_BLOCKS, OPT_WALK_HW_WAIT, OPT_GRAD2_OCC, OPT_COUNT };
+           OPT_GRAD_STAGED, OPT_MEET, OPT_GRAD2, OPT_GRAD2_BLOCKS, OPT_WALK_HW_WAIT, OPT_GRAD2_OCC, OPT_PROJ_CTAS, OPT_COUNT };
 const char* const kOptNames[OPT_COUNT] = {"walk_p", "walk_nw", "walk_stages", "overlap", "fused", "walk_per_sm",
-                                          "emit_staged", "grad_staged", "meet", "grad2", "grad2_blocks", "walk_hw_wait", "grad2_occ"};
+                                          "emit_staged", "grad_staged", "meet", "grad2", "grad2_blocks", "walk_hw_wait", "grad2_occ", "proj_ctas"};
 struct Options {
     int v[OPT_COUNT];
     Options() {
@@ -381,9 +381,10 @@ int launch_proj(const ctcb_proj_t* pj, const ctcb_problem_t* p, const ctcb::Prob
         return fail(CTCB_INVALID_VALUE, "projection: K and the hidden strides must be multiples of 4 elements, bases 16-byte aligned");
     if (!is_device_ptr(pj->hidden) || !is_device_ptr(pj->weight) || !is_device_ptr(pj->bias))
         return fail(CTCB_INVALID_VALUE, "projection: hidden / weight / bias must be CUDA device memory");
-    const size_t smem = ctcb::proj_smem_bytes(p->Lmax, lay.Lp, p->logits != nullptr);
-    if (smem > 232448 - 256) return fail(CTCB_UNSUPPORTED, "projection: Lmax=%d label columns do not fit the kernel's shared memory", p->Lmax);
-    if ((p->V + 127) / 128 + 1 > ctcb::kPMaxHalfTiles) return fail(CTCB_UNSUPPORTED, "projection: V=%d is wider than the kernel's column index", p->V);
+    // CTA pairs (tcgen05 cta_group::2: 256 frames per pair, each CTA stages half of the vocabulary tile) or single CTAs
+    const int ctas = opt(OPT_PROJ_CTAS) == 2 ? 2 : 1;
+    const size_t smem = ctcb::proj_smem_bytes(p->Lmax, lay.Lp, p->logits != nullptr, (p->V + ctcb::kPN - 1) / ctcb::kPN, ctas);
+    if (smem > 232448 - 64) return fail(CTCB_UNSUPPORTED, "projection: Lmax=%d label columns do not fit the kernel's shared memory", p->Lmax);
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return fail(CTCB_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
     CUtensorMap tmA, tmB;
@@ -400,7 +401,7 @@ int launch_proj(const ctcb_proj_t* pj, const ctcb_problem_t* p, const ctcb::Prob
     {
         const cuuint64_t gdim[2] = {(cuuint64_t)pj->K, (cuuint64_t)p->V};
         const cuuint64_t gstr[1] = {(cuuint64_t)pj->K * 4};
-        const cuuint32_t box[2] = {(cuuint32_t)ctcb::kPK, (cuuint32_t)ctcb::kPN};
+        const cuuint32_t box[2] = {(cuuint32_t)ctcb::kPK, (cuuint32_t)(ctcb::kPN / ctas)};
         const cuuint32_t est[2] = {1, 1};
         const CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(pj->weight), gdim, gstr, box, est,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -410,6 +411,7 @@ int launch_proj(const ctcb_proj_t* pj, const ctcb_problem_t* p, const ctcb::Prob
     ctcb::ProjArgs pa{};
     pa.p = dp; pa.w = w; pa.bias = pj->bias; pa.logits = const_cast<float*>(p->logits);
     pa.K = pj->K; pa.NT = (p->V + ctcb::kPN - 1) / ctcb::kPN; pa.KB = (pj->K + ctcb::kPK - 1) / ctcb::kPK;
+    pa.ctas = ctas;
     pa.vec4 = (p->V % 4 == 0 && reinterpret_cast<uintptr_t>(pj->bias) % 16 == 0) ? 1 : 0;
     // the logits (kept for the gradient kernel) leave through TMA stores when their rows allow a tensor map
     CUtensorMap tmC = tmA;
@@ -429,7 +431,8 @@ int launch_proj(const ctcb_proj_t* pj, const ctcb_problem_t* p, const ctcb::Prob
             if (r == CUDA_SUCCESS) pa.store = 1;
         }
     }
-    const dim3 pgrid((p->T + ctcb::kPM - 1) / ctcb::kPM, p->B);
+    const int mtiles = (p->T + ctcb::kPM - 1) / ctcb::kPM;
+    const dim3 pgrid(ctas == 2 ? (mtiles + 1) / 2 * 2 : mtiles, p->B);
     CUDA_TRY(ctcb::launch_proj_emit(tmA, tmB, tmC, pa, pgrid, smem, stream));
     mark(stream);
     // per-utterance metadata: k_emit's extra CTA alone (grid.x = 1: every CTA is the metadata CTA)

@@ -44,13 +44,13 @@ namespace ctcb {
 constexpr int kPM = 128;                 // frames per CTA tile = UMMA M (TMEM lanes)
 constexpr int kPN = 256;                 // vocabulary columns per accumulator stage = UMMA N
 constexpr int kPK = 32;                  // fp32 values per K block: 128 bytes, one SWIZZLE_128B row
-constexpr int kPStages = 3;              // shared-memory ring depth
+__host__ __device__ constexpr int proj_stages(int ctas) { return ctas == 2 ? 4 : 3; }    // shared-memory ring depth
 constexpr int kPEpiWarps = 8;             // two epilogue warps per TMEM lane quadrant: each takes half of a tile's columns
 constexpr int kPThreads = 64 + 32 * kPEpiWarps;   // warp 0 TMA, warp 1 MMA + TMEM allocation, warps 2.. epilogue
 constexpr uint32_t kPBytesA = kPM * kPK * 4;     // 16 KB
-constexpr uint32_t kPBytesB = kPN * kPK * 4;     // 32 KB
+constexpr uint32_t kPBytesB = kPN * kPK * 4;     // 32 KB (a CTA pair: each CTA stages half of it)
+__host__ __device__ constexpr uint32_t proj_stage_bytes(int ctas) { return kPBytesA + kPBytesB / ctas; }
 constexpr uint32_t kPTmemCols = 512;             // two accumulator stages of kPN columns
-constexpr int kPMaxHalfTiles = 512;              // half tiles of 128 columns: vocabularies up to 65536 symbols
 
 struct ProjArgs {
     Problem p; Workspace w;
@@ -60,6 +60,7 @@ struct ProjArgs {
     int vec4;                // bias allows 16-byte loads
     int store;               // 0: logits not stored; 1: TMA store through the staging tiles; 2: direct scalar stores
     int smem_stash;          // the label columns are parked in shared memory (store == 0 and they fit), else in E
+    int ctas;                // 1: one CTA per tile; 2: CTA pairs (tcgen05 cta_group::2) over 256 frames
 };
 
 constexpr uint32_t kPStageTile = 32 * 32 * 4;    // one warp's 32 frames x 32 columns on their way to the logits tensor
@@ -70,11 +71,12 @@ __host__ __device__ inline size_t proj_side_bytes(int Lmax, bool store) {
     if (store) return (size_t)kPEpiWarps * 2 * kPStageTile;
     return proj_smem_stash(Lmax, store) ? (size_t)(Lmax + 1) * kPM * sizeof(float) : 0;
 }
-__host__ __device__ inline size_t proj_smem_bytes(int Lmax, int Lp, bool store) {
-    return 1024 + (size_t)kPStages * (kPBytesA + kPBytesB) + proj_side_bytes(Lmax, store) +
-           (size_t)Lp * sizeof(int) + 128 + 2 * kPM * sizeof(float2) + (size_t)(Lp + 4) * sizeof(int) + kPMaxHalfTiles * sizeof(int);
+__host__ __device__ inline size_t proj_smem_bytes(int Lmax, int Lp, bool store, int NT, int ctas) {
+    return 1024 + (size_t)proj_stages(ctas) * proj_stage_bytes(ctas) + proj_side_bytes(Lmax, store) +
+           (size_t)Lp * sizeof(int) + 128 + 2 * kPM * sizeof(float2) + (size_t)(Lp + 4) * sizeof(int) + (size_t)(2 * NT + 4) * sizeof(int);
 }
 
+// (a.ctas == 2: grid.x even, launched as clusters of two CTAs along x)
 // host-side launcher, defined in ctcb_proj.cu (its own translation unit: the kernel below is compiled there only)
 cudaError_t launch_proj_emit(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const ProjArgs& a, dim3 grid, size_t smem,
                              cudaStream_t stream);
@@ -89,6 +91,24 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// CTA pair: each CTA loads its own tiles, the transaction bytes are counted on the LEADER's mbarrier (`bar` is the
+// barrier's address with the pair's rank bit cleared)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+constexpr uint32_t kPairRankMask = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the pair's even CTA
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPairRankMask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 // shared -> global tile store (the staging tile was written with ordinary stores: the caller fences the proxy)
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
@@ -107,6 +127,14 @@ __device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
+// CTA pair: the same warp of BOTH CTAs allocates (and frees), with the same shared-memory slot offset
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t slot_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
 // D[tmem] (+)= A[smem] . B[smem]^T, tf32 inputs, fp32 accumulation; issued by ONE thread for the CTA
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -114,6 +142,20 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// CTA pair: M = 256 (128 rows from each CTA's A tile), B = the two CTAs' halves, D in each CTA's own tensor memory;
+// issued by one thread of the LEADER CTA for both SMs
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// ... and the completion arrives on the mbarrier at the same offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 // arrives on the mbarrier when every tcgen05.mma issued so far by this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -147,9 +189,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // instruction descriptor: D fp32 (bit 4), A and B tf32 (format 2 at bits 7 and 10), both K-major, N >> 3 at
 // bit 17, M >> 4 at bit 24
 constexpr uint32_t kPIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kPN >> 3) << 17) | ((uint32_t)(kPM >> 4) << 24);
+constexpr uint32_t kPIdescPair = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kPN >> 3) << 17) | ((uint32_t)((2 * kPM) >> 4) << 24);
 
 __device__ __forceinline__ void bar_sync_epilogue() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kPEpiWarps) : "memory"); }
 
+template <int CTAS>
 __global__ void __launch_bounds__(kPThreads, 1)
 k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
             ProjArgs a) {
@@ -167,15 +211,19 @@ k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         t64 = t64 < 0 ? 0 : (t64 > p.T ? p.T : t64);
         Tb = (int)t64;
     }
-    if (m0 >= Tb) return;                 // a tile of padded frames: nothing of it is ever read
+    // a tile of padded frames: nothing of it is ever read (a pair leaves together: its second CTA stages half of B)
+    if ((CTAS == 2 ? (int)(blockIdx.x & ~1u) * kPM : m0) >= Tb) return;
+    constexpr int kPStages = proj_stages(CTAS);
+    constexpr uint32_t kBytesB = kPBytesB / CTAS;
+    const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
 
     const uint32_t raw = smem_u32(proj_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;          // SWIZZLE_128B tiles want 1024-byte alignment
     unsigned char* gbase = proj_raw + (base - raw);
     const uint32_t sA = base, sB = base + kPStages * kPBytesA;
-    const uint32_t sC = base + kPStages * (kPBytesA + kPBytesB);          // [epilogue warp][2] staging tiles of the logits store
-    float* stash = reinterpret_cast<float*>(gbase + (size_t)kPStages * (kPBytesA + kPBytesB));   // [Lmax+1][128], a.smem_stash only
-    int* labs = reinterpret_cast<int*>(gbase + (size_t)kPStages * (kPBytesA + kPBytesB) + proj_side_bytes(p.Lmax, a.store != 0));
+    const uint32_t sC = base + kPStages * (kPBytesA + kBytesB);           // [epilogue warp][2] staging tiles of the logits store
+    float* stash = reinterpret_cast<float*>(gbase + (size_t)kPStages * (kPBytesA + kBytesB));    // [Lmax+1][128], a.smem_stash only
+    int* labs = reinterpret_cast<int*>(gbase + (size_t)kPStages * (kPBytesA + kBytesB) + proj_side_bytes(p.Lmax, a.store != 0));
     uint64_t* bars = reinterpret_cast<uint64_t*>(labs + w.Lp);
     uint64_t* full = bars;
     uint64_t* empty = bars + kPStages;
@@ -188,16 +236,16 @@ k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
     if (tid == 0) {
         for (int s = 0; s < kPStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 32 * kPEpiWarps); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, CTAS * 32 * kPEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_L = p.Lmax;
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         if (a.store == 1) tma_prefetch_desc(&tmC);
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kPTmemCols);
+    if (warp == 1) { if (CTAS == 2) tmem_alloc_pair(smem_u32(tmem_slot), kPTmemCols); else tmem_alloc(smem_u32(tmem_slot), kPTmemCols); }
     tc_fence_before();
-    __syncthreads();
+    if (CTAS == 2) cluster_sync_all(); else __syncthreads();      // the pair's barriers exist before anything arrives on them
     tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
@@ -208,15 +256,24 @@ k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int n = 0; n < a.NT; ++n)
                 for (int kb = 0; kb < a.KB; ++kb) {
                     mbar_wait(empty + st, ph ^ 1u);
-                    mbar_expect_tx(full + st, kPBytesA + kPBytesB);
-                    tma_load_3d(sA + st * kPBytesA, &tmA, smem_u32(full + st), kb * kPK, m0, b);
-                    tma_load_2d(sB + st * kPBytesB, &tmB, smem_u32(full + st), kb * kPK, n * kPN);
+                    if (CTAS == 2) {
+                        // both CTAs' bytes are counted on the leader's barrier; this CTA stages its own 128 frames and its
+                        // half of the vocabulary tile
+                        if (rank == 0) mbar_expect_tx(full + st, 2 * (kPBytesA + kBytesB));
+                        const uint32_t lbar = smem_u32(full + st) & kPairRankMask;
+                        tma_load_3d_pair(sA + st * kPBytesA, &tmA, lbar, kb * kPK, m0, b);
+                        tma_load_2d_pair(sB + st * kBytesB, &tmB, lbar, kb * kPK, n * kPN + (int)rank * (kPN / 2));
+                    } else {
+                        mbar_expect_tx(full + st, kPBytesA + kBytesB);
+                        tma_load_3d(sA + st * kPBytesA, &tmA, smem_u32(full + st), kb * kPK, m0, b);
+                        tma_load_2d(sB + st * kBytesB, &tmB, smem_u32(full + st), kb * kPK, n * kPN);
+                    }
                     if (++st == kPStages) { st = 0; ph ^= 1u; }
                 }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer (a pair: its leader CTA, for both SMs) =====
+        if (lane == 0 && rank == 0) {
             int st = 0; uint32_t ph = 0;
             for (int n = 0; n < a.NT; ++n) {
                 const int as = n & 1;
@@ -226,14 +283,18 @@ k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 for (int kb = 0; kb < a.KB; ++kb) {
                     mbar_wait(full + st, ph);
                     tc_fence_after();
-                    const uint32_t a0 = sA + st * kPBytesA, b0 = sB + st * kPBytesB;
+                    const uint32_t a0 = sA + st * kPBytesA, b0 = sB + st * kBytesB;
 #pragma unroll
-                    for (int k = 0; k < kPK / 8; ++k)                          // 8 tf32 values = 32 bytes per instruction
-                        umma_tf32(dcol, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), kPIdesc, (uint32_t)((kb | k) != 0));
-                    umma_commit(smem_u32(empty + st));                         // the stage is free once these MMAs have read it
+                    for (int k = 0; k < kPK / 8; ++k) {                        // 8 tf32 values = 32 bytes per instruction
+                        if (CTAS == 2) umma_tf32_pair(dcol, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), kPIdescPair, (uint32_t)((kb | k) != 0));
+                        else umma_tf32(dcol, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), kPIdesc, (uint32_t)((kb | k) != 0));
+                    }
+                    // the stage is free (in both CTAs) once these MMAs have read it
+                    if (CTAS == 2) umma_commit_pair(smem_u32(empty + st)); else umma_commit(smem_u32(empty + st));
                     if (++st == kPStages) { st = 0; ph ^= 1u; }
                 }
-                umma_commit(smem_u32(tfull + as));                             // the accumulator tile is complete
+                // the accumulator tile is complete (in both CTAs' tensor memory)
+                if (CTAS == 2) umma_commit_pair(smem_u32(tfull + as)); else umma_commit(smem_u32(tfull + as));
             }
         }
     } else {
@@ -375,7 +436,7 @@ k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 else if (eblock) ecol[(size_t)j * kEC] = valid ? (double)xv : 0.0;
             }
             tc_fence_before();
-            mbar_arrive(tempty + as);
+            if (CTAS == 2) mbar_arrive_leader(tempty + as); else mbar_arrive(tempty + as);
         }
         // ---- the two column halves of a row meet: row max and normaliser ----
         part[hsel * kPM + r] = make_float2(mx, sum);
@@ -421,8 +482,8 @@ k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (a.store == 1 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tiles are read before the CTA exits
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem, kPTmemCols);
+    if (CTAS == 2) cluster_sync_all(); else __syncthreads();      // a pair: nobody leaves while its peer may still signal it
+    if (warp == 1) { if (CTAS == 2) tmem_dealloc_pair(tmem, kPTmemCols); else tmem_dealloc(tmem, kPTmemCols); }
 }
 
 #endif  // CTCB_PROJ_IMPL

@@ -11,6 +11,7 @@ HOT = [  # (file tag, mangled-name regex, opcode to centre the excerpt on)
     ("k_grad_staged_CH8", r"k_gradILi4ELi8ELin1ELi0E", "UBLKCP"),
     ("k_walk_P2_NW3_unfused", r"k_walkILi2ELi3ELb1ELb0E", "UBLKCP"),
     ("k_meet_P4", r"k_meetILi4E", "UBLKCP"),
+    ("k_proj_emit_tcgen05", r"k_proj_emit", "UTCHMMA"),
 ]
 res = subprocess.run(["cuobjdump", "--dump-resource-usage", LIB], capture_output=True, text=True).stdout
 sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
