@@ -60,9 +60,9 @@ thread_local int g_prof_count = 0;
 // Read from the environment ONCE (CTCB_<NAME>, at first use) and changeable through ctcb_set_option (tests, A/B
 // runs): nothing on the per-call host path calls getenv.  -1 = automatic.
 enum Opt { OPT_WALK_P, OPT_WALK_NW, OPT_WALK_STAGES, OPT_OVERLAP, OPT_FUSED, OPT_WALK_PER_SM, OPT_EMIT_STAGED,
-           OPT_GRAD_STAGED, OPT_MEET, OPT_GRAD2, OPT_GRAD2_BLOCKS, OPT_WALK_HW_WAIT, OPT_GRAD2_OCC, OPT_PROJ_CTAS, OPT_COUNT };
+           OPT_GRAD_STAGED, OPT_MEET, OPT_GRAD2, OPT_GRAD2_BLOCKS, OPT_WALK_HW_WAIT, OPT_GRAD2_OCC, OPT_PROJ_CTAS, OPT_PROJ_DBG, OPT_COUNT };
 const char* const kOptNames[OPT_COUNT] = {"walk_p", "walk_nw", "walk_stages", "overlap", "fused", "walk_per_sm",
-                                          "emit_staged", "grad_staged", "meet", "grad2", "grad2_blocks", "walk_hw_wait", "grad2_occ", "proj_ctas"};
+                                          "emit_staged", "grad_staged", "meet", "grad2", "grad2_blocks", "walk_hw_wait", "grad2_occ", "proj_ctas", "proj_dbg"};
 struct Options {
     int v[OPT_COUNT];
     Options() {
@@ -382,7 +382,7 @@ int launch_proj(const ctcb_proj_t* pj, const ctcb_problem_t* p, const ctcb::Prob
     if (!is_device_ptr(pj->hidden) || !is_device_ptr(pj->weight) || !is_device_ptr(pj->bias))
         return fail(CTCB_INVALID_VALUE, "projection: hidden / weight / bias must be CUDA device memory");
     // CTA pairs (tcgen05 cta_group::2: 256 frames per pair, each CTA stages half of the vocabulary tile) or single CTAs
-    const int ctas = opt(OPT_PROJ_CTAS) == 2 ? 2 : 1;
+    const int ctas = opt(OPT_PROJ_CTAS) == 1 ? 1 : 2;            // measured: pairs 186 us, single CTAs 190 us per fused forward (cfg3, H = 512)
     const size_t smem = ctcb::proj_smem_bytes(p->Lmax, lay.Lp, p->logits != nullptr, (p->V + ctcb::kPN - 1) / ctcb::kPN, ctas);
     if (smem > 232448 - 64) return fail(CTCB_UNSUPPORTED, "projection: Lmax=%d label columns do not fit the kernel's shared memory", p->Lmax);
     EncodeTiledFn enc = encode_tiled();
@@ -412,6 +412,7 @@ int launch_proj(const ctcb_proj_t* pj, const ctcb_problem_t* p, const ctcb::Prob
     pa.p = dp; pa.w = w; pa.bias = pj->bias; pa.logits = const_cast<float*>(p->logits);
     pa.K = pj->K; pa.NT = (p->V + ctcb::kPN - 1) / ctcb::kPN; pa.KB = (pj->K + ctcb::kPK - 1) / ctcb::kPK;
     pa.ctas = ctas;
+    pa.dbg = opt(OPT_PROJ_DBG) > 0 ? opt(OPT_PROJ_DBG) : 0;
     pa.vec4 = (p->V % 4 == 0 && reinterpret_cast<uintptr_t>(pj->bias) % 16 == 0) ? 1 : 0;
     // the logits (kept for the gradient kernel) leave through TMA stores when their rows allow a tensor map
     CUtensorMap tmC = tmA;
@@ -435,8 +436,18 @@ int launch_proj(const ctcb_proj_t* pj, const ctcb_problem_t* p, const ctcb::Prob
     const dim3 pgrid(ctas == 2 ? (mtiles + 1) / 2 * 2 : mtiles, p->B);
     CUDA_TRY(ctcb::launch_proj_emit(tmA, tmB, tmC, pa, pgrid, smem, stream));
     mark(stream);
-    // per-utterance metadata: k_emit's extra CTA alone (grid.x = 1: every CTA is the metadata CTA)
-    ctcb::k_emit<1, 0><<<dim3(1, p->B), 128, ctcb::emit_smem_bytes(lay.Lp, 0), stream>>>(dp, w);
+    // per-utterance metadata: k_emit's extra CTA alone (grid.x = 1: every CTA is the metadata CTA), as the projection
+    // kernel's programmatic dependent -- it starts at once and runs beside it (it reads nothing the projection writes);
+    // the recursion kernel that follows is an ordinary launch and waits for both
+    {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(1, p->B); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = ctcb::emit_smem_bytes(lay.Lp, 0); cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = g_prof_events ? 0 : 1;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, ctcb::k_emit<1, 0>, dp, w));
+    }
     mark(stream);
     return CTCB_OK;
 }

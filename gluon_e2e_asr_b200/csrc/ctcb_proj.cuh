@@ -61,6 +61,7 @@ struct ProjArgs {
     int store;               // 0: logits not stored; 1: TMA store through the staging tiles; 2: direct scalar stores
     int smem_stash;          // the label columns are parked in shared memory (store == 0 and they fit), else in E
     int ctas;                // 1: one CTA per tile; 2: CTA pairs (tcgen05 cta_group::2) over 256 frames
+    int dbg;                 // measurement only (option proj_dbg): 1 = the epilogue skips its arithmetic (results are garbage)
 };
 
 constexpr uint32_t kPStageTile = 32 * 32 * 4;    // one warp's 32 frames x 32 columns on their way to the logits tensor
@@ -204,6 +205,9 @@ k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y, m0 = blockIdx.x * kPM;
 
+    // the metadata kernel behind this one in the stream is its programmatic dependent: it needs nothing from here and
+    // runs in this kernel's shadow (its small CTAs fit beside a resident projection CTA)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // operator parameter layer, frame count: lengths truncated and clamped (as k_emit does)
     int Tb = p.T;
     if (p.data_len) {
@@ -360,6 +364,7 @@ k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kPN + hsel * HC);
             const int cbase = n * kPN + hsel * HC;
             uint32_t v[2][32];
+            if (a.dbg & 1) { tc_fence_before(); if (CTAS == 2) mbar_arrive_leader(tempty + as); else mbar_arrive(tempty + as); continue; }
             if (cbase < p.V) tmem_ld32(trow, v[0]);
 #pragma unroll
             for (int c = 0; c < HC / 32; ++c) {
@@ -386,7 +391,7 @@ k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             x[i] = in ? __uint_as_float(v[c & 1][i]) + (a.bias ? __ldg(a.bias + col0 + i) : 0.0f) : -INFINITY;
                         }
                     }
-                    if (a.store == 1) {
+                    if (a.store == 1 && !(a.dbg & 2)) {
                         // 32 frames x 32 columns through a swizzled staging tile: row = lane, 16-byte chunk i at (i ^ row % 8)
                         const uint32_t tile = sbuf + (uint32_t)(nstored & 1) * kPStageTile;
                         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that read this tile two chunks ago
@@ -396,7 +401,7 @@ k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
                                          ::"r"(tile + (uint32_t)lane * 128u + (uint32_t)((i ^ (lane & 7)) << 4)),
                                            "f"(x[4 * i]), "f"(x[4 * i + 1]), "f"(x[4 * i + 2]), "f"(x[4 * i + 3]) : "memory");
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        if (!(a.dbg & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         __syncwarp();
                         if (lane == 0) tma_store_3d(&tmC, tile, col0, m0 + q * 32, b);
                         ++nstored;
@@ -433,7 +438,7 @@ k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 tmem_ld_wait();
                 const float xv = __uint_as_float(raw1) + (a.bias ? __ldg(a.bias + vj) : 0.0f);
                 if (a.smem_stash) stash[j * kPM + r] = xv;
-                else if (eblock) ecol[(size_t)j * kEC] = valid ? (double)xv : 0.0;
+                else if (eblock && !(a.dbg & 4)) ecol[(size_t)j * kEC] = valid ? (double)xv : 0.0;
             }
             tc_fence_before();
             if (CTAS == 2) mbar_arrive_leader(tempty + as); else mbar_arrive(tempty + as);
@@ -461,7 +466,7 @@ k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
                 if (floored && p.status) atomicOr(p.status + b, UTT_WIDE_LOGITS);
             }
-        } else if (eblock && valid) {
+        } else if (eblock && valid && !(a.dbg & 4)) {
             bool floored = false;
             const int k1 = hstart[(hsel + 1) * a.NT];
             for (int k0 = hstart[hsel * a.NT]; k0 < k1; k0 += 8) {          // eight independent round trips to L2 at a time

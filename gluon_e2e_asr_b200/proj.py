@@ -45,9 +45,21 @@ def _check_inputs(hidden, weight, bias):
         raise ValueError("bias must be (V,)")
 
 
+class _tf32_matmul:
+    """Library GEMMs of the training path at the precision of the fused product (tf32 in, fp32 accumulate)."""
+
+    def __enter__(self):
+        self.old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.old
+        return False
+
+
 class _ProjCtcLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, hidden, weight, bias, label, pred_lengths, label_lengths, blank_last, tn):
+    def forward(ctx, hidden, weight, bias, label, pred_lengths, label_lengths, blank_last, tn, fused=True):
         _check_inputs(hidden, weight, bias)
         if hidden.stride(2) != 1:
             hidden = hidden.contiguous()
@@ -58,7 +70,11 @@ class _ProjCtcLossFn(torch.autograd.Function):
         dev = hidden.device
         need = any(ctx.needs_input_grad[:3])
         # the logits buffer exists only when a gradient will be asked for (NTC, like the model's output)
-        logits = torch.empty((B, T, V), dtype=torch.float32, device=dev) if need else None
+        if need and not fused:
+            with _tf32_matmul():      # the library product, written once: what the gradient kernel reads
+                logits = torch.nn.functional.linear(hidden, weight, bias)
+        else:
+            logits = torch.empty((B, T, V), dtype=torch.float32, device=dev) if need else None
         shape_only = logits if logits is not None else torch.empty((B, T, V), dtype=torch.float32, device="meta")
         call = _Call(_MetaLogits(shape_only, dev), label, pred_lengths, label_lengths, blank_last, True, tn)
         loss = torch.empty((B,), dtype=torch.float32, device=dev)
@@ -68,8 +84,11 @@ class _ProjCtcLossFn(torch.autograd.Function):
             p.logits = None
         pj = _proj_struct(hidden, weight, bias)
         with _on_device(dev):
-            rc = _lib.load().ctcb_proj_forward(ctypes.byref(pj), ctypes.byref(p), 1 if need else 0, ws.data_ptr(), ws.numel(),
-                                               _stream_ptr(dev))
+            if need and not fused:
+                rc = _lib.load().ctcb_forward(ctypes.byref(p), 1, ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+            else:
+                rc = _lib.load().ctcb_proj_forward(ctypes.byref(pj), ctypes.byref(p), 1 if need else 0, ws.data_ptr(), ws.numel(),
+                                                   _stream_ptr(dev))
         _lib.check(rc)
         ctx.call, ctx.ws, ctx.logits = call, (ws if need else None), logits
         ctx.save_for_backward(hidden, weight)
@@ -90,13 +109,14 @@ class _ProjCtcLossFn(torch.autograd.Function):
         ctx.ws = ctx.logits = None
         G2 = G.view(-1, G.shape[2])
         dh = dw = db = None
-        if ctx.needs_input_grad[0]:
-            dh = (G2 @ weight).view(hidden.shape)
-        if ctx.needs_input_grad[1]:
-            dw = G2.t() @ hidden.reshape(-1, hidden.shape[2])
+        with _tf32_matmul():
+            if ctx.needs_input_grad[0]:
+                dh = (G2 @ weight).view(hidden.shape)
+            if ctx.needs_input_grad[1]:
+                dw = G2.t() @ hidden.reshape(-1, hidden.shape[2])
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = G2.sum(0)
-        return dh, dw, db, None, None, None, None, None
+        return dh, dw, db, None, None, None, None, None, None
 
 
 class _MetaLogits:
@@ -114,13 +134,20 @@ class _MetaLogits:
 
 
 def proj_ctc_loss(hidden, weight, bias, label, pred_lengths=None, label_lengths=None, blank_label="first",
-                  label_layout="NT"):
+                  label_layout="NT", fused_training=False):
     """Per-utterance CTC loss (B,) of ``hidden (B,T,K) @ weight (V,K).T + bias`` -- model.py:424 + loss.py:121-139.
 
     tf32 tensor-core product (hidden and weight are read as they are; the low 13 mantissa bits do not take part),
-    fp32 accumulation; everything after the product as in ``CtcLoss``."""
+    fp32 accumulation; everything after the product as in ``CtcLoss``.
+
+    Without a gradient (validation, train_ctc_ce.py:143) the fused kernel runs and the logits never exist in HBM.
+    With a gradient the logits have to exist for the gradient kernel; measured on B200 (scripts/proj_bench.py, cfg3
+    shape, H = 512) a 2-SM 256x256 library GEMM writes them faster than the fused epilogue does (forward with logits
+    kept: 211 us against 251), so by default the training call is the library product followed by ``CtcLoss``;
+    ``fused_training=True`` forces the fused kernel (``ctcb_proj_forward`` with a logits buffer)."""
+    needs_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (hidden, weight, bias))
     return _ProjCtcLossFn.apply(hidden, weight, bias, label, pred_lengths, label_lengths, _blank_last(blank_label),
-                                label_layout == "TN")
+                                label_layout == "TN", (not needs_grad) or bool(fused_training))
 
 
 class ProjCtcLoss(torch.nn.Module):
@@ -133,6 +160,6 @@ class ProjCtcLoss(torch.nn.Module):
         torch.nn.init.uniform_(self.weight, -0.07, 0.07)
         self.blank_label, self.label_layout = blank_label, label_layout
 
-    def forward(self, hidden, label, pred_lengths=None, label_lengths=None):
+    def forward(self, hidden, label, pred_lengths=None, label_lengths=None, fused_training=False):
         return proj_ctc_loss(hidden, self.weight, self.bias, label, pred_lengths, label_lengths, self.blank_label,
-                             self.label_layout)
+                             self.label_layout, fused_training)

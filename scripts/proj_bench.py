@@ -76,6 +76,12 @@ def main():
         s = sets[i % a.sets]
         h, w, b = s["h"].requires_grad_(True), s["w"].requires_grad_(True), s["bias"].requires_grad_(True)
         h.grad = w.grad = b.grad = None
+        proj_ctc_loss(h, w, b, s["lab"], s["pl"], s["ll"], fused_training=True).mean().backward()
+
+    def plugin_step(i):
+        s = sets[i % a.sets]
+        h, w, b = s["h"].requires_grad_(True), s["w"].requires_grad_(True), s["bias"].requires_grad_(True)
+        h.grad = w.grad = b.grad = None
         proj_ctc_loss(h, w, b, s["lab"], s["pl"], s["ll"]).mean().backward()
 
     def unfused_step(i):
@@ -89,7 +95,7 @@ def main():
     def fused_fwd_keep(i):
         s = sets[i % a.sets]
         h = s["h"].requires_grad_(True)
-        return proj_ctc_loss(h, s["w"], s["bias"], s["lab"], s["pl"], s["ll"])
+        return proj_ctc_loss(h, s["w"], s["bias"], s["lab"], s["pl"], s["ll"], fused_training=True)
 
     def unfused_fwd_keep(i):
         s = sets[i % a.sets]
@@ -108,7 +114,7 @@ def main():
     for name, fn in (("gemm_only_tf32_cublas", gemm_only), ("fused_forward", fused_fwd), ("unfused_forward", unfused_fwd),
                      ("fused_forward_keep_logits", fused_fwd_keep), ("unfused_forward_keep", unfused_fwd_keep),
                      ("backward_gemms_tf32_cublas", backward_gemms),
-                     ("fused_step", fused_step), ("unfused_step", unfused_step)):
+                     ("fused_step", fused_step), ("plugin_default_step", plugin_step), ("unfused_step", unfused_step)):
         res[name + "_us"] = round(timed(fn, a.iters), 1)
     flops = 2.0 * a.B * a.T * a.H * a.V
     res["gemm_tflops_cublas"] = round(flops / res["gemm_only_tf32_cublas_us"] / 1e6, 1)
