@@ -688,6 +688,7 @@ def run_cuda(args, rank, world, local_rank):
 
     # ---- other workloads, same run (N=1 only): context numbers, not the headline ----------
     others = []
+    next_rows = None
     if world == 1 and not args.no_others:
         for oname in ("cfg1", "cfg2", "cfg3", "cfg4", "cfg5"):
             if oname == name:
@@ -696,6 +697,10 @@ def run_cuda(args, rank, world, local_rank):
                 others.append(measure_other(torch, ops, dev, oname, peak))
             except Exception as exc:  # noqa: BLE001
                 others.append({"workload": oname, "error": str(exc)[:200]})
+        try:
+            next_rows = {"proj_ctc_forward": measure_proj(torch, dev)}
+        except Exception as exc:  # noqa: BLE001
+            next_rows = {"proj_ctc_forward": {"error": str(exc)[:200]}}
         c5 = next((o for o in others if o.get("workload") == "cfg5" and "value" in o), None)
         if c5:
             sweep = {"workload": "cfg5: one B=1024 batch (the sharded sweep of BASELINE configs[4]), whole batch on this GPU",
@@ -745,6 +750,8 @@ def run_cuda(args, rank, world, local_rank):
             line["cpu_baseline"] = cpu_baseline
         if others:
             line["other_workloads"] = others
+        if next_rows:
+            line["next_rows"] = next_rows
         print(json.dumps(line), flush=True)
     if world > 1:
         # The captured graphs hold NCCL work: tearing the communicator down under them can block, and a
@@ -791,6 +798,60 @@ def measure_other(torch, ops, dev, oname, peak, steps=20, warmup=3):
     return {"workload": oname, "B": B, "T": T, "V": V, "Lmax": L, "ms_per_step": ms / steps,
             "value": frames / (ms * 1e-3), "unit": UNIT, "step_achieved_gbs": alg / (ms * 1e-3) / 1e9,
             "step_frac": alg / (ms * 1e-3) / 1e9 / peak, "launch": "eager"}
+
+
+def measure_proj(torch, dev, B=64, T=500, V=2000, L=150, H=512, steps=20, warmup=3):
+    """SURVEY 8f rank 1 (context, not the headline): the output projection fused with the loss's forward
+    (ctcb_proj_forward: tcgen05 tf32 GEMM whose epilogue feeds the lattice recursion, logits never stored) against the pair
+    it replaces -- a library tf32 GEMM that writes the logits + ctcb_forward that reads them -- at BASELINE configs[2]'s
+    shape with H hidden units.  Device-resident inputs, two buffer sets, CUDA events."""
+    from gluon_e2e_asr_b200 import proj_ctc_loss
+    from gluon_e2e_asr_b200.ops import ctc_loss
+    sets = []
+    for i in range(2):
+        d = make_batch(B, T, V, L, seed=i)
+        g = torch.Generator(device="cpu").manual_seed(i)
+        sets.append((torch.randn((B, T, H), generator=g).to(dev), (torch.randn((V, H), generator=g) / H ** 0.5).to(dev),
+                     torch.zeros((V,), device=dev), torch.tensor(d["label"], device=dev), torch.tensor(d["pred_lengths"], device=dev),
+                     torch.tensor(d["label_lengths"], device=dev), float(d["pred_lengths"].sum())))
+    old_tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+
+    def fused(s):
+        with torch.no_grad():
+            return proj_ctc_loss(s[0], s[1], s[2], s[3], s[4], s[5])
+
+    def unfused(s):
+        with torch.no_grad():
+            logits = torch.addmm(s[2], s[0].view(-1, H), s[1].t()).view(B, T, V)
+            return ctc_loss(logits.transpose(0, 1), s[3], s[4], s[5], True, True)
+
+    def gemm(s):
+        return torch.addmm(s[2], s[0].view(-1, H), s[1].t())
+
+    out = {"shape": {"B": B, "T": T, "V": V, "Lmax": L, "H": H}, "dtype": "tf32 product, fp32 accumulate, fp64 recursion"}
+    try:
+        for key, fn in (("fused_forward_us", fused), ("unfused_forward_us", unfused), ("library_gemm_us", gemm)):
+            for i in range(warmup):
+                fn(sets[i % 2])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                fn(sets[i % 2])
+            e1.record()
+            torch.cuda.synchronize()
+            out[key] = e0.elapsed_time(e1) / steps * 1e3
+        frames = 0.5 * (sets[0][6] + sets[1][6])
+        out["valid_frames_per_step"] = frames
+        out["fused_forward_frames_per_s"] = frames / out["fused_forward_us"] * 1e6
+        out["max_rel_loss_difference"] = float(((fused(sets[0]) - unfused(sets[0])).abs() / unfused(sets[0]).abs().clamp_min(1)).max())
+        out["projection_flops"] = 2.0 * B * T * H * V
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old_tf32
+    del sets
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
