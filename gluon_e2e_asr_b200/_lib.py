@@ -57,7 +57,7 @@ class Proj(ctypes.Structure):
     """ctcb_proj_t (include/ctcb.h): the output projection in front of the loss."""
     _fields_ = [
         ("hidden", ctypes.c_void_p), ("hidden_stride_t", ctypes.c_int64), ("hidden_stride_b", ctypes.c_int64),
-        ("K", ctypes.c_int32), ("weight", ctypes.c_void_p), ("bias", ctypes.c_void_p),
+        ("K", ctypes.c_int32), ("weight", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("operand_dtype", ctypes.c_int32),
     ]
 
 

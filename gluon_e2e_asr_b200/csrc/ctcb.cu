@@ -376,9 +376,13 @@ int launch_proj(const ctcb_proj_t* pj, const ctcb_problem_t* p, const ctcb::Prob
     if (lay.fused || lay.dense)
         return fail(CTCB_UNSUPPORTED, "projection fused with the loss needs V > 64 and V > Lmax + 1 (V=%d, Lmax=%d)", p->V, p->Lmax);
     if (p->logits_row_offsets) return fail(CTCB_UNSUPPORTED, "projection: packed logits are not supported");
-    if (pj->K % 4 || pj->hidden_stride_t % 4 || pj->hidden_stride_b % 4 || reinterpret_cast<uintptr_t>(pj->hidden) % 16 ||
+    if (pj->operand_dtype != CTCB_PROJ_F32 && pj->operand_dtype != CTCB_PROJ_BF16)
+        return fail(CTCB_INVALID_VALUE, "projection: operand_dtype %d is neither CTCB_PROJ_F32 nor CTCB_PROJ_BF16", pj->operand_dtype);
+    const bool bf = pj->operand_dtype == CTCB_PROJ_BF16;
+    const int esz = bf ? 2 : 4, per16 = 16 / esz;
+    if (pj->K % per16 || pj->hidden_stride_t % per16 || pj->hidden_stride_b % per16 || reinterpret_cast<uintptr_t>(pj->hidden) % 16 ||
         reinterpret_cast<uintptr_t>(pj->weight) % 16)
-        return fail(CTCB_INVALID_VALUE, "projection: K and the hidden strides must be multiples of 4 elements, bases 16-byte aligned");
+        return fail(CTCB_INVALID_VALUE, "projection: K and the hidden strides must be multiples of 16 bytes, bases 16-byte aligned");
     if (!is_device_ptr(pj->hidden) || !is_device_ptr(pj->weight) || !is_device_ptr(pj->bias))
         return fail(CTCB_INVALID_VALUE, "projection: hidden / weight / bias must be CUDA device memory");
     // CTA pairs (tcgen05 cta_group::2: 256 frames per pair, each CTA stages half of the vocabulary tile) or single CTAs
@@ -390,27 +394,28 @@ int launch_proj(const ctcb_proj_t* pj, const ctcb_problem_t* p, const ctcb::Prob
     CUtensorMap tmA, tmB;
     {
         const cuuint64_t gdim[3] = {(cuuint64_t)pj->K, (cuuint64_t)p->T, (cuuint64_t)p->B};
-        const cuuint64_t gstr[2] = {(cuuint64_t)pj->hidden_stride_t * 4, (cuuint64_t)pj->hidden_stride_b * 4};
-        const cuuint32_t box[3] = {(cuuint32_t)ctcb::kPK, (cuuint32_t)ctcb::kPM, 1};
+        const cuuint64_t gstr[2] = {(cuuint64_t)pj->hidden_stride_t * esz, (cuuint64_t)pj->hidden_stride_b * esz};
+        const cuuint32_t box[3] = {(cuuint32_t)(128 / esz), (cuuint32_t)ctcb::kPM, 1};
         const cuuint32_t est[3] = {1, 1, 1};
-        const CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(pj->hidden), gdim, gstr, box, est,
+        const CUresult r = enc(&tmA, bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(pj->hidden), gdim, gstr, box, est,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(CTCB_INVALID_VALUE, "cuTensorMapEncodeTiled(hidden) failed: %d", (int)r);
     }
     {
         const cuuint64_t gdim[2] = {(cuuint64_t)pj->K, (cuuint64_t)p->V};
-        const cuuint64_t gstr[1] = {(cuuint64_t)pj->K * 4};
-        const cuuint32_t box[2] = {(cuuint32_t)ctcb::kPK, (cuuint32_t)(ctcb::kPN / ctas)};
+        const cuuint64_t gstr[1] = {(cuuint64_t)pj->K * esz};
+        const cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)(ctcb::kPN / ctas)};
         const cuuint32_t est[2] = {1, 1};
-        const CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(pj->weight), gdim, gstr, box, est,
+        const CUresult r = enc(&tmB, bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(pj->weight), gdim, gstr, box, est,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(CTCB_INVALID_VALUE, "cuTensorMapEncodeTiled(weight) failed: %d", (int)r);
     }
     ctcb::ProjArgs pa{};
     pa.p = dp; pa.w = w; pa.bias = pj->bias; pa.logits = const_cast<float*>(p->logits);
-    pa.K = pj->K; pa.NT = (p->V + ctcb::kPN - 1) / ctcb::kPN; pa.KB = (pj->K + ctcb::kPK - 1) / ctcb::kPK;
+    pa.K = pj->K; pa.NT = (p->V + ctcb::kPN - 1) / ctcb::kPN; pa.KB = (pj->K + 128 / esz - 1) / (128 / esz);
+    pa.bf16 = bf ? 1 : 0;
     pa.ctas = ctas;
     pa.dbg = opt(OPT_PROJ_DBG) > 0 ? opt(OPT_PROJ_DBG) : 0;
     pa.vec4 = (p->V % 4 == 0 && reinterpret_cast<uintptr_t>(pj->bias) % 16 == 0) ? 1 : 0;

@@ -61,6 +61,7 @@ struct ProjArgs {
     int store;               // 0: logits not stored; 1: TMA store through the staging tiles; 2: direct scalar stores
     int smem_stash;          // the label columns are parked in shared memory (store == 0 and they fit), else in E
     int ctas;                // 1: one CTA per tile; 2: CTA pairs (tcgen05 cta_group::2) over 256 frames
+    int bf16;                // operands are bfloat16 (64 values per 128-byte K block, kind::f16) instead of fp32 (32, kind::tf32)
     int dbg;                 // measurement only (option proj_dbg): 1 = the epilogue skips its arithmetic (results are garbage)
 };
 
@@ -158,6 +159,21 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
+// the same two with bfloat16 operands (kind::f16: 16 values = 32 bytes of K per instruction, twice the rate)
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // arrives on the mbarrier when every tcgen05.mma issued so far by this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -191,10 +207,13 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // bit 17, M >> 4 at bit 24
 constexpr uint32_t kPIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kPN >> 3) << 17) | ((uint32_t)(kPM >> 4) << 24);
 constexpr uint32_t kPIdescPair = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kPN >> 3) << 17) | ((uint32_t)((2 * kPM) >> 4) << 24);
+// bfloat16 operands: format 1 at bits 7 and 10
+constexpr uint32_t kPIdescBf = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kPN >> 3) << 17) | ((uint32_t)(kPM >> 4) << 24);
+constexpr uint32_t kPIdescBfPair = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kPN >> 3) << 17) | ((uint32_t)((2 * kPM) >> 4) << 24);
 
 __device__ __forceinline__ void bar_sync_epilogue() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kPEpiWarps) : "memory"); }
 
-template <int CTAS>
+template <int CTAS, bool BF16>
 __global__ void __launch_bounds__(kPThreads, 1)
 k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
             ProjArgs a) {
@@ -257,6 +276,7 @@ k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // ===== TMA producer =====
         if (lane == 0) {
             int st = 0; uint32_t ph = 0;
+            constexpr int kelems = BF16 ? 2 * kPK : kPK;        // values per 128-byte K block
             for (int n = 0; n < a.NT; ++n)
                 for (int kb = 0; kb < a.KB; ++kb) {
                     mbar_wait(empty + st, ph ^ 1u);
@@ -265,12 +285,12 @@ k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         // half of the vocabulary tile
                         if (rank == 0) mbar_expect_tx(full + st, 2 * (kPBytesA + kBytesB));
                         const uint32_t lbar = smem_u32(full + st) & kPairRankMask;
-                        tma_load_3d_pair(sA + st * kPBytesA, &tmA, lbar, kb * kPK, m0, b);
-                        tma_load_2d_pair(sB + st * kBytesB, &tmB, lbar, kb * kPK, n * kPN + (int)rank * (kPN / 2));
+                        tma_load_3d_pair(sA + st * kPBytesA, &tmA, lbar, kb * kelems, m0, b);
+                        tma_load_2d_pair(sB + st * kBytesB, &tmB, lbar, kb * kelems, n * kPN + (int)rank * (kPN / 2));
                     } else {
                         mbar_expect_tx(full + st, kPBytesA + kBytesB);
-                        tma_load_3d(sA + st * kPBytesA, &tmA, smem_u32(full + st), kb * kPK, m0, b);
-                        tma_load_2d(sB + st * kBytesB, &tmB, smem_u32(full + st), kb * kPK, n * kPN);
+                        tma_load_3d(sA + st * kPBytesA, &tmA, smem_u32(full + st), kb * kelems, m0, b);
+                        tma_load_2d(sB + st * kBytesB, &tmB, smem_u32(full + st), kb * kelems, n * kPN);
                     }
                     if (++st == kPStages) { st = 0; ph ^= 1u; }
                 }
@@ -289,9 +309,11 @@ k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     tc_fence_after();
                     const uint32_t a0 = sA + st * kPBytesA, b0 = sB + st * kBytesB;
 #pragma unroll
-                    for (int k = 0; k < kPK / 8; ++k) {                        // 8 tf32 values = 32 bytes per instruction
-                        if (CTAS == 2) umma_tf32_pair(dcol, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), kPIdescPair, (uint32_t)((kb | k) != 0));
-                        else umma_tf32(dcol, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), kPIdesc, (uint32_t)((kb | k) != 0));
+                    for (int k = 0; k < kPK / 8; ++k) {                        // 32 bytes of K per instruction: 8 tf32 or 16 bf16 values
+                        const uint64_t da = umma_desc_sw128(a0 + k * 32), db = umma_desc_sw128(b0 + k * 32);
+                        const uint32_t acc = (uint32_t)((kb | k) != 0);
+                        if (BF16) { if (CTAS == 2) umma_bf16_pair(dcol, da, db, kPIdescBfPair, acc); else umma_bf16(dcol, da, db, kPIdescBf, acc); }
+                        else { if (CTAS == 2) umma_tf32_pair(dcol, da, db, kPIdescPair, acc); else umma_tf32(dcol, da, db, kPIdesc, acc); }
                     }
                     // the stage is free (in both CTAs) once these MMAs have read it
                     if (CTAS == 2) umma_commit_pair(smem_u32(empty + st)); else umma_commit(smem_u32(empty + st));

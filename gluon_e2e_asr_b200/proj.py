@@ -30,6 +30,7 @@ def _proj_struct(hidden, weight, bias):
     pj.K = hidden.shape[2]
     pj.weight = weight.data_ptr()
     pj.bias = bias.data_ptr() if bias is not None else None
+    pj.operand_dtype = 1 if hidden.dtype == torch.bfloat16 else 0
     return pj
 
 
@@ -37,8 +38,11 @@ def _check_inputs(hidden, weight, bias):
     for name, t in (("hidden", hidden), ("weight", weight)) + ((("bias", bias),) if bias is not None else ()):
         if not isinstance(t, torch.Tensor) or not t.is_cuda:
             raise RuntimeError("proj_ctc_loss has no CPU path: %s must be a CUDA tensor" % name)
-        if t.dtype != torch.float32:
-            raise TypeError("%s must be float32 (the reference's Dense dtype), got %s" % (name, t.dtype))
+    if hidden.dtype not in (torch.float32, torch.bfloat16) or weight.dtype != hidden.dtype:
+        raise TypeError("hidden and weight must both be float32 (the reference's Dense dtype) or both bfloat16, got %s / %s"
+                        % (hidden.dtype, weight.dtype))
+    if bias is not None and bias.dtype != torch.float32:
+        raise TypeError("bias must be float32, got %s" % bias.dtype)
     if hidden.dim() != 3 or weight.dim() != 2 or weight.shape[1] != hidden.shape[2]:
         raise ValueError("hidden must be (B, T, K) and weight (V, K)")
     if bias is not None and (bias.dim() != 1 or bias.shape[0] != weight.shape[0]):
@@ -70,6 +74,8 @@ class _ProjCtcLossFn(torch.autograd.Function):
         dev = hidden.device
         need = any(ctx.needs_input_grad[:3])
         # the logits buffer exists only when a gradient will be asked for (NTC, like the model's output)
+        if hidden.dtype == torch.bfloat16:
+            fused = True              # no library GEMM gives fp32 logits from bfloat16 operands without a rounding in between
         if need and not fused:
             with _tf32_matmul():      # the library product, written once: what the gradient kernel reads
                 logits = torch.nn.functional.linear(hidden, weight, bias)
@@ -111,9 +117,9 @@ class _ProjCtcLossFn(torch.autograd.Function):
         dh = dw = db = None
         with _tf32_matmul():
             if ctx.needs_input_grad[0]:
-                dh = (G2 @ weight).view(hidden.shape)
+                dh = (G2 @ weight.float()).view(hidden.shape).to(hidden.dtype)
             if ctx.needs_input_grad[1]:
-                dw = G2.t() @ hidden.reshape(-1, hidden.shape[2])
+                dw = (G2.t() @ hidden.reshape(-1, hidden.shape[2]).float()).to(weight.dtype)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = G2.sum(0)
         return dh, dw, db, None, None, None, None, None, None

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CTCB_VERSION 102 /* 0.1.2: ctcb_proj_forward, ctcb_proj_loss_grad */
+#define CTCB_VERSION 103 /* 0.1.3: ctcb_proj_forward, ctcb_proj_loss_grad (fp32 / bf16 operands) */
 
 typedef enum {
     CTCB_OK = 0,
@@ -269,14 +269,19 @@ int ctcb_get_option(const char* name, int32_t* value);
  * logits[b,t,:] = hidden[b,t,:] . weight^T + bias is formed on the tensor cores (tcgen05, tf32 inputs read straight
  * from the fp32 tensors, fp32 accumulation in tensor memory) and reduced to what the lattice recursion reads -- row
  * maximum, softmax normaliser, the utterance's own label columns -- before it leaves the SM (csrc/ctcb_proj.cuh).
- * All pointers are device pointers.  hidden: (B, T, K) in any T/B strides (elements, multiples of 4), unit stride along
- * K; weight: (V, K) row-major, gluon's Dense layout (units, in_units); K a multiple of 4; 16-byte aligned bases. */
+ * All pointers are device pointers.  hidden: (B, T, K) in any T/B strides (elements), unit stride along K; weight: (V, K)
+ * row-major, gluon's Dense layout (units, in_units); strides and K multiples of 16 bytes, 16-byte aligned bases.
+ * operand_dtype CTCB_PROJ_F32: fp32 tensors, tf32 product; CTCB_PROJ_BF16: bfloat16 tensors (mixed-precision encoders),
+ * exact products at twice the tensor rate.  Accumulation, bias, logits and everything behind them are fp32 either way. */
+#define CTCB_PROJ_F32 0
+#define CTCB_PROJ_BF16 1
 typedef struct ctcb_proj {
-    const float* hidden;
+    const void* hidden;
     int64_t hidden_stride_t, hidden_stride_b;
     int32_t K;
-    const float* weight;
-    const float* bias;              /* (V,) or NULL (Dense(use_bias=False)) */
+    const void* weight;
+    const float* bias;              /* (V,) fp32 or NULL (Dense(use_bias=False)) */
+    int32_t operand_dtype;          /* CTCB_PROJ_F32 / CTCB_PROJ_BF16: element type of hidden and weight */
 } ctcb_proj_t;
 
 /* Loss of one batch from the encoder output.  p->logits is an OUTPUT here: NULL = the logits are never stored (the

@@ -109,9 +109,23 @@ def main():
         return (G2 @ s["w"]), (G2.t() @ s["h"].view(-1, a.H)), G2.sum(0)
 
     gbuf = torch.randn((a.B, a.T, a.V), device=dev)
+    def fused_fwd_bf16(i):
+        s = sets[i % a.sets]
+        with torch.no_grad():
+            return proj_ctc_loss(s["hb"], s["wb"], s["bias"], s["lab"], s["pl"], s["ll"])
+
+    def unfused_fwd_bf16(i):      # library bf16 GEMM (bf16 logits, widened) + the logits path
+        s = sets[i % a.sets]
+        with torch.no_grad():
+            logits = (s["hb"].view(-1, a.H) @ s["wb"].t()).float().add_(s["bias"]).view(a.B, a.T, a.V)
+            return ctc_loss(logits.transpose(0, 1), s["lab"], s["pl"], s["ll"], True, True)
+
+    for s_ in sets:
+        s_["hb"], s_["wb"] = s_["h"].bfloat16(), s_["w"].bfloat16()
     lf, lu = fused_fwd(0), unfused_fwd(0)
     res["max_rel_loss_difference_fused_vs_unfused"] = float(((lf - lu).abs() / lu.abs().clamp_min(1)).max())
     for name, fn in (("gemm_only_tf32_cublas", gemm_only), ("fused_forward", fused_fwd), ("unfused_forward", unfused_fwd),
+                     ("fused_forward_bf16", fused_fwd_bf16), ("unfused_forward_bf16", unfused_fwd_bf16),
                      ("fused_forward_keep_logits", fused_fwd_keep), ("unfused_forward_keep", unfused_fwd_keep),
                      ("backward_gemms_tf32_cublas", backward_gemms),
                      ("fused_step", fused_step), ("plugin_default_step", plugin_step), ("unfused_step", unfused_step)):

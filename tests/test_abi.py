@@ -40,7 +40,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 def test_version_and_error_string(lib):
     l = lib.load()
-    assert l.ctcb_version() == 102
+    assert l.ctcb_version() == 103
     assert isinstance(l.ctcb_last_error(), bytes)
 
 

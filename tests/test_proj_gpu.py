@@ -190,6 +190,35 @@ def test_arbitrary_fp32_inputs_cost_the_tf32_rounding(dev):
     np.testing.assert_allclose(loss, lo, rtol=5e-3)
 
 
+@pytest.mark.parametrize("K", [128, 96])
+def test_bfloat16_operands(dev, K):
+    """CTCB_PROJ_BF16: bfloat16 hidden / weight (a mixed-precision encoder), fp32 accumulation and logits.  The products of
+    bfloat16 values are exact in fp32, so the loss meets the logits path's bar against the oracle of the fp64 product of
+    the SAME bfloat16 values; K = 96 leaves half a K block to the hardware's zero fill."""
+    from gluon_e2e_asr_b200 import proj_ctc_loss
+    B, T, V, L = 3, 200, 600, 25
+    d, h, w, bv = _problem(B, T, K, V, L, seed=21, exact=False)
+    th, tw = torch.tensor(h, device=dev).bfloat16(), torch.tensor(w, device=dev).bfloat16()
+    hb, wb = th.float().cpu().numpy(), tw.float().cpu().numpy()
+    head = np.array([1.0, 0.5, 2.0])
+    _, lo, G, dh, dw, db = _oracle(d, hb, wb, bv, head)
+    lab, pl, ll = (torch.tensor(d[k], device=dev) for k in ("label", "pred_lengths", "label_lengths"))
+    tb = torch.tensor(bv, device=dev)
+    with torch.no_grad():
+        loss = proj_ctc_loss(th, tw, tb, lab, pl, ll)
+    np.testing.assert_allclose(loss.cpu().numpy(), lo, rtol=RTOL, atol=ATOL)
+    th.requires_grad_(True); tw.requires_grad_(True); tb.requires_grad_(True)
+    loss2 = proj_ctc_loss(th, tw, tb, lab, pl, ll)
+    (loss2 * torch.tensor(head, device=dev, dtype=torch.float32)).sum().backward()
+    np.testing.assert_allclose(loss2.detach().cpu().numpy(), lo, rtol=RTOL, atol=ATOL)
+    assert th.grad.dtype == torch.bfloat16 and tw.grad.dtype == torch.bfloat16
+    # gradients come back in the operands' dtype: bfloat16's 2^-9 on top of the tf32 contractions
+    for got, want, what in ((th.grad, dh, "d hidden"), (tw.grad, dw, "d weight")):
+        err, scale = np.abs(got.float().cpu().numpy() - want).max(), np.abs(want).max()
+        assert err <= 1e-2 * scale, "%s: %.3e against %.3e" % (what, err, scale)
+    np.testing.assert_allclose(tb.grad.cpu().numpy(), db, rtol=2e-3, atol=2e-4)
+
+
 def test_cfg3_shape_and_unsupported_shapes(dev):
     """BASELINE configs[2]'s vocabulary and label row (V=2000, L<=150, T=500) with H=512, at a batch the oracle does in
     seconds; small vocabularies are refused (CTCB_UNSUPPORTED), CPU tensors raise."""
