@@ -190,6 +190,39 @@ def test_arbitrary_fp32_inputs_cost_the_tf32_rounding(dev):
     np.testing.assert_allclose(loss, lo, rtol=5e-3)
 
 
+@pytest.mark.parametrize("blank_label", ["first", "last"])
+def test_inferred_lengths_and_blank_last(dev, blank_label):
+    """No length vectors (use_*_lengths=False in the reference's operator): every utterance has T frames and its labels end
+    at the first padding value (0 for blank 'first', -1 for 'last'); blank 'last' puts the blank in the LAST vocabulary
+    tile's partial half -- the epilogue infers L itself (it runs before the metadata kernel's result exists)."""
+    from gluon_e2e_asr_b200 import proj_ctc_loss
+    from oracle import ctc_oracle as O
+    B, T, K, V, L = 4, 170, 64, 300, 18
+    blank = 0 if blank_label == "first" else V - 1
+    d = make_batch(B, T, V, L, seed=31, blank=blank)
+    rng = np.random.Generator(np.random.PCG64(32))
+    h = _tf32(rng.standard_normal((B, T, K)).astype(np.float32))
+    w = _tf32((rng.standard_normal((V, K)) / np.sqrt(K)).astype(np.float32))
+    logits = h.astype(np.float64) @ w.astype(np.float64).T
+    lo, _, ok = O.CtcLossOracle("NTC", "NT", blank_label)(logits, d["label"], None, None)
+    assert ok.all()
+    with torch.no_grad():
+        loss = proj_ctc_loss(torch.tensor(h, device=dev), torch.tensor(w, device=dev), None,
+                             torch.tensor(d["label"], device=dev), None, None, blank_label=blank_label)
+    np.testing.assert_allclose(loss.cpu().numpy(), lo, rtol=RTOL, atol=ATOL)
+
+
+def test_long_label_rows_park_in_the_emission_table(dev):
+    """Label rows whose parked columns do not fit shared memory (here 321 columns x 128 frames x 4 B = 164 KB): the
+    columns are parked in the emission table itself even though no logits are stored."""
+    B, T, K, V, L = 2, 700, 32, 600, 320
+    d, h, w, bv = _problem(B, T, K, V, L, seed=41, full_lengths=True)
+    head = np.ones(B)
+    _, lo, _, _, _, _ = _oracle(d, h, w, bv, head)
+    loss = _run(dev, d, h, w, bv, head, need_grad=False)
+    np.testing.assert_allclose(loss, lo, rtol=RTOL, atol=ATOL)
+
+
 @pytest.mark.parametrize("K", [128, 96])
 def test_bfloat16_operands(dev, K):
     """CTCB_PROJ_BF16: bfloat16 hidden / weight (a mixed-precision encoder), fp32 accumulation and logits.  The products of
