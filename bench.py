@@ -598,7 +598,8 @@ def run_cuda(args, rank, world, local_rank):
         def pipe_run(k, record=False):
             acc, pending = 0.0, []
             for i in range(k):
-                sum_bufs[i % npb].zero_()
+                if world > 1:
+                    sum_bufs[i % npb].zero_()
                 _lib.check(lib.ctcb_pipe_submit(ph, ctypes.byref(pprobs[i % npb]), ctypes.byref(tk)))
                 if record:
                     _lib.check(lib.ctcb_pipe_last_h2d_bytes(ph, ctypes.byref(hb), ctypes.byref(pulled)))
@@ -862,7 +863,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(CONFIGS),
                     help="default: cfg2 on one GPU (BASELINE configs[1]); cfg5 split by utterance on N > 1 (configs[4])")
-    ap.add_argument("--pipe-depth", type=int, default=2, help="batches in flight in the prefetching host entry (e2e)")
+    ap.add_argument("--pipe-depth", type=int, default=3, help="batches in flight in the prefetching host entry (e2e)")
     ap.add_argument("--no-others", action="store_true", help="skip the context measurements of the other configs")
     ap.add_argument("--dense-host", action="store_true", help="e2e: dense (B,T,V) host batches instead of the packed arena")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
