@@ -60,9 +60,9 @@ thread_local int g_prof_count = 0;
 // Read from the environment ONCE (CTCB_<NAME>, at first use) and changeable through ctcb_set_option (tests, A/B
 // runs): nothing on the per-call host path calls getenv.  -1 = automatic.
 enum Opt { OPT_WALK_P, OPT_WALK_NW, OPT_WALK_STAGES, OPT_OVERLAP, OPT_FUSED, OPT_WALK_PER_SM, OPT_EMIT_STAGED,
-           OPT_GRAD_STAGED, OPT_MEET, OPT_GRAD2, OPT_GRAD2_BLOCKS, OPT_WALK_HW_WAIT, OPT_GRAD2_OCC, OPT_PROJ_CTAS, OPT_PROJ_DBG, OPT_COUNT };
+           OPT_GRAD_STAGED, OPT_MEET, OPT_GRAD2, OPT_GRAD2_BLOCKS, OPT_WALK_HW_WAIT, OPT_GRAD2_OCC, OPT_PROJ_CTAS, OPT_PROJ_DBG, OPT_PROJ_OVERLAP, OPT_COUNT };
 const char* const kOptNames[OPT_COUNT] = {"walk_p", "walk_nw", "walk_stages", "overlap", "fused", "walk_per_sm",
-                                          "emit_staged", "grad_staged", "meet", "grad2", "grad2_blocks", "walk_hw_wait", "grad2_occ", "proj_ctas", "proj_dbg"};
+                                          "emit_staged", "grad_staged", "meet", "grad2", "grad2_blocks", "walk_hw_wait", "grad2_occ", "proj_ctas", "proj_dbg", "proj_overlap"};
 struct Options {
     int v[OPT_COUNT];
     Options() {
@@ -180,7 +180,8 @@ cudaError_t ensure_dynamic_smem(const void* fn, size_t bytes) {
 }
 
 struct Layout {
-    size_t off_Tb, off_Lb, off_flags, off_lab, off_rank, off_dl, off_nd, off_fr, off_E, off_hA, off_hB, off_oA, off_oB, off_gprog, off_runv, off_pinfo, total;
+    size_t off_Tb, off_Lb, off_flags, off_lab, off_rank, off_dl, off_nd, off_fr, off_E, off_hA, off_hB, off_oA, off_oB, off_gprog, off_runv, off_pinfo, off_tflag, total;
+    int ntile;
     int Lp, W, NB, dense, fused, P, NW;
     int stamp;               // nonzero hash of everything the workspace layout depends on (Workspace::stamp)
     const WalkEntry* walk;
@@ -220,6 +221,8 @@ Layout make_layout(int T, int B, int V, int Lmax, int need_grad) {
     l.off_gprog = take(sizeof(int) * 4 * (size_t)B);
     l.off_runv = take(sizeof(int2) * 64 * (size_t)B);
     l.off_pinfo = take(sizeof(int2) * (size_t)B);
+    l.ntile = (T + 127) / 128 + 1;                // 128-frame tiles of the fused projection (+1: an odd count is paired up)
+    l.off_tflag = take(sizeof(int) * (size_t)B * l.ntile);
     l.off_fr = take(sizeof(float2) * (size_t)B * T);
     l.off_E = take(l.fused ? 0 : sizeof(double) * (size_t)B * l.NB * l.W * ctcb::kEC);
     if (need_grad) {
@@ -254,6 +257,7 @@ ctcb::Workspace carve(const Layout& l, void* ws) {
     w.gprog = reinterpret_cast<int*>(base + l.off_gprog);
     w.runv = reinterpret_cast<int2*>(base + l.off_runv);
     w.pinfo = reinterpret_cast<int2*>(base + l.off_pinfo);
+    w.tflag = reinterpret_cast<int*>(base + l.off_tflag); w.ntile = l.ntile;
     w.Lp = l.Lp; w.W = l.W; w.NB = l.NB; w.dense = l.dense; w.P = l.P; w.NW = l.NW;
     w.fused = l.fused;
     w.stamp = l.stamp;
@@ -378,8 +382,10 @@ EncodeTiledFn encode_tiled() {
 
 // the projection kernel (ctcb_proj.cuh) in k_emit's place: {row max, normaliser} and the emission table from the
 // encoder output, then the metadata CTAs of k_emit (one per utterance)
+// beside: the recursion kernel will be launched as the projection's programmatic dependent and follow its tiles (loss
+// evaluation only): the metadata kernel then goes FIRST (the walkers poll its "ready" word) and the projection starts beside it
 int launch_proj(const ctcb_proj_t* pj, const ctcb_problem_t* p, const ctcb::Problem& dp, const ctcb::Workspace& w,
-                const Layout& lay, cudaStream_t stream) {
+                const Layout& lay, cudaStream_t stream, bool beside) {
     if (!pj->hidden || !pj->weight || pj->K <= 0) return fail(CTCB_INVALID_VALUE, "projection: hidden / weight is NULL or K <= 0");
     if (lay.fused || lay.dense)
         return fail(CTCB_UNSUPPORTED, "projection fused with the loss needs V > 64 and V > Lmax + 1 (V=%d, Lmax=%d)", p->V, p->Lmax);
@@ -446,22 +452,33 @@ int launch_proj(const ctcb_proj_t* pj, const ctcb_problem_t* p, const ctcb::Prob
         }
     }
     const int mtiles = (p->T + ctcb::kPM - 1) / ctcb::kPM;
-    const dim3 pgrid(ctas == 2 ? (mtiles + 1) / 2 * 2 : mtiles, p->B);
-    CUDA_TRY(ctcb::launch_proj_emit(tmA, tmB, tmC, pa, pgrid, smem, stream));
-    mark(stream);
-    // per-utterance metadata: k_emit's extra CTA alone (grid.x = 1: every CTA is the metadata CTA), as the projection
-    // kernel's programmatic dependent -- it starts at once and runs beside it (it reads nothing the projection writes);
-    // the recursion kernel that follows is an ordinary launch and waits for both
-    {
+    const dim3 pgrid(ctas, p->B, (mtiles + ctas - 1) / ctas);
+    auto launch_meta = [&](bool programmatic) -> int {
+        // per-utterance metadata: k_emit's extra CTA alone (grid.x = 1: every CTA is the metadata CTA)
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(1, p->B); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = ctcb::emit_smem_bytes(lay.Lp, 0); cfg.stream = stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr; cfg.numAttrs = g_prof_events ? 0 : 1;
+        cfg.attrs = attr; cfg.numAttrs = programmatic ? 1 : 0;
         CUDA_TRY(cudaLaunchKernelEx(&cfg, ctcb::k_emit<1, 0>, dp, w));
+        mark(stream);
+        return CTCB_OK;
+    };
+    if (beside) {
+        // the tile flags and the metadata-ready words of this call start at zero (one memset: the regions are adjacent)
+        CUDA_TRY(cudaMemsetAsync(w.tflag, 0, sizeof(int) * (size_t)p->B * w.ntile, stream));
+        CUDA_TRY(cudaMemsetAsync(w.gprog, 0, sizeof(int) * 4 * (size_t)p->B, stream));
+        if (int rc = launch_meta(false)) return rc;
+        CUDA_TRY(ctcb::launch_proj_emit(tmA, tmB, tmC, pa, pgrid, smem, stream, true));    // programmatic: beside the metadata kernel
+        mark(stream);
+        return CTCB_OK;
     }
+    CUDA_TRY(ctcb::launch_proj_emit(tmA, tmB, tmC, pa, pgrid, smem, stream, false));
     mark(stream);
+    // the metadata kernel as the projection kernel's programmatic dependent -- it starts at once and runs beside it (it
+    // reads nothing the projection writes); the recursion kernel that follows is an ordinary launch and waits for both
+    if (int rc = launch_meta(!g_prof_events)) return rc;
     return CTCB_OK;
 }
 
@@ -573,8 +590,9 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
         // (With a gradient kernel in the call the exchange goes behind that one instead, see below.)
         const bool xchg = !(phases & PH_BACKWARD) && launch_pending_xchg(stream);
         if (xchg) mark(stream);
-        auto launch_walk = [&](bool after_xchg) -> int {
-            ctcb::WalkArgs wa{dp, w, p->T, stages, p->blank, p->loss, p->loss_sum, nullptr, 0, 1};
+        auto launch_walk = [&](bool after_xchg, bool beside_proj) -> int {
+            ctcb::WalkArgs wa{dp, w, p->T, stages, p->blank, p->loss, p->loss_sum, nullptr, 0, 1, 0};
+            wa.beside_proj = beside_proj ? 1 : 0;
             // several walker CTAs per SM: the producers wait in hardware (no polling instructions)
             wa.hw_wait = opt(OPT_WALK_HW_WAIT) >= 0 ? opt(OPT_WALK_HW_WAIT) : (2 * p->B > 148 ? 1 : 0);
             // the per-group progress is for gradient CTAs that run concurrently with the walkers; a gradient kernel that
@@ -591,10 +609,13 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
             mark(stream);
             return CTCB_OK;
         };
+        // loss evaluation from the encoder output: the recursion kernel is the projection's programmatic dependent and
+        // follows its 128-frame tiles (the utterances' first tiles are scheduled first) instead of waiting for the kernel
+        const bool beside = g_proj && !need_grad && !xchg && !g_prof_events && opt(OPT_PROJ_OVERLAP) != 0;
         if (g_proj) {
-            if (int rc = launch_proj(g_proj, p, dp, w, lay, stream)) return rc;
+            if (int rc = launch_proj(g_proj, p, dp, w, lay, stream, beside)) return rc;
         } else if (!lay.fused) { if (int rc = launch_emit()) return rc; }
-        if (int rc = launch_walk(xchg && lay.fused != 0)) return rc;
+        if (int rc = launch_walk((xchg && lay.fused != 0) || beside, beside)) return rc;
     }
     if (phases & PH_BACKWARD) {
         ctcb::GradArgs ga{dp, w};

@@ -80,6 +80,9 @@ struct Workspace {        // carved out of the caller's workspace by the host (c
     int* gprog;                       // (B, 4) {frame blocks whose history is complete: alpha walker, beta walker;
                                       //   metadata ready (Tb, Lb, flags, rank, dl, nd); pinfo ready}: published with
                                       //   release/gpu scope, polled by the gradient CTAs
+    int* tflag;                       // (B, ntile) fused projection (ctcb_proj.cuh): 1 once the 128-frame tile's rows of `fr` and E are
+                                      //   written -- polled by the recursion kernel when it runs beside the projection
+    int ntile;
     int Lp, W, NB, dense, P, NW;      // PW = 32*P pairs per walker warp
     int stamp;                        // nonzero hash of the call's shape and layout choices: the value of the
                                       //   "metadata ready" progress word, checked by the gradient CTAs (a workspace
@@ -185,6 +188,8 @@ __host__ __device__ inline size_t emit_smem_bytes(int Lp, int staged_V) {
 template <int VEC, int NQ>
 __global__ void __launch_bounds__(NQ < 0 ? 256 : 128) k_emit(Problem p, Workspace w) {
     using V_t = typename VecT<VEC>::type;
+    // (a programmatic dependent -- the fused projection, ctcb_proj.cuh -- needs nothing from this kernel and may start at once)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     extern __shared__ __align__(128) int slab[];  // 2*Lp ints: this utterance's labels, metadata scratch
     __shared__ int s_L, s_rep, s_flags;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -455,7 +460,9 @@ __global__ void __launch_bounds__(NQ < 0 ? 256 : 128) k_emit(Problem p, Workspac
         w.nd[b] = s_nd; dl[s_nd] = make_int2(-1, L);
         if (p.status && flags) atomicOr(p.status + b, flags);   // zeroed by the host before the call; frame CTAs OR their bits in
         if (flags & UTT_INFEASIBLE) p.loss[b] = 0.0f;   // defined behaviour, SURVEY 7.3-6
-        w.gprog[4 * b] = 0; w.gprog[4 * b + 1] = 0; w.gprog[4 * b + 3] = 0; w.gprog[4 * b + 2] = w.stamp;
+        w.gprog[4 * b] = 0; w.gprog[4 * b + 1] = 0; w.gprog[4 * b + 3] = 0;
+        __threadfence();
+        st_release_gpu(w.gprog + 4 * b + 2, w.stamp);      // "metadata ready": a recursion kernel that runs beside this one polls it
     }
 }
 
@@ -591,6 +598,8 @@ struct WalkArgs {
     int hw_wait;           // producers wait on mbarrier.try_wait (hardware suspend) instead of nanosleep polls
     int publish;           // 1: the progress of every group is published promptly (gradient CTAs run concurrently);
                            // 2: lazily (the gradient kernel runs after this one: only the final count matters)
+    int beside_proj;       // unfused variant launched as the programmatic dependent of the fused projection: metadata and
+                           // emission blocks are awaited through Workspace::gprog / tflag instead of the stream order
 };
 
 #ifdef CTCB_TRACE
@@ -765,14 +774,22 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
 
     if (!FUSED && warp == NW) {                 // ---- producer warp (emission table from k_emit, by TMA) ----
         const double* Eb = w.E + (size_t)b * w.NB * W * kEC;
+        int tile_seen = -1;                     // beside the projection: the last 128-frame tile known to be written
         auto issue = [&](int n, int st) {       // block of walker group n into ring stage st
             const int blk = DIR ? NQ - 1 - n : n;
+            if (a.beside_proj && (blk >> 4) != tile_seen) {
+                const int* f = w.tflag + (size_t)b * w.ntile + (blk >> 4);
+                const long long t0 = clock64();     // bounded: a projection that never ran gives garbage, not a hang
+                while (ld_acquire_gpu(f) == 0 && clock64() - t0 < kSpinLimit) __nanosleep(256);
+                asm volatile("fence.proxy.async;" ::: "memory");     // the bulk copy below reads what generic stores wrote
+                tile_seen = blk >> 4;
+            }
             mbar_expect_tx(&full[st], stage_bytes);
             tma_load_1d(smem_raw + (size_t)st * stage_bytes, Eb + (size_t)blk * W * kEC, stage_bytes, &full[st]);
         };
         const int npro = min(NS, NQ);
         if (lane == 0) for (int n = 0; n < npro; ++n) issue(n, n);
-        if (DIR == 0) {                         // sum_t log2(softmax denominator), fixed order
+        if (DIR == 0 && !a.beside_proj) {       // sum_t log2(softmax denominator), fixed order
             double s = 0.0;
             for (int t = lane; t < Tb; t += 32) s += (double)w.fr[(size_t)b * a.T + t].y;
 #pragma unroll
@@ -795,6 +812,16 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
                 if (++st == NS) { st = 0; par ^= 1; }
                 if (HIST && (n + 1 == NQ || !mbar_test(&empty[st], par))) st_release_gpu(gp, n + 1);
             }
+        }
+        if (DIR == 0 && a.beside_proj) {        // every tile has been seen by lane 0: the same sum, now that `fr` is complete
+            __syncwarp();
+            double s = 0.0;
+            for (int t = lane; t < Tb; t += 32) s += (double)__ldcg(&w.fr[(size_t)b * a.T + t].y);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                s += __hiloint2double(__shfl_xor_sync(FULL, __double2hiint(s), o), __shfl_xor_sync(FULL, __double2loint(s), o));
+            }
+            if (lane == 0) { sts_f64(lsum, s); sts_release(lsum + 8, 1); }
         }
         return;
     }
@@ -1090,6 +1117,13 @@ __global__ void __launch_bounds__((NW + (FUSED ? kFusedProducers + 1 : 1)) * 32)
         // the gradient kernel may start as soon as every walker CTA is resident: its CTAs wait per
         // frame block on the progress this kernel publishes (Workspace::gprog)
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        if (a.beside_proj) {                    // the metadata kernel ran before the projection: its word is set, with release
+            if (threadIdx.x == 0) {
+                const long long t0 = clock64();
+                while (ld_acquire_gpu(a.w.gprog + 4 * b + 2) != a.w.stamp && clock64() - t0 < kSpinLimit) __nanosleep(256);
+            }
+            __syncthreads();
+        }
         const int flags = __ldcg(a.w.flags + b), Tb = __ldcg(a.w.Tb + b), Lb = __ldcg(a.w.Lb + b);
         if (flags & UTT_INFEASIBLE) return;
         if (blockIdx.y == 0) walk_dir<P, NW, 0, HIST, false>(a, smem_raw, Tb, Lb, flags);

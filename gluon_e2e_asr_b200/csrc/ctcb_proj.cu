@@ -6,7 +6,7 @@
 namespace ctcb {
 
 cudaError_t launch_proj_emit(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const ProjArgs& a, dim3 grid, size_t smem,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, bool programmatic) {
     // the opt-in shared-memory size is a per-device function attribute: raised when a launch needs more than any before
     static thread_local int done_dev = -1;
     static thread_local size_t done_bytes[4] = {0, 0, 0, 0};
@@ -24,10 +24,19 @@ cudaError_t launch_proj_emit(const CUtensorMap& tmA, const CUtensorMap& tmB, con
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = dim3(kPThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = pair ? 1 : 0;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (pair) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (programmatic) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
     const cudaError_t rc = cudaLaunchKernelEx(&cfg, fn, tmA, tmB, tmC, a);
     if (rc != cudaSuccess) return rc;
     return cudaGetLastError();

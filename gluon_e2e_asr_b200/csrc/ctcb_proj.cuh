@@ -80,8 +80,9 @@ __host__ __device__ inline size_t proj_smem_bytes(int Lmax, int Lp, bool store, 
 
 // (a.ctas == 2: grid.x even, launched as clusters of two CTAs along x)
 // host-side launcher, defined in ctcb_proj.cu (its own translation unit: the kernel below is compiled there only)
+// programmatic: launched with programmatic stream serialization (it starts beside the kernel enqueued before it)
 cudaError_t launch_proj_emit(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const ProjArgs& a, dim3 grid, size_t smem,
-                             cudaStream_t stream);
+                             cudaStream_t stream, bool programmatic);
 
 #ifdef CTCB_PROJ_IMPL
 // ---- tcgen05 / TMA wrappers -------------------------------------------------------------------------------------
@@ -222,7 +223,9 @@ k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const Problem& p = a.p;
     const Workspace& w = a.w;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.y, m0 = blockIdx.x * kPM;
+    // grid (CTAS, B, tiles / CTAS): the utterances' first tiles (pairs) are scheduled before anybody's second -- a recursion
+    // kernel that runs beside this one (its programmatic dependent) can start on the first frames of every utterance
+    const int b = blockIdx.y, mt = (int)blockIdx.z * CTAS + (int)blockIdx.x, m0 = mt * kPM;
 
     // the metadata kernel behind this one in the stream is its programmatic dependent: it needs nothing from here and
     // runs in this kernel's shadow (its small CTAs fit beside a resident projection CTA)
@@ -235,7 +238,7 @@ k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         Tb = (int)t64;
     }
     // a tile of padded frames: nothing of it is ever read (a pair leaves together: its second CTA stages half of B)
-    if ((CTAS == 2 ? (int)(blockIdx.x & ~1u) * kPM : m0) >= Tb) return;
+    if ((CTAS == 2 ? (int)blockIdx.z * 2 * kPM : m0) >= Tb) return;
     constexpr int kPStages = proj_stages(CTAS);
     constexpr uint32_t kBytesB = kPBytesB / CTAS;
     const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
@@ -507,6 +510,10 @@ k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (floored && p.status) atomicOr(p.status + b, UTT_WIDE_LOGITS);
         }
         if (a.store == 1 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tiles are read before the CTA exits
+        // this tile's rows of `fr` and E are written: tell a recursion kernel that runs beside this one
+        __threadfence();
+        bar_sync_epilogue();
+        if (etid == 0) st_release_gpu(w.tflag + (size_t)b * w.ntile + mt, 1);
     }
     tc_fence_before();
     if (CTAS == 2) cluster_sync_all(); else __syncthreads();      // a pair: nobody leaves while its peer may still signal it
