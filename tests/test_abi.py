@@ -64,6 +64,33 @@ def test_problem_struct_layout_matches_header(lib):
                    P.status.offset, P.logits_row_offsets.offset]
 
 
+def test_proj_struct_layout_matches_header(lib):
+    """ctypes mirror of ctcb_proj_t (the output projection in front of the loss)."""
+    import subprocess
+    import tempfile
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "ctcb.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n",' \
+          'sizeof(ctcb_proj_t), offsetof(ctcb_proj_t, hidden_stride_b), offsetof(ctcb_proj_t, K),' \
+          'offsetof(ctcb_proj_t, weight), offsetof(ctcb_proj_t, bias), offsetof(ctcb_proj_t, operand_dtype));return 0;}'
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "l.c")
+        with open(c, "w") as f:
+            f.write(src)
+        exe = os.path.join(td, "l")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, c])
+        got = [int(x) for x in subprocess.check_output([exe]).split()]
+    P = lib.Proj
+    assert got == [ctypes.sizeof(P), P.hidden_stride_b.offset, P.K.offset, P.weight.offset, P.bias.offset, P.operand_dtype.offset]
+
+
+def test_proj_entry_validation_without_gpu(lib):
+    """ctcb_proj_forward refuses NULL arguments before it touches a device."""
+    l = lib.load()
+    p = lib.Problem()
+    assert l.ctcb_proj_forward(None, ctypes.byref(p), 0, None, 0, None) == lib.CTCB_INVALID_VALUE
+    assert b"proj" in l.ctcb_last_error()
+    assert l.ctcb_proj_loss_grad(None, ctypes.byref(p), None, 0, None) == lib.CTCB_INVALID_VALUE
+
+
 def test_workspace_bytes(lib):
     a = lib.workspace_bytes(500, 32, 46, 120, True)
     b = lib.workspace_bytes(500, 32, 46, 120, False)
