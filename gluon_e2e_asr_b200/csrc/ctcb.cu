@@ -60,9 +60,9 @@ thread_local int g_prof_count = 0;
 // Read from the environment ONCE (CTCB_<NAME>, at first use) and changeable through ctcb_set_option (tests, A/B
 // runs): nothing on the per-call host path calls getenv.  -1 = automatic.
 enum Opt { OPT_WALK_P, OPT_WALK_NW, OPT_WALK_STAGES, OPT_OVERLAP, OPT_FUSED, OPT_WALK_PER_SM, OPT_EMIT_STAGED,
-           OPT_GRAD_STAGED, OPT_MEET, OPT_GRAD2, OPT_GRAD2_BLOCKS, OPT_WALK_HW_WAIT, OPT_GRAD2_OCC, OPT_PROJ_CTAS, OPT_PROJ_DBG, OPT_PROJ_OVERLAP, OPT_COUNT };
+           OPT_GRAD_STAGED, OPT_MEET, OPT_GRAD2, OPT_GRAD2_BLOCKS, OPT_WALK_HW_WAIT, OPT_GRAD2_OCC, OPT_PROJ_CTAS, OPT_PROJ_DBG, OPT_PROJ_OVERLAP, OPT_MEET_FWD, OPT_COUNT };
 const char* const kOptNames[OPT_COUNT] = {"walk_p", "walk_nw", "walk_stages", "overlap", "fused", "walk_per_sm",
-                                          "emit_staged", "grad_staged", "meet", "grad2", "grad2_blocks", "walk_hw_wait", "grad2_occ", "proj_ctas", "proj_dbg", "proj_overlap"};
+                                          "emit_staged", "grad_staged", "meet", "grad2", "grad2_blocks", "walk_hw_wait", "grad2_occ", "proj_ctas", "proj_dbg", "proj_overlap", "meet_fwd"};
 struct Options {
     int v[OPT_COUNT];
     Options() {
@@ -180,7 +180,7 @@ cudaError_t ensure_dynamic_smem(const void* fn, size_t bytes) {
 }
 
 struct Layout {
-    size_t off_Tb, off_Lb, off_flags, off_lab, off_rank, off_dl, off_nd, off_fr, off_E, off_hA, off_hB, off_oA, off_oB, off_gprog, off_runv, off_pinfo, off_tflag, total;
+    size_t off_Tb, off_Lb, off_flags, off_lab, off_rank, off_dl, off_nd, off_fr, off_E, off_hA, off_hB, off_oA, off_oB, off_gprog, off_runv, off_pinfo, off_tflag, off_meet, off_meetlz, off_meetcnt, total;
     int ntile;
     int Lp, W, NB, dense, fused, P, NW;
     int stamp;               // nonzero hash of everything the workspace layout depends on (Workspace::stamp)
@@ -223,6 +223,9 @@ Layout make_layout(int T, int B, int V, int Lmax, int need_grad) {
     l.off_pinfo = take(sizeof(int2) * (size_t)B);
     l.ntile = (T + 127) / 128 + 1;                // 128-frame tiles of the fused projection (+1: an odd count is paired up)
     l.off_tflag = take(sizeof(int) * (size_t)B * l.ntile);
+    l.off_meet = take(sizeof(ctcb::MeetSlot) * (size_t)B * 2 * pairs);      // loss evaluation: walkers that meet in the middle
+    l.off_meetlz = take(sizeof(double) * 2 * (size_t)B);
+    l.off_meetcnt = take(sizeof(int) * (size_t)B);
     l.off_fr = take(sizeof(float2) * (size_t)B * T);
     l.off_E = take(l.fused ? 0 : sizeof(double) * (size_t)B * l.NB * l.W * ctcb::kEC);
     if (need_grad) {
@@ -258,6 +261,9 @@ ctcb::Workspace carve(const Layout& l, void* ws) {
     w.runv = reinterpret_cast<int2*>(base + l.off_runv);
     w.pinfo = reinterpret_cast<int2*>(base + l.off_pinfo);
     w.tflag = reinterpret_cast<int*>(base + l.off_tflag); w.ntile = l.ntile;
+    w.meet = reinterpret_cast<ctcb::MeetSlot*>(base + l.off_meet);
+    w.meetlz = reinterpret_cast<double*>(base + l.off_meetlz);
+    w.meetcnt = reinterpret_cast<int*>(base + l.off_meetcnt);
     w.Lp = l.Lp; w.W = l.W; w.NB = l.NB; w.dense = l.dense; w.P = l.P; w.NW = l.NW;
     w.fused = l.fused;
     w.stamp = l.stamp;
@@ -385,7 +391,7 @@ EncodeTiledFn encode_tiled() {
 // beside: the recursion kernel will be launched as the projection's programmatic dependent and follow its tiles (loss
 // evaluation only): the metadata kernel then goes FIRST (the walkers poll its "ready" word) and the projection starts beside it
 int launch_proj(const ctcb_proj_t* pj, const ctcb_problem_t* p, const ctcb::Problem& dp, const ctcb::Workspace& w,
-                const Layout& lay, cudaStream_t stream, bool beside) {
+                const Layout& lay, cudaStream_t stream, bool beside, bool outside_in) {
     if (!pj->hidden || !pj->weight || pj->K <= 0) return fail(CTCB_INVALID_VALUE, "projection: hidden / weight is NULL or K <= 0");
     if (lay.fused || lay.dense)
         return fail(CTCB_UNSUPPORTED, "projection fused with the loss needs V > 64 and V > Lmax + 1 (V=%d, Lmax=%d)", p->V, p->Lmax);
@@ -431,6 +437,7 @@ int launch_proj(const ctcb_proj_t* pj, const ctcb_problem_t* p, const ctcb::Prob
     pa.K = pj->K; pa.NT = (p->V + ctcb::kPN - 1) / ctcb::kPN; pa.KB = (pj->K + 128 / esz - 1) / (128 / esz);
     pa.bf16 = bf ? 1 : 0;
     pa.ctas = ctas;
+    pa.outside_in = outside_in ? 1 : 0;
     pa.dbg = opt(OPT_PROJ_DBG) > 0 ? opt(OPT_PROJ_DBG) : 0;
     pa.vec4 = (p->V % 4 == 0 && reinterpret_cast<uintptr_t>(pj->bias) % 16 == 0) ? 1 : 0;
     // the logits (kept for the gradient kernel) leave through TMA stores when their rows allow a tensor map
@@ -590,9 +597,20 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
         // (With a gradient kernel in the call the exchange goes behind that one instead, see below.)
         const bool xchg = !(phases & PH_BACKWARD) && launch_pending_xchg(stream);
         if (xchg) mark(stream);
+        // loss evaluation from the encoder output: the recursion kernel is the projection's programmatic dependent and
+        // follows its 128-frame tiles (the utterances' first tiles are scheduled first) instead of waiting for the kernel
+        const bool beside = g_proj && !need_grad && !xchg && !g_prof_events && opt(OPT_PROJ_OVERLAP) != 0;
+        // loss evaluation (no history): the alpha and the beta walker take half of the frames each and meet in the middle --
+        // while every walker CTA of the batch can be resident at once (beyond that one walker per utterance does less work:
+        // cfg5, B = 1024: 136 us against 153).  Beside the projection kernel one walker per utterance is the better schedule
+        // (the walkers share the few SMs the projection leaves free: 163 us against 168 with twice as many walker CTAs,
+        // even with the tiles computed from both ends inwards) unless the option asks for both.
+        const bool meet_fwd = !need_grad && (opt(OPT_MEET_FWD) >= 0 ? opt(OPT_MEET_FWD) != 0 : (p->B <= 148 && !beside));
+        if (meet_fwd) CUDA_TRY(cudaMemsetAsync(w.meetcnt, 0, sizeof(int) * (size_t)p->B, stream));
         auto launch_walk = [&](bool after_xchg, bool beside_proj) -> int {
-            ctcb::WalkArgs wa{dp, w, p->T, stages, p->blank, p->loss, p->loss_sum, nullptr, 0, 1, 0};
+            ctcb::WalkArgs wa{dp, w, p->T, stages, p->blank, p->loss, p->loss_sum, nullptr, 0, 1, 0, 0};
             wa.beside_proj = beside_proj ? 1 : 0;
+            wa.meet = meet_fwd ? 1 : 0;
             // several walker CTAs per SM: the producers wait in hardware (no polling instructions)
             wa.hw_wait = opt(OPT_WALK_HW_WAIT) >= 0 ? opt(OPT_WALK_HW_WAIT) : (2 * p->B > 148 ? 1 : 0);
             // the per-group progress is for gradient CTAs that run concurrently with the walkers; a gradient kernel that
@@ -600,7 +618,7 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
             wa.publish = ((phases & PH_BACKWARD) && !g_prof_events && overlap_allowed(p->B, lay.fused != 0)) ? 1 : 2;
             const int wthreads = (we->NW + (lay.fused ? ctcb::kFusedProducers + 1 : 1)) * 32;
             cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3(p->B, need_grad ? 2 : 1); cfg.blockDim = dim3(wthreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+            cfg.gridDim = dim3(p->B, (need_grad || meet_fwd) ? 2 : 1); cfg.blockDim = dim3(wthreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -609,11 +627,8 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
             mark(stream);
             return CTCB_OK;
         };
-        // loss evaluation from the encoder output: the recursion kernel is the projection's programmatic dependent and
-        // follows its 128-frame tiles (the utterances' first tiles are scheduled first) instead of waiting for the kernel
-        const bool beside = g_proj && !need_grad && !xchg && !g_prof_events && opt(OPT_PROJ_OVERLAP) != 0;
         if (g_proj) {
-            if (int rc = launch_proj(g_proj, p, dp, w, lay, stream, beside)) return rc;
+            if (int rc = launch_proj(g_proj, p, dp, w, lay, stream, beside, beside && meet_fwd)) return rc;
         } else if (!lay.fused) { if (int rc = launch_emit()) return rc; }
         if (int rc = launch_walk((xchg && lay.fused != 0) || beside, beside)) return rc;
     }

@@ -58,6 +58,10 @@ struct Problem {          // device view of ctcb_problem_t
     float* loss; double* loss_sum; int* status;
 };
 
+// loss evaluation with walkers that meet in the middle (WalkArgs::meet): what a walker hands over at the meeting frame --
+// per state pair the mantissas in [1,2) (0 for an exact zero) and the full exponents of its blank / label state
+struct MeetSlot { double vb, vl; int ob, ol; };
+
 struct Workspace {        // carved out of the caller's workspace by the host (ctcb.cu)
     int* Tb; int* Lb; int* flags;     // (B,)
     int* lab;                         // (B, Lp) int32 labels
@@ -80,6 +84,9 @@ struct Workspace {        // carved out of the caller's workspace by the host (c
     int* gprog;                       // (B, 4) {frame blocks whose history is complete: alpha walker, beta walker;
                                       //   metadata ready (Tb, Lb, flags, rank, dl, nd); pinfo ready}: published with
                                       //   release/gpu scope, polled by the gradient CTAs
+    MeetSlot* meet;                   // (B, 2, NW*PW) meeting-frame states of the alpha / beta walker (loss evaluation, WalkArgs::meet)
+    double* meetlz;                   // (B, 2) each side's sum of log2(softmax denominator) over its frames
+    int* meetcnt;                     // (B,) walker warps that have handed over (zeroed by the host before the launch)
     int* tflag;                       // (B, ntile) fused projection (ctcb_proj.cuh): 1 once the 128-frame tile's rows of `fr` and E are
                                       //   written -- polled by the recursion kernel when it runs beside the projection
     int ntile;
@@ -598,6 +605,9 @@ struct WalkArgs {
     int hw_wait;           // producers wait on mbarrier.try_wait (hardware suspend) instead of nanosleep polls
     int publish;           // 1: the progress of every group is published promptly (gradient CTAs run concurrently);
                            // 2: lazily (the gradient kernel runs after this one: only the final count matters)
+    int meet;              // loss evaluation only (no history): the alpha walker takes the first half of the frame blocks, the
+                           // beta walker the second half from the end, and P(l|x) = sum_s alpha_m(s) beta'_m(s) is formed
+                           // at the meeting frame by whichever warp hands over last -- half the dependent chain
     int beside_proj;       // unfused variant launched as the programmatic dependent of the fused projection: metadata and
                            // emission blocks are awaited through Workspace::gprog / tflag instead of the stream order
 };
@@ -632,6 +642,11 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
     const int W = w.W, NS = a.stages;
     const int NQ = (Tb + kG - 1) / kG;              // frame blocks of this utterance
     const int rlast = Tb - (NQ - 1) * kG;           // frames in the last block, 1..8
+    // meeting in the middle (loss evaluation): alpha walks blocks [0, Mblk), beta blocks [Mblk, NQ) from the end
+    const bool meet = !HIST && a.meet && NQ >= 2;
+    const int Mblk = (NQ + 1) / 2;
+    const int NQr = meet ? (DIR ? NQ - Mblk : Mblk) : NQ;      // groups this walker runs
+    if (!HIST && DIR == 1 && !meet) return;         // an utterance too short to split: the alpha CTA does it all
     const uint32_t stage_bytes = (uint32_t)W * kEC * 8u;
 
     const uint32_t ring = smem_u32(smem_raw);
@@ -679,10 +694,10 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
         double ls = 0.0;
         bool floored = false;
         int n = q;
-        if (n < NQ) load_blk(n, cur);
+        if (n < NQr) load_blk(n, cur);
 #pragma unroll 1
-        for (; n < NQ; n += kFusedProducers) {
-            if (n + kFusedProducers < NQ) load_blk(n + kFusedProducers, nxt);
+        for (; n < NQr; n += kFusedProducers) {
+            if (n + kFusedProducers < NQr) load_blk(n + kFusedProducers, nxt);
             const int t = (DIR ? NQ - 1 - n : n) * kG + fj;
             const bool valid = t < Tb;
             float mx = cur[0];
@@ -696,14 +711,14 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
                 e[i] = valid ? fast_ex2((cur[i] - mx) * kLog2e) : 0.0f;
                 sm += e[i];
                 // an emission below the floor (any symbol of a valid frame): reported, UTT_WIDE_LOGITS
-                if (DIR == 0) floored |= valid && i < cpl && col0 + i < V && e[i] < kMinProb;
+                if (DIR == 0 || meet) floored |= valid && i < cpl && col0 + i < V && e[i] < kMinProb;
             }
             sm += __shfl_xor_sync(FULL, sm, 1);
             sm += __shfl_xor_sync(FULL, sm, 2);
-            if (DIR == 0 && valid && qk == 0) {
+            if ((DIR == 0 || meet) && valid && qk == 0) {
                 const float l2 = log2f(sm);
                 ls += (double)l2;
-                w.fr[(size_t)b * a.T + t] = make_float2(mx, l2);
+                if (DIR == 0) w.fr[(size_t)b * a.T + t] = make_float2(mx, l2);
             }
             const int st = n % NS, use = n / NS;
             if (use > 0) mbar_wait_relaxed(&empty[st], (uint32_t)((use - 1) & 1), a.hw_wait);
@@ -711,13 +726,13 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
 #pragma unroll
             for (int i = 0; i < CPL; ++i)
                 if (i < cpl && col0 + i < V) sts_f64(dst + (uint32_t)i * (kEC * 8u), valid ? (double)fmaxf(e[i], kMinProb) : 0.0);
-            if (DIR == 0 && qk == 0) sts_f64(lsum + 16 + (q * 8 + fj) * 8, ls);   // before the arrive: the walkers' acquire covers it
+            if ((DIR == 0 || meet) && qk == 0) sts_f64(lsum + 16 + (q * 8 + fj) * 8, ls);   // before the arrive: the walkers' acquire covers it
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[st]);
 #pragma unroll
             for (int i = 0; i < CPL; ++i) cur[i] = nxt[i];
         }
-        if (DIR == 0 && p.status && __any_sync(FULL, floored) && lane == 0) atomicOr(p.status + b, UTT_WIDE_LOGITS);
+        if ((DIR == 0 || meet) && p.status && __any_sync(FULL, floored) && lane == 0) atomicOr(p.status + b, UTT_WIDE_LOGITS);
         return;
     }
     if (FUSED && warp == NW + kFusedProducers) {
@@ -787,11 +802,13 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
             mbar_expect_tx(&full[st], stage_bytes);
             tma_load_1d(smem_raw + (size_t)st * stage_bytes, Eb + (size_t)blk * W * kEC, stage_bytes, &full[st]);
         };
-        const int npro = min(NS, NQ);
+        const int npro = min(NS, NQr);
         if (lane == 0) for (int n = 0; n < npro; ++n) issue(n, n);
-        if (DIR == 0 && !a.beside_proj) {       // sum_t log2(softmax denominator), fixed order
+        // this walker's frames: all of them, or its side of the meeting frame
+        const int t_lo = (meet && DIR) ? Mblk * kG : 0, t_hi = (meet && !DIR) ? min(Tb, Mblk * kG) : Tb;
+        if ((DIR == 0 || meet) && !a.beside_proj) {       // sum_t log2(softmax denominator), fixed order
             double s = 0.0;
-            for (int t = lane; t < Tb; t += 32) s += (double)w.fr[(size_t)b * a.T + t].y;
+            for (int t = t_lo + lane; t < t_hi; t += 32) s += (double)w.fr[(size_t)b * a.T + t].y;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 s += __hiloint2double(__shfl_xor_sync(FULL, __double2hiint(s), o), __shfl_xor_sync(FULL, __double2loint(s), o));
@@ -806,17 +823,17 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
             // on its own: the fence of a release at gpu scope costs about one group.
             int* gp = HIST ? w.gprog + 4 * b + DIR : nullptr;
             int st = 0; uint32_t par = 0;
-            for (int n = 0; n < NQ; ++n) {
+            for (int n = 0; n < NQr; ++n) {
                 mbar_wait_relaxed(&empty[st], par, a.hw_wait);
-                if (n + NS < NQ) issue(n + NS, st);
+                if (n + NS < NQr) issue(n + NS, st);
                 if (++st == NS) { st = 0; par ^= 1; }
-                if (HIST && (n + 1 == NQ || !mbar_test(&empty[st], par))) st_release_gpu(gp, n + 1);
+                if (HIST && (n + 1 == NQr || !mbar_test(&empty[st], par))) st_release_gpu(gp, n + 1);
             }
         }
-        if (DIR == 0 && a.beside_proj) {        // every tile has been seen by lane 0: the same sum, now that `fr` is complete
+        if ((DIR == 0 || meet) && a.beside_proj) {   // every tile of this side has been seen by lane 0: the same sum, `fr` is complete
             __syncwarp();
             double s = 0.0;
-            for (int t = lane; t < Tb; t += 32) s += (double)__ldcg(&w.fr[(size_t)b * a.T + t].y);
+            for (int t = t_lo + lane; t < t_hi; t += 32) s += (double)__ldcg(&w.fr[(size_t)b * a.T + t].y);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 s += __hiloint2double(__shfl_xor_sync(FULL, __double2hiint(s), o), __shfl_xor_sync(FULL, __double2loint(s), o));
@@ -871,7 +888,7 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
     int st = 0, ph = 0;
     uint32_t stage_base = ring;
 #pragma unroll 1
-    for (int n = 0; n < NQ; ++n) {
+    for (int n = 0; n < NQr; ++n) {
         const int blk = DIR ? NQ - 1 - n : n;
         const int ns = blk == NQ - 1 ? rlast : kG;
         const uint32_t par = (uint32_t)(n & (kHaloDepth - 1));
@@ -1085,7 +1102,78 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
         if (HIST) { hch += DIR ? -kHistStep : kHistStep; och += DIR ? -kOffStep : kOffStep; }
     }
 
-    if (DIR == 0) {
+    if (meet) {
+        // ---- hand over at the meeting frame m = 8 Mblk - 1: alpha_m (this walker's state) resp. beta'_m (the
+        // reversed walker's sums BEFORE frame m's emission: one more transition-only step); mantissa + full exponent ----
+        MeetSlot* mine = w.meet + ((size_t)b * 2 + DIR) * (NW * PW) + g0;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            double vb = bm[p], vl = lm[p];
+            if (DIR) {
+                const double prev = p == 0 ? pm : lm[p - 1];
+                const double t0 = fma(bm[p], flb[p], lm[p]);
+                vb = fma(prev, fb[p], bm[p]);
+                vl = fma(prev, fls[p], t0);
+            }
+            MeetSlot ms;
+            ms.ob = vb != 0.0 ? eb[p] + dexp(vb) : kZeroE; ms.vb = vb != 0.0 ? dmant(vb) : 0.0;
+            ms.ol = vl != 0.0 ? el[p] + dexp(vl) : kZeroE; ms.vl = vl != 0.0 ? dmant(vl) : 0.0;
+            mine[p] = ms;
+        }
+        if (tid == 0) {                             // this side's sum of the frames' log2 normalisers
+            double lz = 0.0;
+            if (FUSED) {
+#pragma unroll
+                for (int q = 0; q < kFusedProducers * 8; ++q) lz += lds_f64(lsum + 16 + q * 8);
+            } else {
+                while (lds_acquire(lsum + 8) == 0) { }
+                lz = lds_f64(lsum);
+            }
+            w.meetlz[2 * b + DIR] = lz;
+        }
+        __threadfence();
+        __syncwarp();
+        int old = 0;
+        if (lane == 0) old = atomicAdd(w.meetcnt + b, 1);
+        old = __shfl_sync(FULL, old, 0);
+        if (old == 2 * NW - 1) {
+            // the last warp of the utterance's two CTAs: P(l|x) = sum_g alpha_b(g) beta'_b(L-g) + sum_g alpha_l(g) beta'_l(L-1-g)
+            // (the reversed walker's pair g holds the original lattice's blank L-g and label L-1-g)
+            __threadfence();
+            const MeetSlot* A = w.meet + (size_t)b * 2 * (NW * PW);
+            const MeetSlot* Bq = A + NW * PW;
+            int emax = 2 * kZeroE;
+#pragma unroll 4                                    // four iterations' loads in flight: the slots come from L2
+            for (int g = lane; g <= Lb; g += 32) {
+                const int eA = __ldcg(&A[g].ob), eB = __ldcg(&Bq[Lb - g].ob);
+                if (eA > kZeroE && eB > kZeroE) emax = max(emax, eA + eB);
+                if (g < Lb) {
+                    const int fA = __ldcg(&A[g].ol), fB = __ldcg(&Bq[Lb - 1 - g].ol);
+                    if (fA > kZeroE && fB > kZeroE) emax = max(emax, fA + fB);
+                }
+            }
+            emax = __reduce_max_sync(FULL, emax);
+            double sum = 0.0;
+#pragma unroll 4
+            for (int g = lane; g <= Lb; g += 32) {
+                const int eA = __ldcg(&A[g].ob), eB = __ldcg(&Bq[Lb - g].ob);
+                if (eA > kZeroE && eB > kZeroE) sum += __ldcg(&A[g].vb) * __ldcg(&Bq[Lb - g].vb) * pow2c(eA + eB - emax);
+                if (g < Lb) {
+                    const int fA = __ldcg(&A[g].ol), fB = __ldcg(&Bq[Lb - 1 - g].ol);
+                    if (fA > kZeroE && fB > kZeroE) sum += __ldcg(&A[g].vl) * __ldcg(&Bq[Lb - 1 - g].vl) * pow2c(fA + fB - emax);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+                sum += __hiloint2double(__shfl_xor_sync(FULL, __double2hiint(sum), o), __shfl_xor_sync(FULL, __double2loint(sum), o));
+            if (lane == 0) {
+                const double lz = __ldcg(w.meetlz + 2 * b) + __ldcg(w.meetlz + 2 * b + 1);
+                const double nll = -kLn2 * ((double)emax + log2(sum) - lz);
+                a.loss[b] = (float)nll;
+                if (a.loss_sum) atomicAdd(a.loss_sum, nll);
+            }
+        }
+    } else if (DIR == 0) {
         // P(l|x) = alpha_{T-1}(2L) + alpha_{T-1}(2L-1) = the blank sum of slot L_b at a
         // virtual step T_b (pm already holds the neighbour's state after step T_b-1).
 #pragma unroll
