@@ -1,6 +1,7 @@
-"""k_proj_emit alone (CUDA events around ctcb_proj_forward minus nothing else is not possible from Python, so: the forward
-call with the walkers' time measured separately is not needed here) -- times the fused forward call for the option sets
-given on the command line, e.g.  python scripts/proj_kernel_time.py proj_ctas=1 proj_ctas=2 proj_ctas=2,proj_dbg=1"""
+"""Times the fused forward call (proj_ctc_loss under no_grad: projection kernel + metadata + walkers) at cfg3 + H = 512 for
+option sets given on the command line, e.g.
+    python scripts/proj_kernel_time.py proj_ctas=1 proj_ctas=2 proj_ctas=2,proj_dbg=1 keep=1,proj_dbg=6 meet_fwd=1,proj_overlap=0
+(keep=1: forward with the logits kept for a backward).  CUDA events, 20 calls; one JSON line."""
 import sys, os, json
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
