@@ -37,6 +37,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "ctcb_kernels.cuh"
 
 namespace ctcb {
@@ -401,69 +403,73 @@ k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             uint32_t v[2][32];
             if (a.dbg & 1) { tc_fence_before(); if (CTAS == 2) mbar_arrive_leader(tempty + as); else mbar_arrive(tempty + as); continue; }
             if (cbase < p.V) tmem_ld32(trow, v[0]);
+            // one chunk of 32 columns; FULLC: every column lies below V (no bounds checks: all but the vocabulary's last chunks)
+            auto chunk = [&](auto full_tag, const int c, const int col0) {
+                constexpr bool FULLC = decltype(full_tag)::value;
+                tmem_ld_wait();
+                // the next chunk's accumulators travel while this one is reduced
+                if (c + 1 < HC / 32 && col0 + 32 < p.V) tmem_ld32(trow + (c + 1) * 32, v[(c + 1) & 1]);
+                float x[32];
+                if (a.vec4) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const bool in = FULLC || col0 + i < p.V;                // V % 4 == 0: whole groups
+                        const float4 bb = (in && a.bias) ? __ldg(reinterpret_cast<const float4*>(a.bias + col0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        x[i] = in ? __uint_as_float(v[c & 1][i]) + bb.x : -INFINITY;
+                        x[i + 1] = in ? __uint_as_float(v[c & 1][i + 1]) + bb.y : -INFINITY;
+                        x[i + 2] = in ? __uint_as_float(v[c & 1][i + 2]) + bb.z : -INFINITY;
+                        x[i + 3] = in ? __uint_as_float(v[c & 1][i + 3]) + bb.w : -INFINITY;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const bool in = FULLC || col0 + i < p.V;
+                        x[i] = in ? __uint_as_float(v[c & 1][i]) + (a.bias ? __ldg(a.bias + col0 + i) : 0.0f) : -INFINITY;
+                    }
+                }
+                if (a.store == 1 && !(a.dbg & 2)) {
+                    // 32 frames x 32 columns through a swizzled staging tile: row = lane, 16-byte chunk i at (i ^ row % 8)
+                    const uint32_t tile = sbuf + (uint32_t)(nstored & 1) * kPStageTile;
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that read this tile two chunks ago
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
+                                     ::"r"(tile + (uint32_t)lane * 128u + (uint32_t)((i ^ (lane & 7)) << 4)),
+                                       "f"(x[4 * i]), "f"(x[4 * i + 1]), "f"(x[4 * i + 2]), "f"(x[4 * i + 3]) : "memory");
+                    if (!(a.dbg & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) tma_store_3d(&tmC, tile, col0, m0 + q * 32, b);
+                    ++nstored;
+                } else if (lrow) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (FULLC || col0 + i < p.V) lrow[col0 + i] = x[i];
+                }
+                float cm[4] = {x[0], x[1], x[2], x[3]};
+#pragma unroll
+                for (int i = 4; i < 32; i += 4) {
+                    cm[0] = fmaxf(cm[0], x[i]); cm[1] = fmaxf(cm[1], x[i + 1]);
+                    cm[2] = fmaxf(cm[2], x[i + 2]); cm[3] = fmaxf(cm[3], x[i + 3]);
+                }
+                const float cmx = fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3]));
+                if (cmx > mx) { sum *= fast_ex2((mx - cmx) * kLog2e); mx = cmx; }     // first chunk: mx = -inf -> sum (0) * 0
+                const float ms = mx * kLog2e;
+                float sp[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    sp[0] += fast_ex2(fmaf(x[i], kLog2e, -ms));
+                    sp[1] += fast_ex2(fmaf(x[i + 1], kLog2e, -ms));
+                    sp[2] += fast_ex2(fmaf(x[i + 2], kLog2e, -ms));
+                    sp[3] += fast_ex2(fmaf(x[i + 3], kLog2e, -ms));
+                }
+                sum += (sp[0] + sp[1]) + (sp[2] + sp[3]);
+            };
 #pragma unroll
             for (int c = 0; c < HC / 32; ++c) {
                 const int col0 = cbase + c * 32;
-                if (col0 < p.V) {                      // warp-uniform
-                    tmem_ld_wait();
-                    // the next chunk's accumulators travel while this one is reduced
-                    if (c + 1 < HC / 32 && col0 + 32 < p.V) tmem_ld32(trow + (c + 1) * 32, v[(c + 1) & 1]);
-                    float x[32];
-                    if (a.vec4) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            const bool in = col0 + i < p.V;                         // V % 4 == 0: whole groups
-                            const float4 bb = (in && a.bias) ? __ldg(reinterpret_cast<const float4*>(a.bias + col0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            x[i] = in ? __uint_as_float(v[c & 1][i]) + bb.x : -INFINITY;
-                            x[i + 1] = in ? __uint_as_float(v[c & 1][i + 1]) + bb.y : -INFINITY;
-                            x[i + 2] = in ? __uint_as_float(v[c & 1][i + 2]) + bb.z : -INFINITY;
-                            x[i + 3] = in ? __uint_as_float(v[c & 1][i + 3]) + bb.w : -INFINITY;
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const bool in = col0 + i < p.V;
-                            x[i] = in ? __uint_as_float(v[c & 1][i]) + (a.bias ? __ldg(a.bias + col0 + i) : 0.0f) : -INFINITY;
-                        }
-                    }
-                    if (a.store == 1 && !(a.dbg & 2)) {
-                        // 32 frames x 32 columns through a swizzled staging tile: row = lane, 16-byte chunk i at (i ^ row % 8)
-                        const uint32_t tile = sbuf + (uint32_t)(nstored & 1) * kPStageTile;
-                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that read this tile two chunks ago
-                        __syncwarp();
-#pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
-                                         ::"r"(tile + (uint32_t)lane * 128u + (uint32_t)((i ^ (lane & 7)) << 4)),
-                                           "f"(x[4 * i]), "f"(x[4 * i + 1]), "f"(x[4 * i + 2]), "f"(x[4 * i + 3]) : "memory");
-                        if (!(a.dbg & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        __syncwarp();
-                        if (lane == 0) tma_store_3d(&tmC, tile, col0, m0 + q * 32, b);
-                        ++nstored;
-                    } else if (lrow) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (col0 + i < p.V) lrow[col0 + i] = x[i];
-                    }
-                    float cm[4] = {x[0], x[1], x[2], x[3]};
-#pragma unroll
-                    for (int i = 4; i < 32; i += 4) {
-                        cm[0] = fmaxf(cm[0], x[i]); cm[1] = fmaxf(cm[1], x[i + 1]);
-                        cm[2] = fmaxf(cm[2], x[i + 2]); cm[3] = fmaxf(cm[3], x[i + 3]);
-                    }
-                    const float cmx = fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3]));
-                    if (cmx > mx) { sum *= fast_ex2((mx - cmx) * kLog2e); mx = cmx; }     // first chunk: mx = -inf -> sum (0) * 0
-                    const float ms = mx * kLog2e;
-                    float sp[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        sp[0] += fast_ex2(fmaf(x[i], kLog2e, -ms));
-                        sp[1] += fast_ex2(fmaf(x[i + 1], kLog2e, -ms));
-                        sp[2] += fast_ex2(fmaf(x[i + 2], kLog2e, -ms));
-                        sp[3] += fast_ex2(fmaf(x[i + 3], kLog2e, -ms));
-                    }
-                    sum += (sp[0] + sp[1]) + (sp[2] + sp[3]);
-                }
+                if (col0 + 32 <= p.V) chunk(std::true_type{}, c, col0);          // warp-uniform
+                else if (col0 < p.V) chunk(std::false_type{}, c, col0);
             }
             // the utterance's own columns in this half tile (blank, l_1..l_L): column index uniform over the warp
             for (int k = hstart[hsel * a.NT + n]; k < hstart[hsel * a.NT + n + 1]; ++k) {
