@@ -270,3 +270,11 @@ def test_cfg3_shape_and_unsupported_shapes(dev):
     assert e.value.code == _lib.CTCB_UNSUPPORTED
     with pytest.raises(RuntimeError):
         proj_ctc_loss(torch.tensor(h2), torch.tensor(w2), None, torch.tensor(d2["label"]))
+
+
+def test_random_shapes_against_the_logits_path(dev):
+    """scripts/proj_stress.py: random (B, T, K, V, L), ragged / zero / infeasible lengths, both operand types, with and without
+    a gradient (the walkers beside the projection kernel, resp. the logits store), against the logits path on the exact
+    product.  A protocol error between the kernels would show up here as a timeout or a wrong loss."""
+    from scripts.proj_stress import run
+    assert run(60, seed=5) < 2e-4
