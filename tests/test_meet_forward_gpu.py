@@ -76,3 +76,25 @@ def test_repeatable_bits(dev):
     a = _gpu_loss(dev, d, 1)
     for _ in range(3):
         np.testing.assert_array_equal(_gpu_loss(dev, d, 1), a)
+
+
+def test_random_shapes_both_schedules_agree(dev):
+    """80 random problems (both walker variants, one to eight walker warps, ragged / zero / infeasible lengths): the loss of
+    the meeting walkers against the loss of the single alpha walker -- two different evaluations of the same lattice."""
+    from gluon_e2e_asr_b200 import _lib
+    from gluon_e2e_asr_b200.ops import ctc_loss
+    rng = np.random.Generator(np.random.PCG64(77))
+    for c in range(80):
+        B = int(rng.integers(1, 24)); T = int(rng.integers(1, 400)); V = int(rng.integers(2, 300))
+        L = int(rng.integers(0, min(T, 250) + 1))
+        Tb = rng.integers(0, T + 1, B); Lb = rng.integers(0, L + 1, B)
+        lab = rng.integers(1, V, (B, max(L, 1)))[:, :L].astype(np.float32) if L else np.zeros((B, 0), np.float32)
+        x = torch.tensor((rng.standard_normal((T, B, V)) * rng.choice([1.0, 4.0])).astype(np.float32), device=dev)
+        args = (x, torch.tensor(lab, device=dev), torch.tensor(Tb.astype(np.float32), device=dev),
+                torch.tensor(Lb.astype(np.float32), device=dev), True, True)
+        with torch.no_grad():
+            with _lib.options(meet_fwd=1):
+                a = ctc_loss(*args).cpu().numpy()
+            with _lib.options(meet_fwd=0):
+                b = ctc_loss(*args).cpu().numpy()
+        np.testing.assert_allclose(a, b, rtol=2e-5, atol=1e-5, err_msg="case %d: B=%d T=%d V=%d L=%d" % (c, B, T, V, L))
