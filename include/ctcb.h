@@ -258,8 +258,11 @@ int ctcb_last_grad_kernel(void);
  * kernel concurrent with the recursion kernel: 0/1), "fused" (0: always the k_emit path), "walk_per_sm",
  * "emit_staged", "grad_staged" (0: register variants for wide vocabularies), "grad2" (0/1: the gradient kernel
  * that normalises by P(l|x); automatic = from 64 utterances on), "grad2_blocks" (frame blocks per CTA of that
- * kernel), "meet" (1: the experimental one-kernel path of ctcb_meet.cuh).  walk_p / walk_nw / fused
- * are part of the workspace layout: do not change them between ctcb_forward and ctcb_backward. */
+ * kernel), "meet" (1: the experimental one-kernel path of ctcb_meet.cuh), "meet_fwd" (loss evaluation without a
+ * gradient: the alpha and the beta walker take half of the frames each and meet in the middle; automatic = while the
+ * batch's walker CTAs are resident together), "proj_ctas" (fused projection: 2 = CTA pairs, 1 = single CTAs),
+ * "proj_overlap" (0: the walkers run after the projection kernel instead of beside it), "proj_dbg" (measurement only).
+ * walk_p / walk_nw / fused are part of the workspace layout: do not change them between ctcb_forward and ctcb_backward. */
 int ctcb_set_option(const char* name, int32_t value);
 int ctcb_get_option(const char* name, int32_t* value);
 
