@@ -417,8 +417,24 @@ def run_cuda(args, rank, world, local_rank):
     # Start gate: after the host barrier every rank enqueues one un-timed all-reduce on the timed stream and records
     # its start event right behind it -- the collective ends on all ranks together, so the timed regions start together
     # on the DEVICES whatever the skew between the host processes.
+    # One rank: the step's launch mechanism is chosen by an un-timed calibration -- per-step CUDA graphs, or eager launches,
+    # where the recursion kernel of step i+1 is the programmatic dependent of step i's gradient kernel (its CTAs become
+    # resident during that kernel's tail and wait there: option walk_pdl), which a chain of separate graph launches cannot have.
+    use_graph, calib = True, None
+    if world == 1:
+        def quick(g_):
+            run_steps(3, g_)
+            torch.cuda.synchronize()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record(stream)
+            run_steps(30, g_)
+            q1.record(stream)
+            torch.cuda.synchronize()
+            return q0.elapsed_time(q1) / 30
+        calib = {"graph_ms_per_step": quick(True), "eager_ms_per_step": quick(False)}
+        use_graph = calib["graph_ms_per_step"] <= calib["eager_ms_per_step"]
     barrier()
-    run_steps(args.warmup)
+    run_steps(args.warmup, use_graph)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.start()
@@ -426,7 +442,7 @@ def run_cuda(args, rank, world, local_rank):
         if world > 1:
             dist.all_reduce(gate)
         e0.record(stream)
-    run_steps(args.steps)
+    run_steps(args.steps, use_graph)
     e1.record(stream)
     sampler.sample()
     torch.cuda.synchronize()
@@ -726,7 +742,11 @@ def run_cuda(args, rank, world, local_rank):
                 "utterances_per_sec": Bg / (ms_per_step * 1e-3),
                 "l2": "inputs rotate over %d buffer sets (%.0f MB logits+grad per rank > 126 MB L2)" % (nset, nset * per_set / 1e6),
                 "launch": "%d kernels per step (k_grad a programmatic dependent of k_walk when the walkers fit the GPU at once) "
-                          "replayed from a CUDA graph; eager_ms_per_step=%.4f (no exchange)" % (launches_per_step, eager_ms),
+                          "%s; eager_ms_per_step=%.4f (no exchange)%s" %
+                          (launches_per_step, "replayed from a CUDA graph" if use_graph else
+                           "launched eagerly (step i+1's recursion kernel is the programmatic dependent of step i's gradient kernel)",
+                           eager_ms, "; un-timed calibration over 30 steps: graph %.4f / eager %.4f ms per step" %
+                           (calib["graph_ms_per_step"], calib["eager_ms_per_step"]) if calib else ""),
                 "walker": {"pairs_per_lane": walk_cfg[0], "warps": walk_cfg[1]},
                 "start_gate": "host barrier, then one un-timed all-reduce on the timed stream right before the start event" if world > 1 else "none (one rank)",
                 "collective": ("none" if not exchange else

@@ -608,6 +608,9 @@ struct WalkArgs {
     int meet;              // loss evaluation only (no history): the alpha walker takes the first half of the frame blocks, the
                            // beta walker the second half from the end, and P(l|x) = sum_s alpha_m(s) beta'_m(s) is formed
                            // at the meeting frame by whichever warp hands over last -- half the dependent chain
+    int pdl_wait;          // launched with programmatic stream serialization behind an arbitrary kernel (the previous step's
+                           // gradient kernel, a model's last kernel): the CTAs become resident during that kernel's tail
+                           // and execute griddepcontrol.wait before they touch memory
     int beside_proj;       // unfused variant launched as the programmatic dependent of the fused projection: metadata and
                            // emission blocks are awaited through Workspace::gprog / tflag instead of the stream order
 };
@@ -1200,6 +1203,7 @@ __device__ __forceinline__ void walk_dir(const WalkArgs& a, unsigned char* smem_
 template <int P, int NW, bool HIST, bool FUSED>
 __global__ void __launch_bounds__((NW + (FUSED ? kFusedProducers + 1 : 1)) * 32) k_walk(WalkArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    if (a.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");   // everything enqueued before this kernel is complete and visible
     const int b = blockIdx.x;
     if (!FUSED) {
         // the gradient kernel may start as soon as every walker CTA is resident: its CTAs wait per
