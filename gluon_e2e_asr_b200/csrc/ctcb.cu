@@ -391,7 +391,7 @@ EncodeTiledFn encode_tiled() {
 // beside: the recursion kernel will be launched as the projection's programmatic dependent and follow its tiles (loss
 // evaluation only): the metadata kernel then goes FIRST (the walkers poll its "ready" word) and the projection starts beside it
 int launch_proj(const ctcb_proj_t* pj, const ctcb_problem_t* p, const ctcb::Problem& dp, const ctcb::Workspace& w,
-                const Layout& lay, cudaStream_t stream, bool beside, bool outside_in) {
+                const Layout& lay, cudaStream_t stream, bool beside) {
     if (!pj->hidden || !pj->weight || pj->K <= 0) return fail(CTCB_INVALID_VALUE, "projection: hidden / weight is NULL or K <= 0");
     if (lay.fused || lay.dense)
         return fail(CTCB_UNSUPPORTED, "projection fused with the loss needs V > 64 and V > Lmax + 1 (V=%d, Lmax=%d)", p->V, p->Lmax);
@@ -437,7 +437,6 @@ int launch_proj(const ctcb_proj_t* pj, const ctcb_problem_t* p, const ctcb::Prob
     pa.K = pj->K; pa.NT = (p->V + ctcb::kPN - 1) / ctcb::kPN; pa.KB = (pj->K + 128 / esz - 1) / (128 / esz);
     pa.bf16 = bf ? 1 : 0;
     pa.ctas = ctas;
-    pa.outside_in = outside_in ? 1 : 0;
     pa.dbg = opt(OPT_PROJ_DBG) > 0 ? opt(OPT_PROJ_DBG) : 0;
     pa.vec4 = (p->V % 4 == 0 && reinterpret_cast<uintptr_t>(pj->bias) % 16 == 0) ? 1 : 0;
     // the logits (kept for the gradient kernel) leave through TMA stores when their rows allow a tensor map
@@ -604,7 +603,7 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
         // while every walker CTA of the batch can be resident at once (beyond that one walker per utterance does less work:
         // cfg5, B = 1024: 136 us against 153).  Beside the projection kernel one walker per utterance is the better schedule
         // (the walkers share the few SMs the projection leaves free: 163 us against 168 with twice as many walker CTAs,
-        // even with the tiles computed from both ends inwards) unless the option asks for both.
+        // also when the tiles were computed from both ends inwards -- that tile order was measured and removed).
         const bool meet_fwd = !need_grad && (opt(OPT_MEET_FWD) >= 0 ? opt(OPT_MEET_FWD) != 0 : (p->B <= 148 && !beside));
         if (meet_fwd) CUDA_TRY(cudaMemsetAsync(w.meetcnt, 0, sizeof(int) * (size_t)p->B, stream));
         auto launch_walk = [&](bool after_xchg, bool beside_proj) -> int {
@@ -632,7 +631,7 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
             return CTCB_OK;
         };
         if (g_proj) {
-            if (int rc = launch_proj(g_proj, p, dp, w, lay, stream, beside, beside && meet_fwd)) return rc;
+            if (int rc = launch_proj(g_proj, p, dp, w, lay, stream, beside)) return rc;
         } else if (!lay.fused) { if (int rc = launch_emit()) return rc; }
         if (int rc = launch_walk((xchg && lay.fused != 0) || beside, beside)) return rc;
     }

@@ -64,8 +64,6 @@ struct ProjArgs {
     int smem_stash;          // the label columns are parked in shared memory (store == 0 and they fit), else in E
     int ctas;                // 1: one CTA per tile; 2: CTA pairs (tcgen05 cta_group::2) over 256 frames
     int bf16;                // operands are bfloat16 (64 values per 128-byte K block, kind::f16) instead of fp32 (32, kind::tf32)
-    int outside_in;          // tiles of an utterance are scheduled first, last, second, second to last, ...: the walkers beside
-                             // this kernel meet in the middle (WalkArgs::meet) and consume the frames from both ends
     int dbg;                 // measurement only (option proj_dbg): 1 = the epilogue skips its arithmetic (results are garbage)
 };
 
@@ -229,8 +227,7 @@ k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // grid (CTAS, B, tiles / CTAS): the utterances' first tiles (pairs) are scheduled before anybody's second -- a recursion
     // kernel that runs beside this one (its programmatic dependent) can start on the first frames of every utterance
-    const int b = blockIdx.y;
-    int mt = (int)blockIdx.z * CTAS + (int)blockIdx.x;
+    const int b = blockIdx.y, mt = (int)blockIdx.z * CTAS + (int)blockIdx.x, m0 = mt * kPM;
 
     // the metadata kernel behind this one in the stream is its programmatic dependent: it needs nothing from here and
     // runs in this kernel's shadow (its small CTAs fit beside a resident projection CTA)
@@ -243,14 +240,7 @@ k_proj_emit(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         Tb = (int)t64;
     }
     // a tile of padded frames: nothing of it is ever read (a pair leaves together: its second CTA stages half of B)
-    if (a.outside_in) {
-        // position q in the order 0, nt-1, 1, nt-2, ... of this utterance's nt tiles; positions beyond nt are padding tiles
-        // (index w.ntile - 1: beyond T, zero-filled by TMA, nothing written) that only keep a CTA pair complete
-        const int nt = (Tb + kPM - 1) / kPM, q = mt;
-        if ((CTAS == 2 ? (int)blockIdx.z * 2 : q) >= nt) return;
-        mt = q >= nt ? w.ntile - 1 : ((q & 1) ? nt - 1 - (q >> 1) : (q >> 1));
-    } else if ((CTAS == 2 ? (int)blockIdx.z * 2 * kPM : mt * kPM) >= Tb) return;
-    const int m0 = mt * kPM;
+    if ((CTAS == 2 ? (int)blockIdx.z * 2 * kPM : m0) >= Tb) return;
     constexpr int kPStages = proj_stages(CTAS);
     constexpr uint32_t kBytesB = kPBytesB / CTAS;
     const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
