@@ -1458,7 +1458,24 @@ __global__ void __launch_bounds__(XQ < 0 ? 256 : 128, XQ < 0 ? (CH == 16 ? 2 : 3
     // Both waits are bounded: a workspace that no matching forward call filled (another shape, other layout
     // switches, a forward that failed) makes this CTA write NaN into its rows and leave instead of hanging the GPU.
     __shared__ int s_ok;
-    if (tid == 0) {
+    constexpr bool STAGED = XQ < 0;
+    // Staged rows are the wide-vocabulary path: never the fused one, so everything k_emit wrote is complete before this grid
+    // exists.  The stamp, the lengths, the flags, the distinct-label table and the rank order are then requested together --
+    // one memory round trip instead of four dependent ones (the kernel's CTAs are short, under load a round trip is microseconds)
+    int Tb_e = 0, Lb_e = 0, fl_e = 0, nd_e = 0, rk_e[NCH];
+    extern __shared__ __align__(128) unsigned char gsm_all[];
+    if (STAGED) {
+        const int st = __ldcg(w.gprog + 4 * b + 2);
+        Tb_e = __ldcg(w.Tb + b); Lb_e = __ldcg(w.Lb + b); fl_e = __ldcg(w.flags + b); nd_e = __ldcg(w.nd + b);
+        const int* rank_e = w.rank + (size_t)b * w.Lp;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) rk_e[c] = __ldcg(rank_e + min(c * 32 + lane, w.Lp - 1));
+        int2* s_dl_e = reinterpret_cast<int2*>(reinterpret_cast<float*>(gsm_all + grad_staged_bytes(p.V)) +
+                                               (size_t)4 * kGradFramesPerWarp * grad_row_floats(w.Lp, 32 * CH));
+        const int2* dl = w.dl + (size_t)b * (w.Lp + 1);
+        for (int j = tid; j <= w.Lp; j += NT) s_dl_e[j] = __ldcg(dl + j);
+        if (tid == 0) s_ok = st == w.stamp;
+    } else if (tid == 0) {
         const long long t0 = clock64();
         int v;
         while ((v = ld_acquire_gpu(w.gprog + 4 * b + 2)) == 0 && clock64() - t0 < kSpinLimit) __nanosleep(256);
@@ -1475,8 +1492,8 @@ __global__ void __launch_bounds__(XQ < 0 ? 256 : 128, XQ < 0 ? (CH == 16 ? 2 : 3
         }
         return;
     }
-    const int Tb = __ldcg(w.Tb + b), Lb = __ldcg(w.Lb + b);
-    const bool infeasible = (__ldcg(w.flags + b) & UTT_INFEASIBLE) != 0;
+    const int Tb = STAGED ? Tb_e : __ldcg(w.Tb + b), Lb = STAGED ? Lb_e : __ldcg(w.Lb + b);
+    const bool infeasible = ((STAGED ? fl_e : __ldcg(w.flags + b)) & UTT_INFEASIBLE) != 0;
     // CTAs are dispatched utterance-fastest, and per utterance in the order the walkers complete
     // the frame blocks: the two walkers meet in the middle, so from the middle outwards
     const int NQ = infeasible ? 0 : (Tb + kG - 1) / kG;
@@ -1486,8 +1503,6 @@ __global__ void __launch_bounds__(XQ < 0 ? 256 : 128, XQ < 0 ? (CH == 16 ? 2 : 3
     const int t_first = blk * kG;
     const bool cta_live = blk < NQ;
     const int GW = grad_row_floats(w.Lp, 32 * CH);
-    constexpr bool STAGED = XQ < 0;
-    extern __shared__ __align__(128) unsigned char gsm_all[];
     unsigned char* gsm_raw = gsm_all + (STAGED ? grad_staged_bytes(p.V) : 0);
     float* srow = reinterpret_cast<float*>(gsm_all);                                         // kG rows of V floats
     uint64_t* rbar = reinterpret_cast<uint64_t*>(gsm_all + (size_t)kG * p.V * 4);            // one barrier per row
@@ -1510,12 +1525,15 @@ __global__ void __launch_bounds__(XQ < 0 ? 256 : 128, XQ < 0 ? (CH == 16 ? 2 : 3
     const int* rank = w.rank + (size_t)b * w.Lp;
     int nd = 0;
     if (cta_live) {
-        nd = __ldcg(w.nd + b);
-        const int2* dl = w.dl + (size_t)b * (w.Lp + 1);
-        for (int j = tid; j <= nd; j += NT) s_dl[j] = __ldcg(dl + j);
+        if (STAGED) nd = nd_e;
+        else {
+            nd = __ldcg(w.nd + b);
+            const int2* dl = w.dl + (size_t)b * (w.Lp + 1);
+            for (int j = tid; j <= nd; j += NT) s_dl[j] = __ldcg(dl + j);
+        }
+        // block n is frame block n of the alpha walker and block NQ-1-n of the beta walker
+        const int* gp = w.gprog + 4 * b;
         if (tid == 0) {
-            // block n is frame block n of the alpha walker and block NQ-1-n of the beta walker
-            const int* gp = w.gprog + 4 * b;
             const long long t0 = clock64();
             while (ld_acquire_gpu(gp) < blk + 1 && clock64() - t0 < kSpinLimit) __nanosleep(256);
             while (ld_acquire_gpu(gp + 1) < NQ - blk && clock64() - t0 < kSpinLimit) __nanosleep(256);
@@ -1549,7 +1567,45 @@ __global__ void __launch_bounds__(XQ < 0 ? 256 : 128, XQ < 0 ? (CH == 16 ? 2 : 3
     // (clamped) history indices, the combined offsets -- kNoState for pairs beyond the lattice,
     // whose history is never masked by the walkers -- and the slot of the label state in rank order.
     int ibb[NCH], ibl[NCH], ofb[NCH], ofl[NCH], rk[NCH];
-    if (CH > 0 && cta_live) {
+    int2 pha[NCH]; int phbb[NCH], phbl[NCH];
+    if (STAGED && CH > 0 && cta_live) {
+        // staged rows, one frame per warp: the warp's history loads go first, then the block's offsets -- ONCE per CTA, through
+        // shared memory (the occupancy rows' space, not yet in use), instead of three gathers per chunk in each of the 8 warps
+        // whose arrival the history loads had to wait for
+        const int tq = t_first + warp;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const int g = c * 32 + lane;
+            ibb[c] = max(Lb - g, 0); ibl[c] = max(Lb - 1 - g, 0);
+            pha[c] = make_int2(0, 0); phbb[c] = 0; phbl[c] = 0;
+        }
+        if (tq < Tb) {
+            const int2* A = hA0 + (size_t)(tq - t_first) * pairs + lane;
+            const int2* Bh = hB0 + (size_t)(tq - t_first) * pairs;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                pha[c] = __ldcg(A + c * 32);
+                phbb[c] = __ldcg(&Bh[ibb[c]].x);
+                phbl[c] = __ldcg(&Bh[ibl[c]].y);
+            }
+        }
+        int2* s_off = reinterpret_cast<int2*>(gsm_raw);          // [0, 32 CH): alpha walker's offsets, [32 CH, 64 CH): beta walker's
+        for (int g = tid; g < 32 * NCH; g += NT) {
+            s_off[g] = g < pairs ? __ldcg(oA + g) : make_int2(0, 0);
+            s_off[32 * NCH + g] = g < pairs ? __ldcg(oB + g) : make_int2(0, 0);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const int g = c * 32 + lane;
+            const int2 oa = s_off[g];
+            const int ob = s_off[32 * NCH + ibb[c]].x, ol = s_off[32 * NCH + ibl[c]].y;
+            ofb[c] = g <= Lb ? oa.x + ob : kNoState;
+            ofl[c] = g < Lb ? oa.y + ol : kNoState;
+            rk[c] = g < Lb ? rk_e[c] : g;
+        }
+        __syncthreads();                                          // the occupancy rows may be written from here on
+    } else if (CH > 0 && cta_live) {
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const int g = c * 32 + lane;
@@ -1558,7 +1614,7 @@ __global__ void __launch_bounds__(XQ < 0 ? 256 : 128, XQ < 0 ? (CH == 16 ? 2 : 3
             const int ob = __ldcg(&oB[ibb[c]].x), ol = __ldcg(&oB[ibl[c]].y);
             ofb[c] = g <= Lb ? oa.x + ob : kNoState;
             ofl[c] = g < Lb ? oa.y + ol : kNoState;
-            rk[c] = g < Lb ? __ldcg(rank + g) : g;
+            rk[c] = g < Lb ? (STAGED ? rk_e[c] : __ldcg(rank + g)) : g;
         }
     }
     const int nvec = p.V / VEC;
@@ -1587,6 +1643,7 @@ __global__ void __launch_bounds__(XQ < 0 ? 256 : 128, XQ < 0 ? (CH == 16 ? 2 : 3
                     const int2* Bh = hB0 + (size_t)(tt[f] - t_first) * pairs;
 #pragma unroll
                     for (int c = 0; c < NCH; ++c) {
+                        if (STAGED) { ha[f][c] = pha[c]; hbb[f][c] = phbb[c]; hbl[f][c] = phbl[c]; continue; }
                         ha[f][c] = __ldcg(A + c * 32);
                         hbb[f][c] = __ldcg(&Bh[ibb[c]].x);
                         hbl[f][c] = __ldcg(&Bh[ibl[c]].y);
