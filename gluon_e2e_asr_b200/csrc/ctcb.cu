@@ -60,9 +60,9 @@ thread_local int g_prof_count = 0;
 // Read from the environment ONCE (CTCB_<NAME>, at first use) and changeable through ctcb_set_option (tests, A/B
 // runs): nothing on the per-call host path calls getenv.  -1 = automatic.
 enum Opt { OPT_WALK_P, OPT_WALK_NW, OPT_WALK_STAGES, OPT_OVERLAP, OPT_FUSED, OPT_WALK_PER_SM, OPT_EMIT_STAGED,
-           OPT_GRAD_STAGED, OPT_MEET, OPT_GRAD2, OPT_GRAD2_BLOCKS, OPT_WALK_HW_WAIT, OPT_GRAD2_OCC, OPT_PROJ_CTAS, OPT_PROJ_DBG, OPT_PROJ_OVERLAP, OPT_MEET_FWD, OPT_WALK_PDL, OPT_COUNT };
+           OPT_GRAD_STAGED, OPT_MEET, OPT_GRAD2, OPT_GRAD2_BLOCKS, OPT_WALK_HW_WAIT, OPT_GRAD2_OCC, OPT_PROJ_CTAS, OPT_PROJ_DBG, OPT_PROJ_OVERLAP, OPT_MEET_FWD, OPT_WALK_PDL, OPT_GRAD_POLL_NS, OPT_COUNT };
 const char* const kOptNames[OPT_COUNT] = {"walk_p", "walk_nw", "walk_stages", "overlap", "fused", "walk_per_sm",
-                                          "emit_staged", "grad_staged", "meet", "grad2", "grad2_blocks", "walk_hw_wait", "grad2_occ", "proj_ctas", "proj_dbg", "proj_overlap", "meet_fwd", "walk_pdl"};
+                                          "emit_staged", "grad_staged", "meet", "grad2", "grad2_blocks", "walk_hw_wait", "grad2_occ", "proj_ctas", "proj_dbg", "proj_overlap", "meet_fwd", "walk_pdl", "grad_poll_ns"};
 struct Options {
     int v[OPT_COUNT];
     Options() {
@@ -504,6 +504,7 @@ int enqueue(const ctcb_problem_t* p, void* workspace, size_t workspace_bytes, vo
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const ctcb::Problem dp = to_device_problem(p);
     ctcb::Workspace w = carve(lay, workspace);
+    w.poll_ns = opt(OPT_GRAD_POLL_NS);
 
     // ---- the one-kernel path (ctcb_meet.cuh): forward and gradient of small-vocabulary utterances in one CTA each ----
     if (phases == (PH_FORWARD | PH_BACKWARD) && lay.fused && p->V <= 64 && p->Lmax + 1 <= 128 && meet_wanted(p->B)) {

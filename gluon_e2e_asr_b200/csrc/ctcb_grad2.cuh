@@ -67,8 +67,9 @@ __global__ void __launch_bounds__(128, CH <= 4 ? (OCC ? 6 : 7) : (CH == 8 ? 4 : 
         int ok = 1;
         if (lane == 0) {
             const long long t0 = clock64();
-            while (ld_acquire_gpu(gp) < blk + 1 && clock64() - t0 < kSpinLimit) __nanosleep(128);
-            while (ld_acquire_gpu(gp + 1) < NQ - blk && clock64() - t0 < kSpinLimit) __nanosleep(128);
+            const unsigned pns = w.poll_ns > 0 ? (unsigned)w.poll_ns : 128u;
+            while (ld_acquire_gpu(gp) < blk + 1 && clock64() - t0 < kSpinLimit) __nanosleep(pns);
+            while (ld_acquire_gpu(gp + 1) < NQ - blk && clock64() - t0 < kSpinLimit) __nanosleep(pns);
             ok = clock64() - t0 < kSpinLimit;
         }
         return __shfl_sync(FULL, ok, 0) != 0;

@@ -91,6 +91,7 @@ struct Workspace {        // carved out of the caller's workspace by the host (c
                                       //   written -- polled by the recursion kernel when it runs beside the projection
     int ntile;
     int Lp, W, NB, dense, P, NW;      // PW = 32*P pairs per walker warp
+    int poll_ns;                      // back-off of the gradient CTAs' polls of the walkers' progress words (<= 0: the kernels' defaults)
     int stamp;                        // nonzero hash of the call's shape and layout choices: the value of the
                                       //   "metadata ready" progress word, checked by the gradient CTAs (a workspace
                                       //   that no matching forward call filled is an error, not a hang)
@@ -1535,8 +1536,11 @@ __global__ void __launch_bounds__(XQ < 0 ? 256 : 128, XQ < 0 ? (CH == 16 ? 2 : 3
         const int* gp = w.gprog + 4 * b;
         if (tid == 0) {
             const long long t0 = clock64();
-            while (ld_acquire_gpu(gp) < blk + 1 && clock64() - t0 < kSpinLimit) __nanosleep(256);
-            while (ld_acquire_gpu(gp + 1) < NQ - blk && clock64() - t0 < kSpinLimit) __nanosleep(256);
+            // back-off between polls: the pollers' traffic is not free for the walkers (profiles/r4r_poll_sweep.log: on the
+            // wide-vocabulary path, whose gradient CTAs share the walkers' SMs, 64 ns costs 11 us per cfg3 step, 1024 ns saves 3)
+            const unsigned pns = w.poll_ns > 0 ? (unsigned)w.poll_ns : (STAGED ? 1024u : 256u);
+            while (ld_acquire_gpu(gp) < blk + 1 && clock64() - t0 < kSpinLimit) __nanosleep(pns);
+            while (ld_acquire_gpu(gp + 1) < NQ - blk && clock64() - t0 < kSpinLimit) __nanosleep(pns);
             if (clock64() - t0 >= kSpinLimit) s_ok = 0;
         }
     }

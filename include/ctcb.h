@@ -262,7 +262,9 @@ int ctcb_last_grad_kernel(void);
  * gradient: the alpha and the beta walker take half of the frames each and meet in the middle; automatic = while the
  * batch's walker CTAs are resident together), "proj_ctas" (fused projection: 2 = CTA pairs, 1 = single CTAs),
  * "proj_overlap" (0: the walkers run after the projection kernel instead of beside it), "proj_dbg" (measurement only),
- * "walk_pdl" (0: the recursion kernel is an ordinary launch instead of a programmatic one that waits on entry).
+ * "walk_pdl" (0: the recursion kernel is an ordinary launch instead of a programmatic one that waits on entry),
+ * "grad_poll_ns" (back-off, in ns, between a gradient CTA's polls of the walkers' progress words; automatic = 128 / 256,
+ * 1024 on the wide-vocabulary path).
  * walk_p / walk_nw / fused are part of the workspace layout: do not change them between ctcb_forward and ctcb_backward. */
 int ctcb_set_option(const char* name, int32_t value);
 int ctcb_get_option(const char* name, int32_t* value);
