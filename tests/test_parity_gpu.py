@@ -949,3 +949,36 @@ def test_grad2_forward_backward_split_and_edge_cases(dev):
     assert l[1] == 0 and l[3] == 0 and not g[1].any() and not g[3].any()
     feas = [b for b in range(64) if b not in (1, 3)]
     _check(l[feas], g[feas], lo[feas], go[feas], "k_grad2 split")
+
+
+def test_random_wide_vocabulary_problems_vs_c_oracle(dev):
+    """Randomised wide-vocabulary problems (rows staged by bulk copies: k_emit, k_walk, the staged k_grad in every
+    chunk variant, L from 0 to 200): ragged, empty and infeasible utterances, head gradients -- the fused call and
+    the forward / backward split against the fp64 C oracle, status bits against its feasibility."""
+    from gluon_e2e_asr_b200 import CtcLoss, ctc_loss_and_grad
+    rng = np.random.default_rng(20261019)
+    for case in range(36):
+        B = int(rng.integers(1, 9)); T = int(rng.integers(1, 70)); V = int(rng.choice([516, 640, 1000, 2000, 3000]))
+        L = int(rng.choice([0, 1, 5, 31, 32, 33, 64, 100, 129, 200]))
+        lab = rng.integers(1, V, (B, max(L, 1))).astype(np.float32)
+        if L > 3:
+            lab[0, 1] = lab[0, 0]; lab[0, 3] = lab[0, 2]                  # repeated labels
+        Lb = rng.integers(0, L + 1, B).astype(np.float32)
+        Tb = rng.integers(0, T + 1, B).astype(np.float32)                # empty and infeasible utterances included
+        Tb[int(rng.integers(0, B))] = T
+        x = (rng.standard_normal((B, T, V)) * float(rng.choice([0.5, 2.0, 5.0]))).astype(np.float32)
+        head = rng.uniform(0.25, 2.0, B)
+        d = dict(pred=x, label=lab, pred_lengths=Tb, label_lengths=Lb)
+        lo, go, ok = _c_oracle(d, head=head)
+        t = _to(dev, d)
+        status = torch.zeros((B,), dtype=torch.int32, device=dev)
+        loss, grad = ctc_loss_and_grad(t["pred"], t["label"], t["pred_lengths"], t["label_lengths"],
+                                       head_grad=torch.tensor(head, device=dev, dtype=torch.float32), status=status)
+        name = "case %d B%d T%d V%d L%d" % (case, B, T, V, L)
+        _check(loss.cpu().numpy(), grad.cpu().numpy(), lo, go, name)
+        np.testing.assert_array_equal((status.cpu().numpy() & 1) == 0, ok, err_msg=name)
+        if case % 3 == 0:                                                # the autograd split: k_grad on its own
+            pred = t["pred"].clone().requires_grad_(True)
+            l2 = CtcLoss(layout="NTC", label_layout="NT")(pred, t["label"], t["pred_lengths"], t["label_lengths"])
+            (l2 * torch.tensor(head, device=dev, dtype=torch.float32)).sum().backward()
+            _check(l2.detach().cpu().numpy(), pred.grad.cpu().numpy(), lo, go, name + " (split)")
