@@ -6,7 +6,8 @@ import torch
 from tests.synth import make_batch
 from gluon_e2e_asr_b200 import ops, greedy_decode, edit_distance
 dev = torch.device("cuda:0")
-for (B, T, V, L) in ((4, 60, 46, 12), (3, 40, 200, 10), (2, 100, 46, 70)):
+# small vocabulary (fused path), V = 200 (k_emit, register rows), V = 600 / 2000 (rows staged by bulk copies, chunk variants 1 and 8)
+for (B, T, V, L) in ((4, 60, 46, 12), (3, 40, 200, 10), (2, 100, 46, 70), (3, 30, 600, 9), (2, 24, 2000, 150)):
     d = make_batch(B, T, V, L, seed=1)
     t = {k: torch.tensor(v, device=dev) for k, v in d.items()}
     loss, grad = ops.ctc_loss_and_grad(t["pred"], t["label"], t["pred_lengths"], t["label_lengths"])
