@@ -441,6 +441,12 @@ def run_cuda(args, rank, world, local_rank):
     with torch.cuda.stream(stream):
         if world > 1:
             dist.all_reduce(gate)
+        elif args.start_gate_us > 0:
+            # one rank: a hold kernel ahead of the start event -- the host queues the event and the first steps behind it, so
+            # the clock starts with work already in the stream (what the all-reduce gate does at N > 1).  Without it the K
+            # timed steps carry the host's launch latency of the first one: a fixed cost of about one and a half steps that a
+            # 20-step region shows (49.6 us per step) and a 2000-step region does not (46.0)
+            torch.cuda._sleep(int(args.start_gate_us * 1e-6 * 1.9e9))       # cycles at ~1.9 GHz
         e0.record(stream)
     run_steps(args.steps, use_graph)
     e1.record(stream)
@@ -748,7 +754,7 @@ def run_cuda(args, rank, world, local_rank):
                            eager_ms, "; un-timed calibration over 30 steps: graph %.4f / eager %.4f ms per step" %
                            (calib["graph_ms_per_step"], calib["eager_ms_per_step"]) if calib else ""),
                 "walker": {"pairs_per_lane": walk_cfg[0], "warps": walk_cfg[1]},
-                "start_gate": "host barrier, then one un-timed all-reduce on the timed stream right before the start event" if world > 1 else "none (one rank)",
+                "start_gate": "host barrier, then one un-timed all-reduce on the timed stream right before the start event" if world > 1 else ("a %.0f us hold kernel ahead of the start event: the first steps are queued behind it when the clock starts" % args.start_gate_us if args.start_gate_us > 0 else "none (one rank)"),
                 "collective": ("none" if not exchange else
                                "none on the data path; float64 loss-sum exchange of the previous step's sum inside each step's CUDA graph: " +
                                ("ctcb_mailbox_exchange_with_next: a one-warp kernel stores the partial sums into every rank's mailbox over "
@@ -884,6 +890,8 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(CONFIGS),
                     help="default: cfg2 on one GPU (BASELINE configs[1]); cfg5 split by utterance on N > 1 (configs[4])")
     ap.add_argument("--pipe-depth", type=int, default=3, help="batches in flight in the prefetching host entry (e2e)")
+    ap.add_argument("--start-gate-us", type=float, default=300.0,
+                    help="one rank: length of the hold kernel ahead of the start event (0 = none)")
     ap.add_argument("--no-others", action="store_true", help="skip the context measurements of the other configs")
     ap.add_argument("--dense-host", action="store_true", help="e2e: dense (B,T,V) host batches instead of the packed arena")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
